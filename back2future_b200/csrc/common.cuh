@@ -1,0 +1,70 @@
+// Shared host/device helpers for libb2f_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/b2f.h"
+
+namespace b2f {
+
+// ---- thread-local error text, launch counter, debug switches (api.cu) -----------------
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);          // sets the message, returns status
+int cuda_fail(cudaError_t e, const char* where);     // positive cudaError_t + message
+void count_launch(int n = 1);
+int costvol_path();   // 0 auto, 1 generic, 2/3/4 force the tiled kernels (fwd strip width 16/8/4)
+
+#define B2F_CUDA_TRY(expr)                                              \
+  do {                                                                  \
+    cudaError_t e__ = (expr);                                           \
+    if (e__ != cudaSuccess) return ::b2f::cuda_fail(e__, #expr);        \
+  } while (0)
+
+// After a kernel launch: catch launch-configuration errors without synchronising.
+#define B2F_CHECK_LAUNCH(name)                                          \
+  do {                                                                  \
+    cudaError_t e__ = cudaGetLastError();                               \
+    if (e__ != cudaSuccess) return ::b2f::cuda_fail(e__, name);         \
+    ::b2f::count_launch();                                              \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+inline int num_sms() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) cached_sms = n;
+    cached_dev = dev;
+  }
+  return cached_sms;
+}
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Penalty functions of criterions/penalty/*.lua.  eps2 is eps^2 of the Lorentzian.
+template <int KIND>
+__device__ __forceinline__ float pen_apply(float x, float eps2) {
+  if (KIND == B2F_PENALTY_QUADRATIC) return x * x;
+  if (KIND == B2F_PENALTY_L1) return sqrtf(x * x + 1e-6f);
+  return logf(1.f + 0.5f * ((x * x) / eps2));
+}
+template <int KIND>
+__device__ __forceinline__ float pen_der(float x, float eps2) {
+  if (KIND == B2F_PENALTY_QUADRATIC) return 2.f * x;
+  if (KIND == B2F_PENALTY_L1) return x / sqrtf(x * x + 1e-6f);
+  return (2.f * x) / (x * x + 2.f * eps2);
+}
+
+}  // namespace b2f

@@ -1,0 +1,586 @@
+// nn.CostVolMulti forward / backward for sm_100a.
+//
+// Semantics (models/CostVolMulti.lua:49-181): for F input maps, window win (odd),
+// n = (win-1)/2, s = +1 (fwd) / -1, channel i = (qx+n)*win + (qy+n)  [x-major]:
+//   out[b,i,y,x]       = 1/(C(F-1)) sum_{f=1..F-1} sum_c ref[b,c,y,x] * frame_f[b,c,y-s f qy,x-s f qx]
+//   gradRef[b,c,y,x]   = 1/(C(F-1)) sum_f sum_i go[b,i,y,x]           * frame_f[b,c,y-dy,x-dx]
+//   gradFrame_f[b,c,p] = 1/(C(F-1))       sum_i go[b,i,p+d]           * ref[b,c,p+d]
+// Out-of-range sources are dropped, the normaliser is constant (also at borders).
+//
+// Two implementations:
+//   * tiled TMA kernels for the model's configuration (F = 2, win = 9, W % 4 == 0): feature tiles
+//     plus the +-4 halo are staged into shared memory by TMA (out-of-bounds box elements read as
+//     zero = "dropped terms"), fp32 FFMA register tiles, no atomics anywhere: the backward is a
+//     gather per output element over the 81 displacements (displacement-major slabs of gradOut).
+//   * generic direct kernels for every other shape (any F, any odd win, any W).
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace b2f {
+namespace {
+
+constexpr int kMaxFrames = 8;
+struct FramePtrs {
+  const float* p[kMaxFrames];
+};
+struct GradPtrs {
+  float* p[kMaxFrames];
+};
+
+// =======================================================================================
+// generic kernels
+// =======================================================================================
+
+__global__ void __launch_bounds__(256)
+costvol_fwd_generic(FramePtrs fr, int F, int B, int C, int H, int W, int win, int sgn,
+                    float* __restrict__ out, int64_t obs, float kdiv) {
+  const int n = (win - 1) / 2;
+  const int win2 = win * win;
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)B * win2 * hw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int i = (int)((idx / hw) % win2);
+    const int b = (int)(idx / (hw * win2));
+    const int qx = i / win - n, qy = i % win - n;
+    const float* r = fr.p[0] + (int64_t)b * C * hw + (int64_t)y * W + x;
+    float acc = 0.f;
+    for (int f = 1; f < F; ++f) {
+      const int xs = x - sgn * f * qx, ys = y - sgn * f * qy;
+      if (xs < 0 || xs >= W || ys < 0 || ys >= H) continue;
+      const float* g = fr.p[f] + (int64_t)b * C * hw + (int64_t)ys * W + xs;
+      for (int c = 0; c < C; ++c) acc = fmaf(__ldg(r + c * hw), __ldg(g + c * hw), acc);
+    }
+    out[(int64_t)b * obs + (int64_t)i * hw + (int64_t)y * W + x] = acc / kdiv;
+  }
+}
+
+// which == 0: gradient of the reference map; which == f >= 1: gradient of frame f.
+__global__ void __launch_bounds__(256)
+costvol_bwd_generic(FramePtrs fr, int F, int which, int B, int C, int H, int W, int win, int sgn,
+                    const float* __restrict__ go, int64_t gbs, float* __restrict__ gout, float kdiv) {
+  const int n = (win - 1) / 2;
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)B * C * hw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int c = (int)((idx / hw) % C);
+    const int b = (int)(idx / (hw * C));
+    const float* gob = go + (int64_t)b * gbs;
+    float acc = 0.f;
+    if (which == 0) {
+      for (int f = 1; f < F; ++f) {
+        const float* g = fr.p[f] + ((int64_t)b * C + c) * hw;
+        for (int ix = 0; ix < win; ++ix) {
+          const int xs = x - sgn * f * (ix - n);
+          if (xs < 0 || xs >= W) continue;
+          for (int iy = 0; iy < win; ++iy) {
+            const int ys = y - sgn * f * (iy - n);
+            if (ys < 0 || ys >= H) continue;
+            acc = fmaf(__ldg(gob + (int64_t)(ix * win + iy) * hw + (int64_t)y * W + x),
+                       __ldg(g + (int64_t)ys * W + xs), acc);
+          }
+        }
+      }
+    } else {
+      const int f = which;
+      const float* r = fr.p[0] + ((int64_t)b * C + c) * hw;
+      for (int ix = 0; ix < win; ++ix) {
+        const int xq = x + sgn * f * (ix - n);
+        if (xq < 0 || xq >= W) continue;
+        for (int iy = 0; iy < win; ++iy) {
+          const int yq = y + sgn * f * (iy - n);
+          if (yq < 0 || yq >= H) continue;
+          const int64_t o = (int64_t)yq * W + xq;
+          acc = fmaf(__ldg(gob + (int64_t)(ix * win + iy) * hw + o), __ldg(r + o), acc);
+        }
+      }
+    }
+    gout[idx] = acc / kdiv;
+  }
+}
+
+// =======================================================================================
+// tiled TMA forward (F = 2, win = 9)
+// =======================================================================================
+//
+// CTA = one 8 x (4A) pixel tile of one batch item; 9 compute warps (one per dy) + 1 TMA producer
+// warp.  Lane = (row r = lane & 7, strip st = lane >> 3); a thread owns A consecutive pixels of
+// row r and the 9 dx displacements of its warp's dy: 9*A accumulators.  Channels stream through a
+// 3-stage full/empty mbarrier ring in chunks of 8: per channel a thread reads A ref values and
+// A+8 frame values (LDS.128) for 9*A FFMAs.  Box row pitches are (odd * 16) bytes so the eight
+// rows of a quarter-warp hit disjoint bank groups.
+namespace cvf {
+constexpr int TH = 8;    // tile rows
+constexpr int CK = 8;    // channels per pipeline stage
+constexpr int NS = 3;    // pipeline stages
+constexpr int NCW = 9;   // compute warps = window rows
+constexpr int THREADS = (NCW + 1) * 32;
+
+template <int A>
+struct Cfg {
+  static constexpr int TW = 4 * A;
+  static constexpr int RW = TW + 4;         // ref box width   (RW/4 odd)
+  static constexpr int FW = TW + 12;        // frame box width (FW/4 odd), covers the +-4 halo
+  static constexpr int FR = TH + 8;         // frame box rows
+  static constexpr int REF_ELEMS = CK * TH * RW;
+  static constexpr int FRM_ELEMS = CK * FR * FW;
+  static constexpr int STAGE_ELEMS = REF_ELEMS + FRM_ELEMS;
+  static constexpr int STAGE_BYTES = STAGE_ELEMS * 4;
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 2 * NS * 8 + 128;
+  static_assert((RW / 4) % 2 == 1 && (FW / 4) % 2 == 1, "row pitch must be odd*16B");
+  static_assert((REF_ELEMS * 4) % 128 == 0 && (FRM_ELEMS * 4) % 128 == 0, "TMA dst alignment");
+};
+
+template <int A, int SGN>
+__global__ void __launch_bounds__(THREADS, 1)
+costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_frm,
+                float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv) {
+  using cfg = Cfg<A>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* stages = reinterpret_cast<float*>(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * cfg::STAGE_BYTES);
+  uint64_t* empty = full + NS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * cfg::TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int nchunks = (C + CK - 1) / CK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NCW) {  // ---- TMA producer ----
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_ref);
+      tma_prefetch_desc(&tm_frm);
+      for (int k = 0; k < nchunks; ++k) {
+        const int s = k % NS, it = k / NS;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        float* rs = stages + s * cfg::STAGE_ELEMS;
+        float* fs = rs + cfg::REF_ELEMS;
+        mbar_arrive_expect_tx(&full[s], cfg::STAGE_BYTES);
+        tma_load_4d(rs, &tm_ref, x0, y0, k * CK, b, &full[s]);
+        tma_load_4d(fs, &tm_frm, x0 - 4, y0 - 4, k * CK, b, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int r = lane & 7, st = lane >> 3;
+  const int iy = warp;
+  const int frow = r + 4 - SGN * (iy - 4);  // frame box row of this thread's source pixels
+
+  float acc[9][A];
+#pragma unroll
+  for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+    for (int j = 0; j < A; ++j) acc[ix][j] = 0.f;
+
+  for (int k = 0; k < nchunks; ++k) {
+    const int s = k % NS, it = k / NS;
+    mbar_wait(&full[s], it & 1);
+    const float* rs = stages + s * cfg::STAGE_ELEMS + r * cfg::RW + A * st;
+    const float* fs = stages + s * cfg::STAGE_ELEMS + cfg::REF_ELEMS + frow * cfg::FW + A * st;
+#pragma unroll 2
+    for (int cc = 0; cc < CK; ++cc) {
+      float rv[A], fv[A + 8];
+#pragma unroll
+      for (int q = 0; q < A / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(rs + cc * (TH * cfg::RW) + 4 * q);
+        rv[4 * q] = v.x; rv[4 * q + 1] = v.y; rv[4 * q + 2] = v.z; rv[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < (A + 8) / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(fs + cc * (cfg::FR * cfg::FW) + 4 * q);
+        fv[4 * q] = v.x; fv[4 * q + 1] = v.y; fv[4 * q + 2] = v.z; fv[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+          acc[ix][j] = fmaf(rv[j], fv[j + (SGN > 0 ? 8 - ix : ix)], acc[ix][j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- epilogue: out[b, ix*9+iy, y, x0 + A*st + j] ----
+  const int y = y0 + r;
+  if (y < H) {
+    const int64_t hw = (int64_t)H * W;
+    const int xb = x0 + A * st;
+    float* ob = out + (int64_t)b * obs + (int64_t)y * W + xb;
+#pragma unroll
+    for (int ix = 0; ix < 9; ++ix) {
+      float* o = ob + (int64_t)(ix * 9 + iy) * hw;
+#pragma unroll
+      for (int q = 0; q < A / 4; ++q) {
+        if (xb + 4 * q < W) {
+          float4 v;
+          v.x = acc[ix][4 * q] / kdiv; v.y = acc[ix][4 * q + 1] / kdiv;
+          v.z = acc[ix][4 * q + 2] / kdiv; v.w = acc[ix][4 * q + 3] / kdiv;
+          *reinterpret_cast<float4*>(o + 4 * q) = v;
+        }
+      }
+    }
+  }
+}
+}  // namespace cvf
+
+// =======================================================================================
+// tiled TMA backward (F = 2, win = 9)
+// =======================================================================================
+//
+// out[c,p] = 1/k sum_q G_q[p] * X[c, p + T q]   with
+//   role 0 (gradRef):   X = frame, T = -s, G_q[p] = go[q, p]
+//   role 1 (gradFrame): X = ref,   T = +s, G_q[p] = go[q, p + s q]   (the shift is the TMA box origin)
+// CTA = (8 x 32 pixel tile, 32-channel chunk, role); 4 compute warps (8 channels each) + 1 TMA
+// producer warp.  A thread owns 8 pixels x 8 channels = 64 accumulators.  The X halo tile of the
+// chunk stays resident; gradOut arrives as one slab per window row iy (9 boxes of 8 x 36, double
+// buffered).  Per slab a thread reads its 9 x 8 gradOut values once and, per channel, 16 X values
+// for 72 FFMAs.  Every output element is written exactly once: no atomics, no zero-fill.
+namespace cvb {
+constexpr int TH = 8, TW = 32;
+constexpr int CC = 32;            // channels per CTA
+constexpr int CG = 8;             // channels per warp
+constexpr int NCW = CC / CG;      // compute warps
+constexpr int THREADS = (NCW + 1) * 32;
+constexpr int XW = TW + 12, XR = TH + 8;       // X box: 44 x 16 (pitch 11*16 B)
+constexpr int GW = TW + 4;                     // gradOut box width 36 (pitch 9*16 B)
+constexpr int XG_ELEMS = CG * XR * XW;         // one warp's X group
+constexpr int X_ELEMS = NCW * XG_ELEMS;
+constexpr int GBOX_ELEMS = TH * GW;
+constexpr int SLAB_ELEMS = 9 * GBOX_ELEMS;
+constexpr int SLAB_BYTES = SLAB_ELEMS * 4;
+constexpr int NBAR = NCW + 4;
+constexpr int SMEM_BYTES = (X_ELEMS + 2 * SLAB_ELEMS) * 4 + NBAR * 8 + 128;
+static_assert((XW / 4) % 2 == 1 && (GW / 4) % 2 == 1, "row pitch must be odd*16B");
+static_assert((XG_ELEMS * 4) % 128 == 0 && (GBOX_ELEMS * 4) % 128 == 0, "TMA dst alignment");
+
+template <int T>
+__device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float* __restrict__ gs,
+                                         const float* __restrict__ xs) {
+  float g[9][8];
+#pragma unroll
+  for (int ix = 0; ix < 9; ++ix) {
+    const float4 a = *reinterpret_cast<const float4*>(gs + ix * GBOX_ELEMS);
+    const float4 c = *reinterpret_cast<const float4*>(gs + ix * GBOX_ELEMS + 4);
+    g[ix][0] = a.x; g[ix][1] = a.y; g[ix][2] = a.z; g[ix][3] = a.w;
+    g[ix][4] = c.x; g[ix][5] = c.y; g[ix][6] = c.z; g[ix][7] = c.w;
+  }
+#pragma unroll
+  for (int c = 0; c < CG; ++c) {
+    float xv[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + c * (XR * XW) + 4 * q);
+      xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[c][j] = fmaf(g[ix][j], xv[j + (T > 0 ? ix : 8 - ix)], acc[c][j]);
+  }
+}
+
+template <int SGN>
+__global__ void __launch_bounds__(THREADS, 2)
+costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
+                const __grid_constant__ CUtensorMap tm_go, float* __restrict__ grad_ref,
+                float* __restrict__ grad_frame, int nroles, int role0, int nchunk, int C, int H, int W,
+                float kdiv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* xsm = reinterpret_cast<float*>(smem);
+  float* gsm = xsm + X_ELEMS;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (X_ELEMS + 2 * SLAB_ELEMS) * 4);
+  uint64_t* gfull = xfull + NCW;
+  uint64_t* gempty = gfull + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  int z = blockIdx.z;
+  const int role = (nroles == 2) ? (z & 1) : role0;
+  if (nroles == 2) z >>= 1;
+  const int chunk = z % nchunk, b = z / nchunk;
+  const int c0 = chunk * CC;
+  const int T = (role == 0) ? -SGN : SGN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NCW; ++i) mbar_init(&xfull[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&gfull[i], 1);
+      mbar_init(&gempty[i], NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NCW) {  // ---- TMA producer ----
+    if (lane == 0) {
+      const CUtensorMap* tmx = (role == 0) ? &tm_frame : &tm_ref;
+      tma_prefetch_desc(tmx);
+      tma_prefetch_desc(&tm_go);
+      const int gshift = (role == 0) ? 0 : SGN;
+      auto load_slab = [&](int iy) {
+        const int s = iy & 1;
+        float* dst = gsm + s * SLAB_ELEMS;
+        mbar_arrive_expect_tx(&gfull[s], SLAB_BYTES);
+#pragma unroll 1
+        for (int ix = 0; ix < 9; ++ix)
+          tma_load_4d(dst + ix * GBOX_ELEMS, &tm_go, x0 + gshift * (ix - 4), y0 + gshift * (iy - 4),
+                      ix * 9 + iy, b, &gfull[s]);
+      };
+      // first gradOut slab, then the X groups, then the pipeline
+      load_slab(0);
+      for (int w = 0; w < NCW; ++w) {
+        mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
+        tma_load_4d(xsm + w * XG_ELEMS, tmx, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
+      }
+      load_slab(1);
+      for (int iy = 2; iy < 9; ++iy) {
+        mbar_wait(&gempty[iy & 1], ((iy >> 1) - 1) & 1);
+        load_slab(iy);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int r = lane & 7, st = lane >> 3;
+  float acc[CG][8];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+
+  mbar_wait(&xfull[warp], 0);
+  const float* xbase = xsm + warp * XG_ELEMS + 8 * st;
+  for (int iy = 0; iy < 9; ++iy) {
+    const int s = iy & 1;
+    mbar_wait(&gfull[s], (iy >> 1) & 1);
+    const float* gs = gsm + s * SLAB_ELEMS + r * GW + 8 * st;
+    const float* xs = xbase + (r + 4 + T * (iy - 4)) * XW;
+    if (T > 0) slab_fma<1>(acc, gs, xs);
+    else       slab_fma<-1>(acc, gs, xs);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&gempty[s]);
+  }
+
+  // ---- epilogue ----
+  float* outp = (role == 0) ? grad_ref : grad_frame;
+  const int y = y0 + r;
+  const int xb = x0 + 8 * st;
+  if (y < H && xb < W) {
+    const int64_t hw = (int64_t)H * W;
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+      const int ch = c0 + warp * CG + c;
+      if (ch < C) {
+        float* o = outp + ((int64_t)b * C + ch) * hw + (int64_t)y * W + xb;
+        float4 v0, v1;
+        v0.x = acc[c][0] / kdiv; v0.y = acc[c][1] / kdiv; v0.z = acc[c][2] / kdiv; v0.w = acc[c][3] / kdiv;
+        v1.x = acc[c][4] / kdiv; v1.y = acc[c][5] / kdiv; v1.z = acc[c][6] / kdiv; v1.w = acc[c][7] / kdiv;
+        *reinterpret_cast<float4*>(o) = v0;
+        if (xb + 4 < W) *reinterpret_cast<float4*>(o + 4) = v1;
+      }
+    }
+  }
+}
+}  // namespace cvb
+
+// =======================================================================================
+// host dispatch
+// =======================================================================================
+
+int check_common(const float* const* frames, int F, int B, int C, int H, int W, int win) {
+  if (!frames) return fail(B2F_EINVAL, "costvol: frames is NULL");
+  if (F < 2 || F > kMaxFrames) return fail(B2F_EINVAL, "costvol: F=%d outside [2,%d]", F, kMaxFrames);
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "costvol: bad size B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (win <= 0 || (win & 1) == 0) return fail(B2F_EINVAL, "costvol: win=%d must be odd and positive", win);
+  for (int f = 0; f < F; ++f) {
+    if (!frames[f]) return fail(B2F_EINVAL, "costvol: frames[%d] is NULL", f);
+    if (!aligned4(frames[f])) return fail(B2F_EALIGN, "costvol: frames[%d] misaligned", f);
+  }
+  return B2F_OK;
+}
+
+int grid_for(int64_t total, int threads) {
+  int64_t blocks = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <int A, int SGN>
+int launch_fwd_tma(const CUtensorMap& tr, const CUtensorMap& tf, float* out, int64_t obs, int B, int C, int H,
+                   int W, float kdiv, cudaStream_t st) {
+  using cfg = cvf::Cfg<A>;
+  auto kern = cvf::costvol_fwd_tma<A, SGN>;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  B2F_CUDA_TRY(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    attr_dev = dev;
+  }
+  dim3 grid((W + cfg::TW - 1) / cfg::TW, (H + cvf::TH - 1) / cvf::TH, B);
+  kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, out, obs, C, H, W, kdiv);
+  B2F_CHECK_LAUNCH("costvol_fwd_tma");
+  return B2F_OK;
+}
+
+template <int A>
+int make_fwd_maps(CUtensorMap* tr, CUtensorMap* tf, const float* ref, const float* frm, int B, int C, int H,
+                  int W) {
+  using cfg = cvf::Cfg<A>;
+  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)W * H * C};
+  const uint32_t box_r[4] = {(uint32_t)cfg::RW, (uint32_t)cvf::TH, (uint32_t)cvf::CK, 1};
+  const uint32_t box_f[4] = {(uint32_t)cfg::FW, (uint32_t)cfg::FR, (uint32_t)cvf::CK, 1};
+  int rc = make_tmap4(tr, ref, dims, str, box_r);
+  if (rc) return rc;
+  return make_tmap4(tf, frm, dims, str, box_f);
+}
+
+int64_t tiles_for(int A, int B, int H, int W) {
+  return (int64_t)B * ((H + 7) / 8) * ((W + 4 * A - 1) / (4 * A));
+}
+
+}  // namespace
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int C, int H, int W, int win,
+                                   int fwd, float* out, int64_t out_batch_stride, b2f_stream_t stream) {
+  int rc = check_common(frames, F, B, C, H, W, win);
+  if (rc) return rc;
+  if (!out) return fail(B2F_EINVAL, "costvol_forward: out is NULL");
+  if (!aligned4(out)) return fail(B2F_EALIGN, "costvol_forward: out misaligned");
+  const int64_t hw = (int64_t)H * W;
+  const int64_t obs = out_batch_stride ? out_batch_stride : (int64_t)win * win * hw;
+  if (obs < (int64_t)win * win * hw) return fail(B2F_EINVAL, "costvol_forward: out_batch_stride too small");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float kdiv = (float)(C * (F - 1));
+  const int sgn = fwd ? 1 : -1;
+
+  const int path = costvol_path();
+  const bool tma_ok = path != 1 && F == 2 && win == 9 && (W % 4) == 0 && aligned16(frames[0]) &&
+                      aligned16(frames[1]) && aligned16(out) && (obs % 4) == 0 && get_encode_fn() != nullptr;
+  if (tma_ok) {
+    // largest strip width whose grid still fills the machine
+    int A = 0;
+    const int sms = num_sms();
+    if (path >= 2) A = path == 2 ? 16 : (path == 3 ? 8 : 4);
+    else if (W >= 64 && tiles_for(16, B, H, W) >= sms) A = 16;
+    else if (W >= 32 && tiles_for(8, B, H, W) >= sms) A = 8;
+    else if (tiles_for(4, B, H, W) >= 64) A = 4;
+    if (A) {
+      CUtensorMap tr, tf;
+      if (A == 16) rc = make_fwd_maps<16>(&tr, &tf, frames[0], frames[1], B, C, H, W);
+      else if (A == 8) rc = make_fwd_maps<8>(&tr, &tf, frames[0], frames[1], B, C, H, W);
+      else rc = make_fwd_maps<4>(&tr, &tf, frames[0], frames[1], B, C, H, W);
+      if (rc) return rc;
+      if (A == 16) return sgn > 0 ? launch_fwd_tma<16, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
+                                  : launch_fwd_tma<16, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
+      if (A == 8) return sgn > 0 ? launch_fwd_tma<8, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
+                                 : launch_fwd_tma<8, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
+      return sgn > 0 ? launch_fwd_tma<4, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
+                     : launch_fwd_tma<4, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
+    }
+  }
+
+  FramePtrs fp;
+  for (int f = 0; f < kMaxFrames; ++f) fp.p[f] = f < F ? frames[f] : nullptr;
+  const int64_t total = (int64_t)B * win * win * hw;
+  costvol_fwd_generic<<<grid_for(total, 256), 256, 0, st>>>(fp, F, B, C, H, W, win, sgn, out, obs, kdiv);
+  B2F_CHECK_LAUNCH("costvol_fwd_generic");
+  return B2F_OK;
+}
+
+extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, int C, int H, int W, int win,
+                                    int fwd, const float* gradOut, int64_t gradOut_batch_stride,
+                                    float* const* gradFrames, b2f_stream_t stream) {
+  int rc = check_common(frames, F, B, C, H, W, win);
+  if (rc) return rc;
+  if (!gradOut || !gradFrames) return fail(B2F_EINVAL, "costvol_backward: NULL gradOut/gradFrames");
+  if (!aligned4(gradOut)) return fail(B2F_EALIGN, "costvol_backward: gradOut misaligned");
+  const int64_t hw = (int64_t)H * W;
+  const int64_t gbs = gradOut_batch_stride ? gradOut_batch_stride : (int64_t)win * win * hw;
+  if (gbs < (int64_t)win * win * hw) return fail(B2F_EINVAL, "costvol_backward: gradOut_batch_stride too small");
+  for (int f = 0; f < F; ++f)
+    if (gradFrames[f] && !aligned4(gradFrames[f])) return fail(B2F_EALIGN, "costvol_backward: gradFrames[%d] misaligned", f);
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float kdiv = (float)(C * (F - 1));
+  const int sgn = fwd ? 1 : -1;
+
+  const int nroles = (gradFrames[0] ? 1 : 0) + ((F == 2 && gradFrames[1]) ? 1 : 0);
+  const int path = costvol_path();
+  bool tma_ok = path != 1 && F == 2 && win == 9 && (W % 4) == 0 && nroles > 0 &&
+                aligned16(frames[0]) && aligned16(frames[1]) && aligned16(gradOut) && (gbs % 4) == 0 &&
+                (!gradFrames[0] || aligned16(gradFrames[0])) && (!gradFrames[1] || aligned16(gradFrames[1])) &&
+                get_encode_fn() != nullptr;
+  if (tma_ok) {
+    const int nchunk = (C + cvb::CC - 1) / cvb::CC;
+    const int64_t ctas = (int64_t)B * ((H + cvb::TH - 1) / cvb::TH) * ((W + cvb::TW - 1) / cvb::TW) * nchunk * nroles;
+    if ((ctas < 48 && path < 2) || (int64_t)B * nchunk * nroles > 65535) tma_ok = false;
+    if (tma_ok) {
+      const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+      const uint64_t str[3] = {(uint64_t)W, (uint64_t)hw, (uint64_t)hw * C};
+      const uint32_t box_x[4] = {(uint32_t)cvb::XW, (uint32_t)cvb::XR, (uint32_t)cvb::CG, 1};
+      const uint64_t gdims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+      const uint64_t gstr[3] = {(uint64_t)W, (uint64_t)hw, (uint64_t)gbs};
+      const uint32_t box_g[4] = {(uint32_t)cvb::GW, (uint32_t)cvb::TH, 1, 1};
+      CUtensorMap tfrm, tref, tgo;
+      if ((rc = make_tmap4(&tfrm, frames[1], dims, str, box_x))) return rc;
+      if ((rc = make_tmap4(&tref, frames[0], dims, str, box_x))) return rc;
+      if ((rc = make_tmap4(&tgo, gradOut, gdims, gstr, box_g))) return rc;
+      static thread_local int attr_dev = -1;
+      int dev = 0;
+      B2F_CUDA_TRY(cudaGetDevice(&dev));
+      if (attr_dev != dev) {
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::SMEM_BYTES));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::SMEM_BYTES));
+        attr_dev = dev;
+      }
+      const int role0 = gradFrames[0] ? 0 : 1;
+      dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
+      if (sgn > 0)
+        cvb::costvol_bwd_tma<1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
+            tfrm, tref, tgo, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+      else
+        cvb::costvol_bwd_tma<-1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
+            tfrm, tref, tgo, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+      B2F_CHECK_LAUNCH("costvol_bwd_tma");
+      return B2F_OK;
+    }
+  }
+
+  FramePtrs fp;
+  for (int f = 0; f < kMaxFrames; ++f) fp.p[f] = f < F ? frames[f] : nullptr;
+  const int64_t total = (int64_t)B * C * hw;
+  for (int f = 0; f < F; ++f) {
+    if (!gradFrames[f]) continue;
+    costvol_bwd_generic<<<grid_for(total, 256), 256, 0, st>>>(fp, F, f, B, C, H, W, win, sgn, gradOut, gbs,
+                                                              gradFrames[f], kdiv);
+    B2F_CHECK_LAUNCH("costvol_bwd_generic");
+  }
+  return B2F_OK;
+}

@@ -1,0 +1,600 @@
+// Fused criterion kernels for sm_100a: one pass per criterion call produces the loss scalar and every
+// gradient the reference returns.  All of them are pure streaming stencils (HBM-bound); the reference
+// runs 10-100 generic THC kernels plus host-built coordinate grids per call.
+//
+// Loss reduction is deterministic: per-thread float partial -> per-block double partial -> the last
+// block to finish (ticket counter) sums the block partials in index order and applies the normaliser.
+#include "common.cuh"
+
+namespace b2f {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct LossOut {
+  double* partials;   // [gridDim.x]
+  unsigned* counter;  // zeroed before launch
+  double* result;     // scratch result (device)
+  double* loss_dev;   // optional user device pointer
+  double scale;       // normaliser applied once at the end
+};
+
+__device__ __forceinline__ void finish_loss(float local, const LossOut& lo) {
+  __shared__ double s_warp[kThreads / 32];
+  __shared__ bool s_last;
+  double v = (double)local;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) t += s_warp[i];
+    lo.partials[blockIdx.x] = t;
+    __threadfence();
+    const unsigned ticket = atomicAdd(lo.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block: fixed-order sum of the block partials
+  double t = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) t += __ldcg(lo.partials + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) tot += s_warp[i];
+    tot *= lo.scale;
+    *lo.result = tot;
+    if (lo.loss_dev) *lo.loss_dev = tot;
+  }
+}
+
+// Host side of the loss delivery: stream-ordered scratch, optional synchronous read-back.
+struct LossScratch {
+  void* mem = nullptr;
+  LossOut lo{};
+  cudaStream_t st = nullptr;
+
+  int begin(int blocks, double scale, double* loss_dev, cudaStream_t stream) {
+    st = stream;
+    const size_t bytes = (size_t)blocks * sizeof(double) + 2 * sizeof(double);
+    cudaError_t e = cudaMallocAsync(&mem, bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(loss scratch)");
+    lo.result = reinterpret_cast<double*>(mem);
+    lo.counter = reinterpret_cast<unsigned*>(lo.result + 1);
+    lo.partials = lo.result + 2;
+    lo.loss_dev = loss_dev;
+    lo.scale = scale;
+    e = cudaMemsetAsync(lo.counter, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(loss counter)");
+    return B2F_OK;
+  }
+  int end(double* loss_host) {
+    cudaError_t e = cudaSuccess;
+    if (loss_host) {
+      e = cudaMemcpyAsync(loss_host, lo.result, sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaError_t e2 = cudaFreeAsync(mem, st);
+    mem = nullptr;
+    if (e != cudaSuccess) return cuda_fail(e, "loss read-back");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync(loss scratch)");
+    return B2F_OK;
+  }
+};
+
+// =======================================================================================
+// OBCC / OBGCC  (criterions/OBCCriterion.lua, criterions/OBGCCriterion.lua), F = 3
+// =======================================================================================
+struct ObArgs {
+  const float* flow;
+  const float* bflow;   // flow used for the past frame's mask (== flow unless past_flow)
+  const float* occ;
+  const float* warp[2];  // [0] past frame (f=1), [1] future frame (f=2)
+  const float* target;
+  float* g_occ;
+  float* g_warp[2];
+  int B, C, h, w;
+  float eps2, penalty_out, alpha, beta, gamma, scale, norm;
+  int grad_check;
+};
+
+template <int PEN, bool GT>
+__global__ void __launch_bounds__(kThreads)
+ob_kernel(ObArgs a, LossOut lo) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int64_t npix = (int64_t)a.B * hw;
+  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  float loss = 0.f;
+  if (pix < npix) {
+    const int x = (int)(pix % a.w);
+    const int y = (int)((pix / a.w) % a.h);
+    const int b = (int)(pix / hw);
+    const int64_t o = (int64_t)y * a.w + x;
+    const int w = a.w, h = a.h;
+#pragma unroll
+    for (int fr = 0; fr < 2; ++fr) {
+      // fr 0: past frame, k = -1, occ channel 2 (index 1); fr 1: future, k = +1, occ channel 1
+      const float k = fr == 0 ? -1.f : 1.f;
+      const int oc = fr == 0 ? 1 : 0;
+      const float* fl = fr == 0 ? a.bflow : a.flow;
+      const float occv = __ldg(a.occ + ((int64_t)b * 2 + oc) * hw + o);
+      bool m = true;
+      if (!a.grad_check) {
+        // tcoord = fl(coord + fl(fl(k*flow)*scale)), 1-based coords (OBCCriterion.lua:81-100, Q14)
+        const float fx = __ldg(fl + ((int64_t)b * 2) * hw + o);
+        const float fy = __ldg(fl + ((int64_t)b * 2 + 1) * hw + o);
+        const float tx = __fadd_rn((float)(x + 1), __fmul_rn(__fmul_rn(fx, k), a.scale));
+        const float ty = __fadd_rn((float)(y + 1), __fmul_rn(__fmul_rn(fy, k), a.scale));
+        m = (tx >= 1.f) && (ty >= 1.f) && (tx <= (float)w) && (ty <= (float)h);
+      }
+      const float* img = a.warp[fr];
+      float* gw = a.g_warp[fr];
+      float e = 0.f, ex = 0.f, ey = 0.f, exm = 0.f, eym = 0.f;
+      const float gscale = m ? occv * a.norm : 0.f;
+      for (int c = 0; c < a.C; ++c) {
+        const int64_t p = ((int64_t)b * a.C + c) * hw + o;
+        const float iv = __ldg(img + p), tv = __ldg(a.target + p);
+        const float d = iv - tv;
+        e += pen_apply<PEN>(d, a.eps2);
+        float gi;
+        if (GT) {
+          const float dgx = (x < w - 1) ? (__ldg(img + p + 1) - iv) - (__ldg(a.target + p + 1) - tv) : 0.f;
+          const float dgy = (y < h - 1) ? (__ldg(img + p + w) - iv) - (__ldg(a.target + p + w) - tv) : 0.f;
+          ex += pen_apply<PEN>(dgx, a.eps2);
+          ey += pen_apply<PEN>(dgy, a.eps2);
+          gi = pen_der<PEN>(d, a.eps2) * a.alpha;
+          gi -= pen_der<PEN>(dgy, a.eps2) * a.gamma;
+          if (y > 0) {
+            const float dm = (iv - __ldg(img + p - w)) - (tv - __ldg(a.target + p - w));
+            gi += pen_der<PEN>(dm, a.eps2) * a.gamma;
+            eym += pen_apply<PEN>(dm, a.eps2);
+          }
+          gi -= pen_der<PEN>(dgx, a.eps2) * a.beta;
+          if (x > 0) {
+            const float dm = (iv - __ldg(img + p - 1)) - (tv - __ldg(a.target + p - 1));
+            gi += pen_der<PEN>(dm, a.eps2) * a.beta;
+            exm += pen_apply<PEN>(dm, a.eps2);
+          }
+        } else {
+          gi = pen_der<PEN>(d, a.eps2);
+        }
+        if (gw) gw[p] = gi * gscale;
+      }
+      // forward energy (alpha is not applied here: OBGCCriterion.lua:97)
+      float tmp = GT ? e + ex * a.beta + ey * a.gamma : e;
+      tmp *= occv;
+      loss += m ? tmp : a.penalty_out;
+      // occlusion gradient (Q6, Q7)
+      if (a.g_occ) {
+        float buf = e;
+        if (GT) {
+          buf = e * a.alpha;
+          buf -= ey * a.gamma;
+          buf += eym * a.gamma;
+          buf -= ex * a.beta;
+          buf += exm * a.beta;
+        }
+        buf = m ? buf : a.penalty_out;
+        a.g_occ[((int64_t)b * 2 + oc) * hw + o] = buf * a.norm;
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+// =======================================================================================
+// SmoothnessCriterion / SecondOrderSmoothnessCriterion
+// =======================================================================================
+struct SmArgs {
+  const float* in;
+  const float* tgt;
+  float* grad;
+  int B, Cin, Ct, h, w;
+  float eps2, cs, norm;
+  int alias;        // order 1: reproduce the view-resize aliasing (only matters when Cin != Ct)
+  int64_t n_dy;     // B*Ct*(h-1)*w, elements of the contiguous y-difference array
+  int64_t n_dx;     // B*Ct*h*(w-1)
+};
+
+// order-1 edge weights -----------------------------------------------------------------
+__device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  float s = 0.f;
+  if (a.alias) {
+    // igy(b,j,y,x) = flat(D_y)[((b*Cin+j)*h+y)*w+x], D_y contiguous (B,Ct,h-1,w)   (Q9)
+    for (int j = 0; j < a.Cin; ++j) {
+      const int64_t idx = (((int64_t)b * a.Cin + j) * a.h + y) * a.w + x;
+      float v = 0.f;
+      if (idx < a.n_dy) {
+        const int xx = (int)(idx % a.w);
+        int64_t t = idx / a.w;
+        const int r = (int)(t % (a.h - 1));
+        t /= (a.h - 1);
+        const int cc = (int)(t % a.Ct);
+        const int bb = (int)(t / a.Ct);
+        const float* p = a.tgt + ((int64_t)bb * a.Ct + cc) * hw + (int64_t)r * a.w + xx;
+        v = __ldg(p + a.w) - __ldg(p);
+      }
+      s += fabsf(v);
+    }
+    return expf(-a.cs * (s / (float)a.Cin));
+  }
+  if (y < a.h - 1) {
+    for (int c = 0; c < a.Ct; ++c) {
+      const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+      s += fabsf(__ldg(p + a.w) - __ldg(p));
+    }
+  }
+  return expf(-a.cs * (s / (float)a.Ct));
+}
+
+__device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  float s = 0.f;
+  if (a.alias) {
+    for (int j = 0; j < a.Cin; ++j) {
+      const int64_t idx = (((int64_t)b * a.Cin + j) * a.h + y) * a.w + x;
+      float v = 0.f;
+      if (idx < a.n_dx) {
+        const int xx = (int)(idx % (a.w - 1));
+        int64_t t = idx / (a.w - 1);
+        const int yy = (int)(t % a.h);
+        t /= a.h;
+        const int cc = (int)(t % a.Ct);
+        const int bb = (int)(t / a.Ct);
+        const float* p = a.tgt + ((int64_t)bb * a.Ct + cc) * hw + (int64_t)yy * a.w + xx;
+        v = __ldg(p + 1) - __ldg(p);
+      }
+      s += fabsf(v);
+    }
+    return expf(-a.cs * (s / (float)a.Cin));
+  }
+  if (x < a.w - 1) {
+    for (int c = 0; c < a.Ct; ++c) {
+      const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+      s += fabsf(__ldg(p + 1) - __ldg(p));
+    }
+  }
+  return expf(-a.cs * (s / (float)a.Ct));
+}
+
+template <int PEN>
+__global__ void __launch_bounds__(kThreads)
+smooth1_kernel(SmArgs a, LossOut lo) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int64_t npix = (int64_t)a.B * hw;
+  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  float loss = 0.f;
+  if (pix < npix) {
+    const int x = (int)(pix % a.w);
+    const int y = (int)((pix / a.w) % a.h);
+    const int b = (int)(pix / hw);
+    const int w = a.w, h = a.h;
+    const float wx0 = w1_x(a, b, y, x), wy0 = w1_y(a, b, y, x);
+    const bool need_g = a.grad != nullptr;
+    const float wxm = (need_g && x > 0) ? w1_x(a, b, y, x - 1) : 0.f;
+    const float wym = (need_g && y > 0) ? w1_y(a, b, y - 1, x) : 0.f;
+    for (int ch = 0; ch < a.Cin; ++ch) {
+      const int64_t p = ((int64_t)b * a.Cin + ch) * hw + (int64_t)y * w + x;
+      const float v = __ldg(a.in + p);
+      const float gx = (x < w - 1) ? __ldg(a.in + p + 1) - v : 0.f;
+      const float gy = (y < h - 1) ? __ldg(a.in + p + w) - v : 0.f;
+      loss += pen_apply<PEN>(gx, a.eps2) * wx0 + pen_apply<PEN>(gy, a.eps2) * wy0;
+      if (need_g) {
+        // -Gx + shift(Gx) - Gy + shift(Gy)   (SmoothnessCriterion.lua:85-103)
+        float g = -(pen_der<PEN>(gx, a.eps2) * wx0);
+        if (x > 0) g += pen_der<PEN>(v - __ldg(a.in + p - 1), a.eps2) * wxm;
+        g -= pen_der<PEN>(gy, a.eps2) * wy0;
+        if (y > 0) g += pen_der<PEN>(v - __ldg(a.in + p - w), a.eps2) * wym;
+        a.grad[p] = g * a.norm;
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+// order-2 weights (SecondOrderSmoothnessCriterion.lua:49-61) ------------------------------
+__device__ __forceinline__ float w2_y(const SmArgs& a, int b, int y, int x) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < a.Ct; ++c) {
+    const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+    const float t = __ldg(p);
+    if (y >= 1) s1 += fabsf(t - __ldg(p - a.w));
+    if (y >= 1 && y <= a.h - 2) s2 += fabsf(t - __ldg(p + a.w));
+  }
+  return expf(-a.cs * (s1 / (float)a.Ct + s2 / (float)a.Ct));
+}
+__device__ __forceinline__ float w2_x(const SmArgs& a, int b, int y, int x) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < a.Ct; ++c) {
+    const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+    const float t = __ldg(p);
+    if (x >= 1) s1 += fabsf(t - __ldg(p - 1));
+    if (x >= 1 && x <= a.w - 2) s2 += fabsf(t - __ldg(p + 1));
+  }
+  return expf(-a.cs * (s1 / (float)a.Ct + s2 / (float)a.Ct));
+}
+
+template <int PEN>
+__global__ void __launch_bounds__(kThreads)
+smooth2_kernel(SmArgs a, LossOut lo) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int64_t npix = (int64_t)a.B * hw;
+  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  float loss = 0.f;
+  if (pix < npix) {
+    const int x = (int)(pix % a.w);
+    const int y = (int)((pix / a.w) % a.h);
+    const int b = (int)(pix / hw);
+    const int w = a.w, h = a.h;
+    const bool need_g = a.grad != nullptr;
+    // weights at the three positions each direction needs
+    float wy[3], wx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int yy = y + k - 1, xx = x + k - 1;
+      wy[k] = (yy >= 0 && yy < h && (k == 1 || need_g)) ? w2_y(a, b, yy, x) : 0.f;
+      wx[k] = (xx >= 0 && xx < w && (k == 1 || need_g)) ? w2_x(a, b, y, xx) : 0.f;
+    }
+    for (int ch = 0; ch < a.Cin; ++ch) {
+      const float* I = a.in + ((int64_t)b * a.Cin + ch) * hw;
+      const int64_t o = (int64_t)y * w + x;
+      // second differences at y-1, y, y+1 (zero outside the interior 1..h-2)
+      float gy[3], gx[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int yy = y + k - 1, xx = x + k - 1;
+        gy[k] = 0.f;
+        gx[k] = 0.f;
+        if ((k == 1 || need_g) && yy >= 1 && yy <= h - 2) {
+          const int64_t q = (int64_t)yy * w + x;
+          gy[k] = (2.f * __ldg(I + q) - __ldg(I + q - w)) - __ldg(I + q + w);
+        }
+        if ((k == 1 || need_g) && xx >= 1 && xx <= w - 2) {
+          const int64_t q = (int64_t)y * w + xx;
+          gx[k] = (2.f * __ldg(I + q) - __ldg(I + q - 1)) - __ldg(I + q + 1);
+        }
+      }
+      loss += pen_apply<PEN>(gx[1], a.eps2) * wx[1] + pen_apply<PEN>(gy[1], a.eps2) * wy[1];
+      if (need_g) {
+        // adjoint of the second difference (SecondOrderSmoothnessCriterion.lua:90-97)
+        float g = 0.f;
+        if (y >= 1 && y <= h - 2) g += 2.f * (pen_der<PEN>(gy[1], a.eps2) * wy[1]);
+        if (x >= 1 && x <= w - 2) g += 2.f * (pen_der<PEN>(gx[1], a.eps2) * wx[1]);
+        if (y + 1 >= 1 && y + 1 <= h - 2) g -= pen_der<PEN>(gy[2], a.eps2) * wy[2];
+        if (x + 1 >= 1 && x + 1 <= w - 2) g -= pen_der<PEN>(gx[2], a.eps2) * wx[2];
+        if (y - 1 >= 1 && y - 1 <= h - 2) g -= pen_der<PEN>(gy[0], a.eps2) * wy[0];
+        if (x - 1 >= 1 && x - 1 <= w - 2) g -= pen_der<PEN>(gx[0], a.eps2) * wx[0];
+        a.grad[((int64_t)b * a.Cin + ch) * hw + o] = g * a.norm;
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+// =======================================================================================
+// ConstVelCriterion / OcclusionPriorCriterion
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads)
+constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float* __restrict__ gf,
+                float* __restrict__ gb, int B, int C, int64_t hw, float gnorm, LossOut lo) {
+  const int64_t npix = (int64_t)B * hw;
+  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  float loss = 0.f;
+  if (pix < npix) {
+    const int b = (int)(pix / hw);
+    const int64_t o = pix - (int64_t)b * hw;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t p = ((int64_t)b * C + c) * hw + o;
+      const float d = __ldg(f + p) - __ldg(bb + p);
+      s += d * d;
+    }
+    const float nrm = sqrtf(s);
+    loss = nrm;
+    if (gf || gb) {
+      const float den = nrm + 1e-12f;
+      for (int c = 0; c < C; ++c) {
+        const int64_t p = ((int64_t)b * C + c) * hw + o;
+        const float fv = __ldg(f + p), bv = __ldg(bb + p);
+        if (gf) gf[p] = ((fv - bv) / den) * gnorm;
+        if (gb) gb[p] = ((bv - fv) / den) * gnorm;
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+__global__ void __launch_bounds__(kThreads)
+occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, int C, int64_t hw,
+                float penalty, float norm, LossOut lo) {
+  const int64_t npix = (int64_t)B * hw;
+  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  float loss = 0.f;
+  if (pix < npix) {
+    const int b = (int)(pix / hw);
+    const int64_t o = pix - (int64_t)b * hw;
+    const int64_t p0 = ((int64_t)b * C) * hw + o;
+    const float o1 = __ldg(occ + p0), o2 = __ldg(occ + p0 + hw);
+    if (C == 3) {
+      const float o3 = __ldg(occ + p0 + 2 * hw);
+      loss = (1.f - o2) * (o1 + o3) * penalty * 0.05f;
+      if (grad) {
+        grad[p0] = (1.f - o2) * penalty * 0.05f * norm;
+        grad[p0 + hw] = -(o1 + o3) * penalty * 0.05f * norm;
+        grad[p0 + 2 * hw] = (1.f - o2) * penalty * 0.05f * norm;
+      }
+    } else {
+      loss = (1.f - o1 * o2) * penalty;
+      if (grad) {
+        grad[p0] = (1.f - o2) * penalty * norm;
+        grad[p0 + hw] = (1.f - o1) * penalty * norm;
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+int blocks_for_pixels(int64_t npix, int* blocks) {
+  const int64_t nb = (npix + kThreads - 1) / kThreads;
+  if (nb > 0x7fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
+  *blocks = (int)(nb < 1 ? 1 : nb);
+  return B2F_OK;
+}
+
+bool valid_penalty(int p) { return p == B2F_PENALTY_QUADRATIC || p == B2F_PENALTY_L1 || p == B2F_PENALTY_LORENTZIAN; }
+
+template <bool GT>
+void launch_ob(int pen, int blocks, cudaStream_t st, const ObArgs& a, const LossOut& lo) {
+  if (pen == B2F_PENALTY_QUADRATIC) ob_kernel<B2F_PENALTY_QUADRATIC, GT><<<blocks, kThreads, 0, st>>>(a, lo);
+  else if (pen == B2F_PENALTY_L1) ob_kernel<B2F_PENALTY_L1, GT><<<blocks, kThreads, 0, st>>>(a, lo);
+  else ob_kernel<B2F_PENALTY_LORENTZIAN, GT><<<blocks, kThreads, 0, st>>>(a, lo);
+}
+
+}  // namespace
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int b2f_ob_criterion(const b2f_ob_params* prm, const float* flow, const float* bflow,
+                                const float* occ, const float* warp_past, const float* warp_future,
+                                const float* target, int B, int C, int h, int w, float* grad_occ,
+                                float* grad_warp_past, float* grad_warp_future, double* loss_dev,
+                                double* loss_host, b2f_stream_t stream) {
+  if (!prm) return fail(B2F_EINVAL, "ob_criterion: params is NULL");
+  if (!flow || !occ || !warp_past || !warp_future || !target) return fail(B2F_EINVAL, "ob_criterion: NULL input");
+  if (prm->past_flow && !bflow) return fail(B2F_EINVAL, "ob_criterion: past_flow set but bflow is NULL");
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return fail(B2F_EINVAL, "ob_criterion: bad size B=%d C=%d h=%d w=%d", B, C, h, w);
+  if (!valid_penalty(prm->penalty)) return fail(B2F_EINVAL, "ob_criterion: unknown penalty %d", prm->penalty);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t npix = (int64_t)B * h * w;
+  int blocks;
+  int rc = blocks_for_pixels(npix, &blocks);
+  if (rc) return rc;
+  const int F = 3;
+  double scale = 1.0 / ((double)C * (F - 1));
+  if (prm->size_average) scale *= 1.0 / (double)npix;
+  ObArgs a;
+  a.flow = flow;
+  a.bflow = prm->past_flow ? bflow : flow;
+  a.occ = occ;
+  a.warp[0] = warp_past;
+  a.warp[1] = warp_future;
+  a.target = target;
+  a.g_occ = grad_occ;
+  a.g_warp[0] = grad_warp_past;
+  a.g_warp[1] = grad_warp_future;
+  a.B = B; a.C = C; a.h = h; a.w = w;
+  a.eps2 = prm->penalty_eps > 0.f ? prm->penalty_eps * prm->penalty_eps : 0.05f * 0.05f;
+  a.penalty_out = prm->penalty_out;
+  a.alpha = prm->alpha; a.beta = prm->beta; a.gamma = prm->gamma;
+  a.scale = prm->pwc_flow_scaling;
+  a.norm = (float)scale;
+  a.grad_check = prm->grad_check;
+  LossScratch ls;
+  if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
+  if (prm->gradient_terms) launch_ob<true>(prm->penalty, blocks, st, a, ls.lo);
+  else launch_ob<false>(prm->penalty, blocks, st, a, ls.lo);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  rc = ls.end(loss_host);
+  if (e != cudaSuccess) return cuda_fail(e, "ob_kernel");
+  return rc;
+}
+
+extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const float* input, const float* target,
+                                        int B, int Cin, int Ct, int h, int w, float* grad, double* loss_dev,
+                                        double* loss_host, b2f_stream_t stream) {
+  if (!prm) return fail(B2F_EINVAL, "smoothness: params is NULL");
+  if (!input || !target) return fail(B2F_EINVAL, "smoothness: NULL input/target");
+  if (B <= 0 || Cin <= 0 || Ct <= 0 || h <= 0 || w <= 0) return fail(B2F_EINVAL, "smoothness: bad size");
+  if (prm->order != 1 && prm->order != 2) return fail(B2F_EINVAL, "smoothness: order %d", prm->order);
+  if (!valid_penalty(prm->penalty)) return fail(B2F_EINVAL, "smoothness: unknown penalty %d", prm->penalty);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t npix = (int64_t)B * h * w;
+  int blocks;
+  int rc = blocks_for_pixels(npix, &blocks);
+  if (rc) return rc;
+  const double scale = prm->size_average ? 1.0 / ((double)npix * Cin) : 1.0;
+  SmArgs a;
+  a.in = input; a.tgt = target; a.grad = grad;
+  a.B = B; a.Cin = Cin; a.Ct = Ct; a.h = h; a.w = w;
+  a.eps2 = prm->penalty_eps > 0.f ? prm->penalty_eps * prm->penalty_eps : 0.05f * 0.05f;
+  a.cs = prm->cs;
+  a.norm = (float)scale;
+  a.alias = (prm->alias_weights && Cin != Ct) ? 1 : 0;
+  a.n_dy = (int64_t)B * Ct * (h - 1) * w;
+  a.n_dx = (int64_t)B * Ct * h * (w - 1);
+  LossScratch ls;
+  if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
+  const int pen = prm->penalty;
+  if (prm->order == 1) {
+    if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    else if (pen == B2F_PENALTY_L1) smooth1_kernel<B2F_PENALTY_L1><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    else smooth1_kernel<B2F_PENALTY_LORENTZIAN><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+  } else {
+    if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    else if (pen == B2F_PENALTY_L1) smooth2_kernel<B2F_PENALTY_L1><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    else smooth2_kernel<B2F_PENALTY_LORENTZIAN><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  rc = ls.end(loss_host);
+  if (e != cudaSuccess) return cuda_fail(e, "smooth_kernel");
+  return rc;
+}
+
+extern "C" int b2f_constvel_criterion(const float* f, const float* b, int B, int C, int h, int w,
+                                      int size_average, float* grad_f, float* grad_b, double* loss_dev,
+                                      double* loss_host, b2f_stream_t stream) {
+  if (!f || !b) return fail(B2F_EINVAL, "constvel: NULL input");
+  if (B <= 0 || C <= 0 || h <= 0 || w <= 0) return fail(B2F_EINVAL, "constvel: bad size");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
+  int blocks;
+  int rc = blocks_for_pixels(npix, &blocks);
+  if (rc) return rc;
+  // forward: 1/nElement (ConstVelCriterion.lua:33, 41-43); backward: 1/npixels (:58, 69-72)  (Q11)
+  const double scale = size_average ? 1.0 / ((double)npix * C) : 1.0;
+  const float gnorm = size_average ? (float)(1.0 / (double)npix) : 1.f;
+  LossScratch ls;
+  if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
+  constvel_kernel<<<blocks, kThreads, 0, st>>>(f, b, grad_f, grad_b, B, C, hw, gnorm, ls.lo);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  rc = ls.end(loss_host);
+  if (e != cudaSuccess) return cuda_fail(e, "constvel_kernel");
+  return rc;
+}
+
+extern "C" int b2f_occprior_criterion(const float* occ, int B, int C, int h, int w, float penalty,
+                                      int size_average, float* grad, double* loss_dev, double* loss_host,
+                                      b2f_stream_t stream) {
+  if (!occ) return fail(B2F_EINVAL, "occprior: NULL input");
+  if (B <= 0 || h <= 0 || w <= 0) return fail(B2F_EINVAL, "occprior: bad size");
+  if (C != 2 && C != 3) return fail(B2F_EINVAL, "occprior: C=%d, expected 2 or 3", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
+  int blocks;
+  int rc = blocks_for_pixels(npix, &blocks);
+  if (rc) return rc;
+  const double scale = size_average ? 1.0 / (double)npix : 1.0;
+  LossScratch ls;
+  if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
+  occprior_kernel<<<blocks, kThreads, 0, st>>>(occ, grad, B, C, hw, penalty, (float)scale, ls.lo);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  rc = ls.end(loss_host);
+  if (e != cudaSuccess) return cuda_fail(e, "occprior_kernel");
+  return rc;
+}

@@ -1,0 +1,170 @@
+/* libb2f_cuda.so -- C ABI of the B200-native Back2Future hot path.
+ *
+ * Drop-in boundary for the reference's Torch7 nn.Module / nn.Criterion surface on this path
+ * (SURVEY.md section 8b).  Plain C symbols, raw DEVICE pointers + explicit sizes/strides + an
+ * explicit stream in, int status out.  No torch / THC / Lua types.  All tensors are fp32.
+ *
+ * Conventions
+ *   - Every entry returns B2F_OK (0), a negative B2F_E* code for a rejected argument, or a
+ *     positive cudaError_t.  Nothing throws, exits or longjmps across the ABI; the host shim
+ *     turns a non-zero status into error()/an exception using b2f_last_error().
+ *   - The caller owns every buffer.  The library owns only a small per-thread scratch for loss
+ *     partials (released by b2f_release_scratch()) and a per-thread cache of TMA descriptors.
+ *   - Re-entrant; the only mutable state is thread-local.  Work is enqueued on `stream` of the
+ *     calling thread's current device and is asynchronous, except that criterion entries
+ *     synchronise the stream when `loss_host` is non-NULL (the reference's criterions return
+ *     a Lua number, i.e. they synchronise too).
+ *   - Layouts follow the reference: feature maps and criterion tensors are BDHW (B,C,h,w)
+ *     contiguous; sampler images are BHWD (B,H,W,C) contiguous; sampler grids are (B,Hg,Wg,2)
+ *     with channel 0 = x offset, channel 1 = y offset, in pixels.
+ *
+ * Citations are relative to the reference repository root.
+ */
+#ifndef B2F_H_
+#define B2F_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B2F_API __attribute__((visibility("default")))
+#else
+#define B2F_API
+#endif
+
+typedef struct CUstream_st* b2f_stream_t; /* == cudaStream_t */
+
+enum {
+  B2F_OK = 0,
+  B2F_EINVAL = -1,      /* bad size / flag / NULL pointer                                   */
+  B2F_EUNSUPPORTED = -2, /* valid in the reference but not implemented (see message)         */
+  B2F_ENOMEM = -3,      /* scratch allocation failed                                        */
+  B2F_EALIGN = -4       /* pointer not 4-byte aligned                                       */
+};
+
+/* penalty functions, criterions/penalty/{quadratic,L1,Lorentzian}_function.lua */
+enum {
+  B2F_PENALTY_QUADRATIC = 0,  /* x^2, 2x                                                     */
+  B2F_PENALTY_L1 = 1,         /* sqrt(x^2+1e-6), x/sqrt(x^2+1e-6)  (exponent is always 0.5)  */
+  B2F_PENALTY_LORENTZIAN = 2  /* log(1+x^2/(2 eps^2)), 2x/(x^2+2 eps^2); eps = penalty_eps   */
+};
+
+/* ---- library ------------------------------------------------------------------------- */
+B2F_API int b2f_abi_version(void);
+B2F_API const char* b2f_last_error(void);          /* thread-local, never NULL                      */
+B2F_API const char* b2f_status_string(int status);
+B2F_API int b2f_release_scratch(void);             /* frees this thread's scratch on the current device */
+/* Test hook selecting the cost-volume kernel family (thread-local; returns the previous mode):
+ * 0 = automatic (default), 1 = generic direct kernels, 2/3/4 = the tiled TMA kernels whenever
+ * their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the grid-size
+ * heuristics, with forward strip width 16/8/4 pixels.                                       */
+B2F_API int b2f_debug_costvol_path(int mode);
+/* Number of kernels (not memsets/copies) this thread has launched through the library since
+ * the last reset; used by bench.py for its `gpu_launches` claim.                            */
+B2F_API int64_t b2f_launch_count(int reset);
+
+/* ---- nn.CostVolMulti  (models/CostVolMulti.lua) ----------------------------------------
+ * frames[0] is the reference map, frames[1..F-1] the other maps; each (B,C,H,W) contiguous.
+ * out (B, win*win, H, W): element stride between batch items is out_batch_stride (0 means
+ * win*win*H*W), which lets both directions write straight into a 162-channel buffer.
+ * Channel index is x-major: i = (qx+n)*win + (qy+n), n=(win-1)/2; source pixel is
+ * p - s*(f)*q with s=+1 for fwd!=0, -1 for fwd==0; normaliser 1/(C*(F-1)) everywhere.
+ * Replaces CostVolMulti:updateOutput (CostVolMulti.lua:49-109).  `frames` is a HOST array
+ * of device pointers.  win must be odd.                                                   */
+B2F_API int b2f_costvol_forward(const float* const* frames, int F, int B, int C, int H, int W,
+                        int win, int fwd, float* out, int64_t out_batch_stride,
+                        b2f_stream_t stream);
+
+/* Replaces CostVolMulti:updateGradInput (CostVolMulti.lua:111-181).  gradOut is (B,win*win,H,W)
+ * with batch stride gradOut_batch_stride elements (0 = contiguous): in the model it is a
+ * narrow of the 162-channel JoinTable gradient (models/pwc.lua:267).  gradFrames[f] are
+ * overwritten (the reference zero-fills then accumulates); gradFrames[f] may be NULL for
+ * f >= 1 to skip that frame's gradient, gradFrames[0] may be NULL to skip the ref gradient. */
+B2F_API int b2f_costvol_backward(const float* const* frames, int F, int B, int C, int H, int W,
+                         int win, int fwd, const float* gradOut, int64_t gradOut_batch_stride,
+                         float* const* gradFrames, b2f_stream_t stream);
+
+/* ---- nn.BilinearSamplerBHWD  (extras/stnbhwd/BilinearSamplerBHWD.cu) --------------------
+ * Replaces cunn_BilinearSamplerBHWD_updateOutput (.cu:118-158 -> kernel :41-115):
+ * out[b,y,x,:] = bilinear(img[b], clamp(x+grid.x,0,W-1), clamp(y+grid.y,0,H-1)); a tap at
+ * index W (or H) reads 0.  img (B,H,W,C), grid (B,Hg,Wg,2), out (B,Hg,Wg,C).               */
+B2F_API int b2f_warp_bhwd_forward(const float* img, const float* grid, float* out,
+                          int B, int H, int W, int C, int Hg, int Wg, b2f_stream_t stream);
+
+/* Replaces cunn_BilinearSamplerBHWD_updateGradInput (.cu:313-365 -> kernel :161-307) and, with
+ * gradImg == NULL, ..._updateGradInputOnlyGrid (.cu:368-419).  Exactly like the reference's
+ * native entry, gradImg is ACCUMULATED into (atomic adds; the Lua wrapper zero-fills it first,
+ * BilinearSamplerBHWD.lua:99-102) and gradGrid is overwritten.  No clamp derivative.        */
+B2F_API int b2f_warp_bhwd_backward(const float* img, const float* grid, const float* gradOut,
+                           float* gradImg, float* gradGrid,
+                           int B, int H, int W, int C, int Hg, int Wg, b2f_stream_t stream);
+
+/* ---- criterions: one fused pass each, loss + gradients ---------------------------------
+ * Loss delivery (all criterion entries): the scalar is accumulated in double; it is written
+ * to *loss_dev (device double, may be NULL) asynchronously, and if loss_host != NULL the
+ * stream is synchronised and the value stored there.  Gradient outputs may be NULL to skip
+ * them (forward only).  size_average mirrors the Lua field `sizeAverage`.                  */
+
+typedef struct b2f_ob_params {
+  int gradient_terms;     /* 0 = OBCC (OBCCriterion.lua), 1 = OBGCC (OBGCCriterion.lua)      */
+  int penalty;            /* B2F_PENALTY_*  (field `p`)                                      */
+  float penalty_eps;      /* Lorentzian eps (0.05 default)                                   */
+  float penalty_out;      /* field `penalty_out`                                             */
+  float alpha, beta, gamma; /* OBGCC weights; alpha is backward-only, as in the reference    */
+  float pwc_flow_scaling; /* field `pwc_flow_scaling` (train.lua:425)                        */
+  int past_flow;          /* field `past_flow`: past frame uses `bflow` for its mask         */
+  int grad_check;         /* field `gradCheck`: non-zero skips the out-of-image mask         */
+  int size_average;       /* field `sizeAverage`                                             */
+} b2f_ob_params;
+
+/* Occlusion-aware photometric criterion for F = 3 frames (two warped frames), the only
+ * configuration the model produces; other F return B2F_EUNSUPPORTED.
+ * flow,bflow,occ (B,2,h,w); warp_past, warp_future, target (B,C,h,w).  bflow may be NULL
+ * unless past_flow.  Outputs: grad_occ (B,2,h,w), grad_warp_past/future (B,C,h,w).
+ * Replaces OBCCriterion:updateOutput+updateGradInput (OBCCriterion.lua:36-240) and
+ * OBGCCriterion (OBGCCriterion.lua:39-300).  No flow gradient exists in the reference.     */
+B2F_API int b2f_ob_criterion(const b2f_ob_params* prm,
+                     const float* flow, const float* bflow, const float* occ,
+                     const float* warp_past, const float* warp_future, const float* target,
+                     int B, int C, int h, int w,
+                     float* grad_occ, float* grad_warp_past, float* grad_warp_future,
+                     double* loss_dev, double* loss_host, b2f_stream_t stream);
+
+typedef struct b2f_smooth_params {
+  int order;              /* 1 = SmoothnessCriterion, 2 = SecondOrderSmoothnessCriterion      */
+  int penalty;            /* B2F_PENALTY_*                                                    */
+  float penalty_eps;
+  float cs;               /* field `cs` (20)                                                  */
+  int size_average;
+  int alias_weights;      /* order 1 only: 1 = reproduce the Torch7 view-resize aliasing of the
+                             edge weights (SmoothnessCriterion.lua:49-59; parity
+                             default), 0 = the intended weights                              */
+} b2f_smooth_params;
+
+/* input (B,Cin,h,w) -- flow or occlusion map; target (B,Ct,h,w).  grad (B,Cin,h,w) or NULL.
+ * Replaces SmoothnessCriterion.lua:28-106 / SecondOrderSmoothnessCriterion.lua:28-104.       */
+B2F_API int b2f_smoothness_criterion(const b2f_smooth_params* prm, const float* input,
+                             const float* target, int B, int Cin, int Ct, int h, int w,
+                             float* grad, double* loss_dev, double* loss_host,
+                             b2f_stream_t stream);
+
+/* ConstVelCriterion.lua:29-74.  f,b (B,C,h,w) future / past flow; grads like inputs or NULL. */
+B2F_API int b2f_constvel_criterion(const float* f, const float* b, int B, int C, int h, int w,
+                           int size_average, float* grad_f, float* grad_b,
+                           double* loss_dev, double* loss_host, b2f_stream_t stream);
+
+/* OcclusionPriorCriterion.lua:28-73.  occ (B,C,h,w) with C = 2 or 3.                         */
+B2F_API int b2f_occprior_criterion(const float* occ, int B, int C, int h, int w, float penalty,
+                           int size_average, float* grad,
+                           double* loss_dev, double* loss_host, b2f_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H_ */

@@ -1,0 +1,532 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes on libb2f_cuda.so), against the
+CPU oracle on the same seeded inputs.
+
+Tolerance (north_star): 1e-4 relative for fp32 values and gradients, measured as
+max|a-b| / max(|b|, rms(b)); hard masks identical.  The oracle runs in float64 so the
+comparison measures the kernel's own rounding, not the oracle's.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import b2f_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def env(cuda_lib):
+    import torch
+    from back2future_b200 import _lib
+
+    class Env:
+        lib = cuda_lib
+        dev = torch.device("cuda:0")
+
+        @staticmethod
+        def t(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(Env.dev)
+
+        @staticmethod
+        def stream():
+            return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        @staticmethod
+        def p(x):
+            return C.c_void_p(x.data_ptr()) if x is not None else None
+
+        check = staticmethod(_lib.check)
+        ptr_array = staticmethod(_lib.ptr_array)
+        torch_ = torch
+        _lib_ = _lib
+    torch.cuda.set_device(0)
+    return Env
+
+
+def rng(seed=2):
+    return np.random.default_rng(seed)
+
+
+# ---------------------------------------------------------------------------------------
+# cost volume
+# ---------------------------------------------------------------------------------------
+
+def _costvol_fwd(env, frames, win, fwd, wide=False):
+    torch = env.torch_
+    B, Cn, h, w = frames[0].shape
+    ft = [env.t(f) for f in frames]
+    ww = win * win
+    if wide:   # write into one half of a 2*win^2-channel buffer (JoinTable elimination)
+        buf = torch.full((B, 2 * ww, h, w), float("nan"), device=env.dev)
+        out = buf[:, ww:]
+        obs = buf.stride(0)
+    else:
+        out = torch.full((B, ww, h, w), float("nan"), device=env.dev)
+        obs = 0
+    env.check(env.lib.b2f_costvol_forward(env.ptr_array([t.data_ptr() for t in ft]), len(ft), B, Cn, h, w,
+                                          win, int(fwd), env.p(out), obs, env.stream()))
+    torch.cuda.synchronize()
+    if wide:
+        assert torch.isnan(buf[:, :ww]).all(), "wrote outside its half of the wide buffer"
+    return out.cpu().numpy()
+
+
+def _costvol_bwd(env, frames, go_wide, sl, win, fwd, skip=()):
+    torch = env.torch_
+    B, Cn, h, w = frames[0].shape
+    ft = [env.t(f) for f in frames]
+    gw = env.t(go_wide)
+    go = gw[:, sl]
+    grads = [None if k in skip else torch.full_like(ft[k], float("nan")) for k in range(len(ft))]
+    env.check(env.lib.b2f_costvol_backward(env.ptr_array([t.data_ptr() for t in ft]), len(ft), B, Cn, h, w,
+                                           win, int(fwd), env.p(go), gw.stride(0),
+                                           env.ptr_array([g.data_ptr() if g is not None else None for g in grads]),
+                                           env.stream()))
+    torch.cuda.synchronize()
+    return [g.cpu().numpy() if g is not None else None for g in grads]
+
+
+# (path mode, B, C, h, w): every tiled variant on ragged tiles (h % 8 != 0, w % TW != 0, C % 8 != 0)
+TILED_CASES = [
+    (2, 2, 32, 16, 128), (2, 1, 20, 13, 72), (3, 2, 32, 16, 64), (3, 1, 12, 9, 44), (4, 2, 24, 14, 32),
+    (4, 1, 7, 7, 16), (4, 1, 3, 5, 4),
+]
+
+
+@pytest.mark.parametrize("mode,B,Cn,h,w", TILED_CASES)
+@pytest.mark.parametrize("fwd", [True, False])
+def test_costvol_forward_tiled(env, mode, B, Cn, h, w, fwd):
+    r = rng()
+    frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(2)]
+    env.lib.b2f_debug_costvol_path(mode)
+    try:
+        out = _costvol_fwd(env, frames, 9, fwd, wide=True)
+    finally:
+        env.lib.b2f_debug_costvol_path(0)
+    assert o.rel_err(out, o.costvol_forward(frames, 9, fwd)) < TOL
+
+
+@pytest.mark.parametrize("win,F,B,Cn,h,w", [(9, 2, 2, 16, 11, 13), (5, 3, 1, 6, 12, 15), (3, 4, 2, 5, 8, 9),
+                                            (9, 2, 1, 192, 7, 16), (1, 2, 1, 4, 3, 3)])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_costvol_forward_generic(env, win, F, B, Cn, h, w, fwd):
+    r = rng(3)
+    frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(F)]
+    env.lib.b2f_debug_costvol_path(1)
+    try:
+        out = _costvol_fwd(env, frames, win, fwd)
+    finally:
+        env.lib.b2f_debug_costvol_path(0)
+    assert o.rel_err(out, o.costvol_forward(frames, win, fwd)) < TOL
+
+
+@pytest.mark.parametrize("B,Cn,h,w", [(2, 32, 16, 64), (1, 40, 13, 36), (2, 8, 7, 16), (1, 70, 9, 100), (1, 3, 5, 4)])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_costvol_backward_tiled(env, B, Cn, h, w, fwd):
+    r = rng(4)
+    frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(2)]
+    wide = r.standard_normal((B, 162, h, w)).astype(np.float32)
+    sl = slice(0, 81) if fwd else slice(81, 162)
+    env.lib.b2f_debug_costvol_path(2)
+    try:
+        grads = _costvol_bwd(env, frames, wide, sl, 9, fwd)
+        only_ref = _costvol_bwd(env, frames, wide, sl, 9, fwd, skip=(1,))
+        only_frm = _costvol_bwd(env, frames, wide, sl, 9, fwd, skip=(0,))
+    finally:
+        env.lib.b2f_debug_costvol_path(0)
+    ref = o.costvol_backward(frames, wide[:, sl], 9, fwd)
+    assert o.rel_err(grads[0], ref[0]) < TOL and o.rel_err(grads[1], ref[1]) < TOL
+    assert np.array_equal(only_ref[0], grads[0]) and only_ref[1] is None
+    assert np.array_equal(only_frm[1], grads[1]) and only_frm[0] is None
+
+
+@pytest.mark.parametrize("win,F,B,Cn,h,w", [(9, 2, 1, 8, 11, 13), (5, 3, 1, 6, 12, 15), (3, 4, 2, 5, 8, 9)])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_costvol_backward_generic(env, win, F, B, Cn, h, w, fwd):
+    r = rng(5)
+    frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(F)]
+    ww = win * win
+    wide = r.standard_normal((B, 2 * ww, h, w)).astype(np.float32)
+    env.lib.b2f_debug_costvol_path(1)
+    try:
+        grads = _costvol_bwd(env, frames, wide, slice(ww, 2 * ww), win, fwd)
+    finally:
+        env.lib.b2f_debug_costvol_path(0)
+    ref = o.costvol_backward(frames, wide[:, ww:], win, fwd)
+    for a, b in zip(grads, ref):
+        assert o.rel_err(a, b) < TOL
+
+
+def test_costvol_auto_dispatch_level_shapes(env):
+    """The automatic dispatch at the model's pyramid shapes for a 256x128 input (levels 3..7),
+    both directions, forward + backward."""
+    r = rng(6)
+    for Cn, h, w in [(32, 32, 64), (64, 16, 32), (96, 8, 16), (128, 4, 8), (192, 2, 4)]:
+        frames = [r.standard_normal((4, Cn, h, w)).astype(np.float32) for _ in range(2)]
+        wide = r.standard_normal((4, 162, h, w)).astype(np.float32)
+        for fwd, sl in ((True, slice(0, 81)), (False, slice(81, 162))):
+            out = _costvol_fwd(env, frames, 9, fwd)
+            assert o.rel_err(out, o.costvol_forward(frames, 9, fwd)) < TOL
+            grads = _costvol_bwd(env, frames, wide, sl, 9, fwd)
+            ref = o.costvol_backward(frames, wide[:, sl], 9, fwd)
+            assert o.rel_err(grads[0], ref[0]) < TOL and o.rel_err(grads[1], ref[1]) < TOL
+
+
+def test_costvol_delta_kat(env):
+    """Derived known-answer test (models/CostVolMulti.lua:225-254 with two frames)."""
+    ref = np.zeros((1, 1, 8, 8), np.float32)
+    frm = np.zeros((1, 1, 8, 8), np.float32)
+    ref[0, 0, 3, 3] = 1
+    frm[0, 0, 4, 5] = 1   # source = p - q  ->  q = (qx, qy) = (-2, -1)
+    for mode in (1, 4):
+        env.lib.b2f_debug_costvol_path(mode)
+        try:
+            out = _costvol_fwd(env, [ref, frm], 9, True)
+        finally:
+            env.lib.b2f_debug_costvol_path(0)
+        nz = np.argwhere(out != 0).tolist()
+        assert nz == [[0, (-2 + 4) * 9 + (-1 + 4), 3, 3]] and out[0, nz[0][1], 3, 3] == 1.0
+
+
+def test_costvol_full_size_properties(env):
+    """BASELINE config 2, level 3 (B=8, C=32, 112x256): adjointness <fwd(x), g> == <x, bwd(g)>
+    (the map is bilinear in (ref, frame)), tiled vs generic agreement, and a direct oracle check of
+    one batch item."""
+    torch = env.torch_
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, Cn, h, w = 8, 32, 112, 256
+    ref = torch.randn((B, Cn, h, w), device=env.dev, generator=g)
+    frm = torch.randn((B, Cn, h, w), device=env.dev, generator=g)
+    go = torch.randn((B, 162, h, w), device=env.dev, generator=g)
+    for fwd, sl in ((True, slice(0, 81)), (False, slice(81, 162))):
+        outs = {}
+        grads = {}
+        for mode in (0, 1):
+            env.lib.b2f_debug_costvol_path(mode)
+            try:
+                out = torch.empty((B, 81, h, w), device=env.dev)
+                env.check(env.lib.b2f_costvol_forward(env.ptr_array([ref.data_ptr(), frm.data_ptr()]), 2, B, Cn, h, w,
+                                                      9, int(fwd), env.p(out), 0, env.stream()))
+                gr, gf = torch.empty_like(ref), torch.empty_like(frm)
+                env.check(env.lib.b2f_costvol_backward(env.ptr_array([ref.data_ptr(), frm.data_ptr()]), 2, B, Cn, h, w,
+                                                       9, int(fwd), env.p(go[:, sl]), go.stride(0),
+                                                       env.ptr_array([gr.data_ptr(), gf.data_ptr()]), env.stream()))
+            finally:
+                env.lib.b2f_debug_costvol_path(0)
+            torch.cuda.synchronize()
+            outs[mode], grads[mode] = out, (gr, gf)
+        assert o.rel_err(outs[0].cpu().numpy(), outs[1].cpu().numpy()) < TOL
+        assert o.rel_err(grads[0][0].cpu().numpy(), grads[1][0].cpu().numpy()) < TOL
+        assert o.rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < TOL
+        # bilinear map: <out, go> = <ref, gradRef> = <frame, gradFrame>
+        lhs = (outs[0].double() * go[:, sl].double()).sum().item()
+        assert abs(lhs - (ref.double() * grads[0][0].double()).sum().item()) < 1e-5 * abs(lhs) + 1e-3
+        assert abs(lhs - (frm.double() * grads[0][1].double()).sum().item()) < 1e-5 * abs(lhs) + 1e-3
+        rb, fb = ref[:1].cpu().numpy(), frm[:1].cpu().numpy()
+        assert o.rel_err(outs[0][:1].cpu().numpy(), o.costvol_forward([rb, fb], 9, fwd)) < TOL
+
+
+def test_costvol_argument_errors(env):
+    lib = env.lib
+    x = env.t(np.zeros((1, 2, 4, 4)))
+    ptrs = env.ptr_array([x.data_ptr(), x.data_ptr()])
+    out = env.t(np.zeros((1, 81, 4, 4)))
+    assert lib.b2f_costvol_forward(ptrs, 2, 1, 2, 4, 4, 8, 1, env.p(out), 0, env.stream()) == -1   # even window
+    assert b"odd" in lib.b2f_last_error()
+    assert lib.b2f_costvol_forward(ptrs, 1, 1, 2, 4, 4, 9, 1, env.p(out), 0, env.stream()) == -1   # F < 2
+    assert lib.b2f_costvol_forward(ptrs, 2, 1, 2, 4, 4, 9, 1, None, 0, env.stream()) == -1
+    assert lib.b2f_costvol_forward(ptrs, 2, 0, 2, 4, 4, 9, 1, env.p(out), 0, env.stream()) == 0    # empty batch
+
+
+# ---------------------------------------------------------------------------------------
+# sampler
+# ---------------------------------------------------------------------------------------
+
+def _warp(env, img, grid, go, only_grid=False):
+    torch = env.torch_
+    B, H, W, Cn = img.shape
+    _, Hg, Wg, _ = grid.shape
+    ti, tg, tgo = env.t(img), env.t(grid), env.t(go)
+    out = torch.full((B, Hg, Wg, Cn), float("nan"), device=env.dev)
+    env.check(env.lib.b2f_warp_bhwd_forward(env.p(ti), env.p(tg), env.p(out), B, H, W, Cn, Hg, Wg, env.stream()))
+    gi = None if only_grid else torch.zeros_like(ti)
+    gg = torch.full_like(tg, float("nan"))
+    env.check(env.lib.b2f_warp_bhwd_backward(env.p(ti), env.p(tg), env.p(tgo), env.p(gi), env.p(gg),
+                                             B, H, W, Cn, Hg, Wg, env.stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), (None if gi is None else gi.cpu().numpy()), gg.cpu().numpy()
+
+
+@pytest.mark.parametrize("B,H,W,Cn,sigma", [
+    (2, 14, 32, 128, 4.0), (2, 28, 64, 96, 4.0), (1, 17, 23, 32, 0.5), (2, 9, 11, 3, 4.0), (1, 33, 65, 3, 0.5),
+    (1, 6, 7, 5, 2.0), (1, 5, 6, 1, 2.0), (1, 4, 5, 4, 30.0), (3, 1, 1, 8, 1.0), (1, 16, 16, 192, 3.0),
+])
+def test_warp_forward_backward(env, B, H, W, Cn, sigma):
+    r = rng(7)
+    img = r.standard_normal((B, H, W, Cn)).astype(np.float32)
+    grid = (r.standard_normal((B, H, W, 2)) * sigma).astype(np.float32)
+    go = r.standard_normal((B, H, W, Cn)).astype(np.float32)
+    out, gi, gg = _warp(env, img, grid, go)
+    rgi, rgg = o.warp_backward(img, grid, go)
+    assert o.rel_err(out, o.warp_forward(img, grid)) < TOL
+    assert o.rel_err(gi, rgi) < TOL
+    assert o.rel_err(gg, rgg) < TOL
+    _, gi2, gg2 = _warp(env, img, grid, go, only_grid=True)
+    assert gi2 is None and np.array_equal(gg2, gg)
+
+
+def test_warp_grid_smaller_than_image_and_integer_coordinates(env):
+    """Hg,Wg != H,W; exact-integer and exactly-on-the-border coordinates (floor / clamp are evaluated
+    with the reference's fp32 operations, so the chosen cell -- hence the flow gradient -- matches)."""
+    r = rng(8)
+    img = r.standard_normal((2, 9, 12, 8)).astype(np.float32)
+    grid = np.round(r.standard_normal((2, 5, 7, 2)) * 3).astype(np.float32)
+    grid[0, 0, 0] = (11.0, 8.0)
+    grid[0, 1, 1] = (-1e-8, 1e-8)
+    go = r.standard_normal((2, 5, 7, 8)).astype(np.float32)
+    out, gi, gg = _warp(env, img, grid, go)
+    rgi, rgg = o.warp_backward(img, grid, go)
+    assert o.rel_err(out, o.warp_forward(img, grid)) < TOL
+    assert o.rel_err(gi, rgi) < TOL and o.rel_err(gg, rgg) < TOL
+
+
+def test_warp_identity_kat(env):
+    img = rng(9).standard_normal((1, 6, 8, 3)).astype(np.float32)
+    zero = np.zeros((1, 6, 8, 2), np.float32)
+    out, _, _ = _warp(env, img, zero, np.zeros_like(img))
+    assert np.array_equal(out, img)
+    shift = zero.copy()
+    shift[..., 0] = 2
+    out, _, _ = _warp(env, img, shift, np.zeros_like(img))
+    assert np.array_equal(out[:, :, :6], img[:, :, 2:]) and np.array_equal(out[:, :, 7], img[:, :, 7])
+
+
+def test_warp_full_size_image_adjoint(env):
+    """BASELINE config 2 finest image warp (B=8, 448x1024, C=3): gradImg is the adjoint of the forward
+    (linear in img), checked with a random probe; plus an oracle check on one batch item."""
+    torch = env.torch_
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, H, W, Cn = 8, 448, 1024, 3
+    img = torch.randn((B, H, W, Cn), device=env.dev, generator=g)
+    probe = torch.randn((B, H, W, Cn), device=env.dev, generator=g)
+    grid = torch.randn((B, H, W, 2), device=env.dev, generator=g) * 4
+    go = torch.randn((B, H, W, Cn), device=env.dev, generator=g)
+    out = torch.empty_like(img)
+    outp = torch.empty_like(img)
+    gi = torch.zeros_like(img)
+    gg = torch.empty_like(grid)
+    L = env.lib
+    env.check(L.b2f_warp_bhwd_forward(env.p(img), env.p(grid), env.p(out), B, H, W, Cn, H, W, env.stream()))
+    env.check(L.b2f_warp_bhwd_forward(env.p(probe), env.p(grid), env.p(outp), B, H, W, Cn, H, W, env.stream()))
+    env.check(L.b2f_warp_bhwd_backward(env.p(img), env.p(grid), env.p(go), env.p(gi), env.p(gg), B, H, W, Cn, H, W,
+                                       env.stream()))
+    torch.cuda.synchronize()
+    lhs = (outp.double() * go.double()).sum().item()
+    rhs = (probe.double() * gi.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs) + 1e-2
+    ib, gb, gob = img[:1].cpu().numpy(), grid[:1].cpu().numpy(), go[:1].cpu().numpy()
+    assert o.rel_err(out[:1].cpu().numpy(), o.warp_forward(ib, gb)) < TOL
+    rgi, rgg = o.warp_backward(ib, gb, gob)
+    assert o.rel_err(gi[:1].cpu().numpy(), rgi) < TOL and o.rel_err(gg[:1].cpu().numpy(), rgg) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# criterions
+# ---------------------------------------------------------------------------------------
+
+def _ob_inputs(r, B, Cn, h, w, sigma):
+    flow = (r.standard_normal((B, 2, h, w)) * sigma).astype(np.float32)
+    bflow = (r.standard_normal((B, 2, h, w)) * sigma).astype(np.float32)
+    e = np.exp(r.standard_normal((B, 2, h, w)))
+    occ = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    w1, w2, tgt = (r.uniform(-2.1, 2.6, (B, Cn, h, w)).astype(np.float32) for _ in range(3))
+    return flow, bflow, occ, w1, w2, tgt
+
+
+def _run_ob(env, prm_kw, flow, bflow, occ, w1, w2, tgt):
+    torch = env.torch_
+    L = env._lib_
+    B, Cn, h, w = tgt.shape
+    prm = L.ObParams(**prm_kw)
+    tf, tb, to, t1, t2, tt = (env.t(a) for a in (flow, bflow, occ, w1, w2, tgt))
+    g_occ = torch.full_like(to, float("nan"))
+    g1, g2 = torch.full_like(t1, float("nan")), torch.full_like(t2, float("nan"))
+    loss_dev = torch.zeros(1, dtype=torch.float64, device=env.dev)
+    host = C.c_double(0)
+    env.check(env.lib.b2f_ob_criterion(C.byref(prm), env.p(tf), env.p(tb), env.p(to), env.p(t1), env.p(t2), env.p(tt),
+                                       B, Cn, h, w, env.p(g_occ), env.p(g1), env.p(g2), env.p(loss_dev),
+                                       C.byref(host), env.stream()))
+    assert loss_dev.item() == host.value
+    return host.value, g_occ.cpu().numpy(), g1.cpu().numpy(), g2.cpu().numpy()
+
+
+@pytest.mark.parametrize("gt", [0, 1])
+@pytest.mark.parametrize("pen", [0, 1, 2])
+@pytest.mark.parametrize("past_flow,size_avg,scale", [(0, 0, 20.0), (1, 1, 2.5)])
+def test_ob_criterion(env, gt, pen, past_flow, size_avg, scale):
+    r = rng(10)
+    B, Cn, h, w = 3, 3, 20, 40
+    flow, bflow, occ, w1, w2, tgt = _ob_inputs(r, B, Cn, h, w, 0.4)
+    kw = dict(gradient_terms=gt, penalty=pen, penalty_eps=0.05, penalty_out=1.0, alpha=0.0 if gt else 1.0,
+              beta=1.0, gamma=1.0, pwc_flow_scaling=scale, past_flow=past_flow, grad_check=0, size_average=size_avg)
+    loss, g_occ, g1, g2 = _run_ob(env, kw, flow, bflow, occ, w1, w2, tgt)
+    oc = o.OBCriterionOracle(bool(gt), o.make_penalty(pen), past_flow=bool(past_flow), pwc_flow_scaling=scale,
+                             size_average=bool(size_avg), alpha=kw["alpha"])
+    bf = bflow if past_flow else None
+    ref_loss = oc.forward(flow, bf, occ, [w1, w2], tgt)
+    ro, rw = oc.backward(flow, bf, occ, [w1, w2], tgt)
+    assert abs(loss - ref_loss) < TOL * abs(ref_loss)
+    assert o.rel_err(g_occ, ro) < TOL and o.rel_err(g1, rw[0]) < TOL and o.rel_err(g2, rw[1]) < TOL
+    # hard masks are identical: masked-out pixels have exactly zero warped-frame gradient
+    m_past = o.out_of_image_mask(bflow if past_flow else flow, -1, scale)
+    m_fut = o.out_of_image_mask(flow, 1, scale)
+    assert np.array_equal(np.all(g1 == 0, axis=1) | m_past, np.ones_like(m_past))
+    assert np.array_equal(~np.all(g1 == 0, axis=1), m_past & ~np.all(rw[0] == 0, axis=1))
+    assert np.array_equal(~np.all(g2 == 0, axis=1), m_fut & ~np.all(rw[1] == 0, axis=1))
+    assert 0 < (~m_fut).sum() < m_fut.size
+
+
+def test_ob_criterion_gradcheck_and_weights(env):
+    r = rng(11)
+    flow, bflow, occ, w1, w2, tgt = _ob_inputs(r, 2, 3, 9, 13, 5.0)
+    kw = dict(gradient_terms=1, penalty=1, penalty_eps=0.05, penalty_out=0.3, alpha=0.6, beta=0.7, gamma=1.3,
+              pwc_flow_scaling=5.0, past_flow=0, grad_check=1, size_average=0)
+    loss, g_occ, g1, g2 = _run_ob(env, kw, flow, bflow, occ, w1, w2, tgt)
+    oc = o.OBCriterionOracle(True, o.L1Penalty(), pwc_flow_scaling=5.0, size_average=False, penalty_out=0.3,
+                             alpha=0.6, beta=0.7, gamma=1.3, grad_check=True)
+    assert abs(loss - oc.forward(flow, None, occ, [w1, w2], tgt)) < TOL * abs(loss)
+    ro, rw = oc.backward(flow, None, occ, [w1, w2], tgt)
+    assert o.rel_err(g_occ, ro) < TOL and o.rel_err(g1, rw[0]) < TOL and o.rel_err(g2, rw[1]) < TOL
+    kw["grad_check"] = 0
+    loss2, g_occ2, _, _ = _run_ob(env, kw, flow, bflow, occ, w1, w2, tgt)
+    oc.gradCheck = False
+    assert abs(loss2 - oc.forward(flow, None, occ, [w1, w2], tgt)) < TOL * abs(loss2)
+    assert o.rel_err(g_occ2, oc.backward(flow, None, occ, [w1, w2], tgt)[0]) < TOL
+
+
+def _run_smooth(env, order, pen, size_avg, alias, x, tgt, cs=20.0, eps=0.05):
+    torch = env.torch_
+    L = env._lib_
+    B, Cin, h, w = x.shape
+    prm = L.SmoothParams(order, pen, eps, cs, size_avg, alias)
+    tx, tt = env.t(x), env.t(tgt)
+    g = torch.full_like(tx, float("nan"))
+    host = C.c_double(0)
+    env.check(env.lib.b2f_smoothness_criterion(C.byref(prm), env.p(tx), env.p(tt), B, Cin, tgt.shape[1], h, w,
+                                               env.p(g), None, C.byref(host), env.stream()))
+    host2 = C.c_double(0)   # forward-only call (no gradient buffer) gives the same loss
+    env.check(env.lib.b2f_smoothness_criterion(C.byref(prm), env.p(tx), env.p(tt), B, Cin, tgt.shape[1], h, w,
+                                               None, None, C.byref(host2), env.stream()))
+    assert host.value == host2.value
+    return host.value, g.cpu().numpy()
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("pen", [0, 1, 2])
+@pytest.mark.parametrize("B,h,w,alias,size_avg", [(3, 20, 40, 1, 0), (2, 7, 9, 0, 1), (1, 3, 3, 1, 0), (2, 2, 5, 1, 1)])
+def test_smoothness_criterion(env, order, pen, B, h, w, alias, size_avg):
+    r = rng(12)
+    x = r.standard_normal((B, 2, h, w)).astype(np.float32)
+    tgt = (r.uniform(-2.1, 2.6, (B, 3, h, w)) * 0.05).astype(np.float32)
+    loss, g = _run_smooth(env, order, pen, size_avg, alias, x, tgt)
+    oc = o.SmoothnessOracle(order, o.make_penalty(pen), size_average=bool(size_avg), alias=bool(alias))
+    ref = oc.forward(x, tgt)
+    assert abs(loss - ref) < TOL * abs(ref) + 1e-12
+    assert o.rel_err(g, oc.backward(x, tgt)) < TOL
+
+
+def test_smoothness_alias_differs_from_intended_and_same_channel_case(env):
+    r = rng(13)
+    x = r.standard_normal((2, 2, 8, 10)).astype(np.float32)
+    tgt = (r.uniform(-1, 1, (2, 3, 8, 10)) * 0.1).astype(np.float32)
+    la, _ = _run_smooth(env, 1, 1, 0, 1, x, tgt)
+    li, _ = _run_smooth(env, 1, 1, 0, 0, x, tgt)
+    assert la != li
+    tgt2 = tgt[:, :2].copy()     # Cin == Ct: no resize happens in Torch7, both variants coincide
+    la, ga = _run_smooth(env, 1, 1, 0, 1, x, tgt2)
+    li, gi = _run_smooth(env, 1, 1, 0, 0, x, tgt2)
+    assert la == li and np.array_equal(ga, gi)
+    oc = o.SmoothnessOracle(1, o.L1Penalty(), size_average=False, alias=True)
+    assert abs(la - oc.forward(x, tgt2)) < TOL * abs(la)
+
+
+@pytest.mark.parametrize("size_avg", [0, 1])
+def test_constvel_and_occprior(env, size_avg):
+    torch = env.torch_
+    r = rng(14)
+    B, h, w = 3, 10, 12
+    f = r.standard_normal((B, 2, h, w)).astype(np.float32)
+    b = r.standard_normal((B, 2, h, w)).astype(np.float32)
+    b[0, :, 0, 0] = f[0, :, 0, 0]     # zero difference: 0/(0+1e-12) = 0
+    tf, tb = env.t(f), env.t(b)
+    gf, gb = torch.empty_like(tf), torch.empty_like(tb)
+    host = C.c_double(0)
+    env.check(env.lib.b2f_constvel_criterion(env.p(tf), env.p(tb), B, 2, h, w, size_avg, env.p(gf), env.p(gb), None,
+                                             C.byref(host), env.stream()))
+    ref = o.constvel_forward(f, b, bool(size_avg))
+    r1, r2 = o.constvel_backward(f, b, bool(size_avg))
+    assert abs(host.value - ref) < TOL * abs(ref)
+    assert o.rel_err(gf.cpu().numpy(), r1) < TOL and o.rel_err(gb.cpu().numpy(), r2) < TOL
+    for Cn in (2, 3):
+        occ = r.uniform(0, 1, (B, Cn, h, w)).astype(np.float32)
+        to = env.t(occ)
+        g = torch.empty_like(to)
+        env.check(env.lib.b2f_occprior_criterion(env.p(to), B, Cn, h, w, 1.0, size_avg, env.p(g), None, C.byref(host),
+                                                 env.stream()))
+        ref = o.occprior_forward(occ, bool(size_avg))
+        assert abs(host.value - ref) < TOL * abs(ref)
+        assert o.rel_err(g.cpu().numpy(), o.occprior_backward(occ, bool(size_avg))) < TOL
+
+
+def test_criterions_training_sizes(env):
+    """BASELINE config 3 / 4 finest level (B=8, 320x640): losses against the float64 oracle."""
+    r = rng(15)
+    B, h, w = 8, 320, 640
+    flow, bflow, occ, w1, w2, tgt = _ob_inputs(r, B, 3, h, w, 0.2)
+    for gt, pen in ((0, 1), (1, 1)):
+        kw = dict(gradient_terms=gt, penalty=pen, penalty_eps=0.05, penalty_out=1.0, alpha=0.0 if gt else 1.0, beta=1.0,
+                  gamma=1.0, pwc_flow_scaling=20.0, past_flow=gt, grad_check=0, size_average=0)
+        loss, g_occ, g1, g2 = _run_ob(env, kw, flow, bflow, occ, w1, w2, tgt)
+        oc = o.OBCriterionOracle(bool(gt), o.L1Penalty(), past_flow=bool(gt), pwc_flow_scaling=20.0, size_average=False,
+                                 alpha=kw["alpha"])
+        bf = bflow if gt else None
+        assert abs(loss - oc.forward(flow, bf, occ, [w1, w2], tgt)) < TOL * abs(loss)
+        ro, rw = oc.backward(flow, bf, occ, [w1, w2], tgt)
+        assert o.rel_err(g_occ, ro) < TOL and o.rel_err(g1, rw[0]) < TOL and o.rel_err(g2, rw[1]) < TOL
+    for order, inp in ((1, flow), (2, flow), (1, occ)):
+        pen = 1 if inp is flow else 0
+        loss, g = _run_smooth(env, order, pen, 0, 1, inp, tgt)
+        oc = o.SmoothnessOracle(order, o.make_penalty(pen), size_average=False)
+        assert abs(loss - oc.forward(inp, tgt)) < TOL * abs(loss)
+        assert o.rel_err(g, oc.backward(inp, tgt)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# host mirror (nn.*) -- the call a user of the reference makes
+# ---------------------------------------------------------------------------------------
+
+def test_nn_modules_end_to_end(env):
+    import __graft_entry__ as ge
+    ge.smoke()
+
+
+def test_nn_costvol_into_joined_buffer_and_clear_state(env):
+    torch = env.torch_
+    from back2future_b200 import nn as bnn
+    r = rng(16)
+    B, Cn, h, w = 2, 16, 16, 32
+    ref, past, fut = (r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(3))
+    joined = torch.empty((B, 162, h, w), device=env.dev)
+    f_mod, b_mod = bnn.CostVolMulti(9, True), bnn.CostVolMulti(9, False)
+    f_mod.updateOutput([env.t(ref), env.t(fut)], out=joined[:, :81])
+    b_mod.updateOutput([env.t(ref), env.t(past)], out=joined[:, 81:])
+    exp = np.concatenate([o.costvol_forward([ref, fut], 9, True), o.costvol_forward([ref, past], 9, False)], axis=1)
+    assert o.rel_err(joined.cpu().numpy(), exp) < TOL
+    f_mod.clearState()
+    assert f_mod.output.numel() == 0 and len(f_mod.gradInput) == 2
+    with pytest.raises(RuntimeError):
+        f_mod.forward([torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4)])   # CPU tensors: no fallback
+    with pytest.raises(AssertionError):
+        f_mod.forward([env.t(ref), env.t(fut[:, :8])])                        # "input sizes mismatch"
