@@ -75,6 +75,14 @@ int b2f_debug_costvol_path(int mode) {
   return prev;
 }
 
+int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream) {
+  if (!ptr && bytes) return b2f::fail(B2F_EINVAL, "zero_async: NULL pointer");
+  if (!bytes) return B2F_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return b2f::cuda_fail(e, "cudaMemsetAsync");
+  return B2F_OK;
+}
+
 int64_t b2f_launch_count(int reset) {
   int64_t v = b2f::g_launches;
   if (reset) b2f::g_launches = 0;

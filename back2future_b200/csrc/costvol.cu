@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_frm,
                 float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv) {
   using cfg = Cfg<A>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // pointer + integer offset keeps the shared address space (LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* stages = reinterpret_cast<float*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * cfg::STAGE_BYTES);
   uint64_t* empty = full + NS;
@@ -193,7 +194,7 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     mbar_wait(&full[s], it & 1);
     const float* rs = stages + s * cfg::STAGE_ELEMS + r * cfg::RW + A * st;
     const float* fs = stages + s * cfg::STAGE_ELEMS + cfg::REF_ELEMS + frow * cfg::FW + A * st;
-#pragma unroll 2
+#pragma unroll 1
     for (int cc = 0; cc < CK; ++cc) {
       float rv[A], fv[A + 8];
 #pragma unroll
@@ -217,6 +218,8 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   }
 
   // ---- epilogue: out[b, ix*9+iy, y, x0 + A*st + j] ----
+  // THC's div(scalar) multiplies floats by the reciprocal; so do we.
+  const float kinv = 1.f / kdiv;
   const int y = y0 + r;
   if (y < H) {
     const int64_t hw = (int64_t)H * W;
@@ -229,8 +232,8 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
       for (int q = 0; q < A / 4; ++q) {
         if (xb + 4 * q < W) {
           float4 v;
-          v.x = acc[ix][4 * q] / kdiv; v.y = acc[ix][4 * q + 1] / kdiv;
-          v.z = acc[ix][4 * q + 2] / kdiv; v.w = acc[ix][4 * q + 3] / kdiv;
+          v.x = acc[ix][4 * q] * kinv; v.y = acc[ix][4 * q + 1] * kinv;
+          v.z = acc[ix][4 * q + 2] * kinv; v.w = acc[ix][4 * q + 3] * kinv;
           *reinterpret_cast<float4*>(o + 4 * q) = v;
         }
       }
@@ -299,11 +302,12 @@ __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float* __res
 template <int SGN>
 __global__ void __launch_bounds__(THREADS, 2)
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
-                const __grid_constant__ CUtensorMap tm_go, float* __restrict__ grad_ref,
-                float* __restrict__ grad_frame, int nroles, int role0, int nchunk, int C, int H, int W,
-                float kdiv) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+                const __grid_constant__ CUtensorMap tm_go, const float* __restrict__ go_raw, int64_t gbs,
+                float* __restrict__ grad_ref, float* __restrict__ grad_frame, int nroles, int role0,
+                int nchunk, int C, int H, int W, float kdiv) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // pointer + integer offset keeps the shared address space (LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* xsm = reinterpret_cast<float*>(smem);
   float* gsm = xsm + X_ELEMS;
   uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (X_ELEMS + 2 * SLAB_ELEMS) * 4);
@@ -322,34 +326,71 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < NCW; ++i) mbar_init(&xfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&gfull[i], 1);
+      mbar_init(&gfull[i], role == 0 ? 1 : 32);   // role 1: one cp.async arrival per producer lane
       mbar_init(&gempty[i], NCW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == NCW) {  // ---- TMA producer ----
-    if (lane == 0) {
-      const CUtensorMap* tmx = (role == 0) ? &tm_frame : &tm_ref;
-      tma_prefetch_desc(tmx);
-      tma_prefetch_desc(&tm_go);
-      const int gshift = (role == 0) ? 0 : SGN;
+  if (warp == NCW) {  // ---- producer warp ----
+    // NOTE: tensor maps are addressed as kernel parameters at every use (a runtime-selected
+    // descriptor pointer is not a constant-bank address any more).
+    if (role == 0) {
+      // gradRef: gradOut boxes start at (x0, y0): aligned -> TMA
+      if (lane == 0) {
+        tma_prefetch_desc(&tm_go);
+        auto load_slab = [&](int iy) {
+          const int s = iy & 1;
+          float* dst = gsm + s * SLAB_ELEMS;
+          mbar_arrive_expect_tx(&gfull[s], SLAB_BYTES);
+#pragma unroll 1
+          for (int ix = 0; ix < 9; ++ix)
+            tma_load_4d(dst + ix * GBOX_ELEMS, &tm_go, x0, y0, ix * 9 + iy, b, &gfull[s]);
+        };
+        load_slab(0);
+        for (int w = 0; w < NCW; ++w) {
+          mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
+          tma_load_4d(xsm + w * XG_ELEMS, &tm_frame, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
+        }
+        load_slab(1);
+        for (int iy = 2; iy < 9; ++iy) {
+          mbar_wait(&gempty[iy & 1], ((iy >> 1) - 1) & 1);
+          load_slab(iy);
+        }
+      }
+    } else {
+      // gradFrame: the slab for displacement q is gradOut shifted by s*q.  Its x start is not a
+      // multiple of 4 elements, which TMA rejects, so the whole warp stages it with zero-filling
+      // 4-byte cp.async: lane = column, one 128-byte row per instruction.
+      const int64_t hw = (int64_t)H * W;
+      const float* gob = go_raw + (int64_t)b * gbs;
       auto load_slab = [&](int iy) {
         const int s = iy & 1;
-        float* dst = gsm + s * SLAB_ELEMS;
-        mbar_arrive_expect_tx(&gfull[s], SLAB_BYTES);
+        float* dst = gsm + s * SLAB_ELEMS + lane;
+        const int gy0 = y0 + SGN * (iy - 4);
 #pragma unroll 1
-        for (int ix = 0; ix < 9; ++ix)
-          tma_load_4d(dst + ix * GBOX_ELEMS, &tm_go, x0 + gshift * (ix - 4), y0 + gshift * (iy - 4),
-                      ix * 9 + iy, b, &gfull[s]);
+        for (int ix = 0; ix < 9; ++ix) {
+          const int gx = x0 + SGN * (ix - 4) + lane;
+          const bool xok = gx >= 0 && gx < W;
+          const float* ch = gob + (int64_t)(ix * 9 + iy) * hw + gx;
+#pragma unroll
+          for (int row = 0; row < TH; ++row) {
+            const int gy = gy0 + row;
+            const bool ok = xok && gy >= 0 && gy < H;
+            cp_async4_zfill(dst + ix * GBOX_ELEMS + row * GW, ok ? ch + (int64_t)gy * W : go_raw, ok);
+          }
+        }
+        cp_async_mbar_arrive_noinc(&gfull[s]);
       };
-      // first gradOut slab, then the X groups, then the pipeline
       load_slab(0);
-      for (int w = 0; w < NCW; ++w) {
-        mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
-        tma_load_4d(xsm + w * XG_ELEMS, tmx, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
+      if (lane == 0) {
+        for (int w = 0; w < NCW; ++w) {
+          mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
+          tma_load_4d(xsm + w * XG_ELEMS, &tm_ref, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
+        }
       }
+      __syncwarp();
       load_slab(1);
       for (int iy = 2; iy < 9; ++iy) {
         mbar_wait(&gempty[iy & 1], ((iy >> 1) - 1) & 1);
@@ -381,6 +422,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   }
 
   // ---- epilogue ----
+  const float kinv = 1.f / kdiv;
   float* outp = (role == 0) ? grad_ref : grad_frame;
   const int y = y0 + r;
   const int xb = x0 + 8 * st;
@@ -392,8 +434,8 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
       if (ch < C) {
         float* o = outp + ((int64_t)b * C + ch) * hw + (int64_t)y * W + xb;
         float4 v0, v1;
-        v0.x = acc[c][0] / kdiv; v0.y = acc[c][1] / kdiv; v0.z = acc[c][2] / kdiv; v0.w = acc[c][3] / kdiv;
-        v1.x = acc[c][4] / kdiv; v1.y = acc[c][5] / kdiv; v1.z = acc[c][6] / kdiv; v1.w = acc[c][7] / kdiv;
+        v0.x = acc[c][0] * kinv; v0.y = acc[c][1] * kinv; v0.z = acc[c][2] * kinv; v0.w = acc[c][3] * kinv;
+        v1.x = acc[c][4] * kinv; v1.y = acc[c][5] * kinv; v1.z = acc[c][6] * kinv; v1.w = acc[c][7] * kinv;
         *reinterpret_cast<float4*>(o) = v0;
         if (xb + 4 < W) *reinterpret_cast<float4*>(o + 4) = v1;
       }
@@ -564,10 +606,10 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
       dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
       if (sgn > 0)
         cvb::costvol_bwd_tma<1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+            tfrm, tref, tgo, gradOut, gbs, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
       else
         cvb::costvol_bwd_tma<-1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+            tfrm, tref, tgo, gradOut, gbs, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
       B2F_CHECK_LAUNCH("costvol_bwd_tma");
       return B2F_OK;
     }

@@ -91,6 +91,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       "r"(smem_u32(bar))
       : "memory");
 }
+// ---- device: 4-byte cp.async with zero-fill, completion signalled on an mbarrier --------
+// Used where a TMA box cannot be: TMA needs the innermost start coordinate 16-byte aligned
+// (an unaligned one faults with "illegal instruction" on sm_100a).
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const float* gsrc, bool valid) {
+  const int src_bytes = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+// The executing thread's prior cp.async operations arrive on `bar` when they complete; the
+// arrival was pre-counted in mbar_init (.noinc).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }

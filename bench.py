@@ -1,0 +1,591 @@
+#!/usr/bin/env python
+"""bench.py -- frame-triplets/sec of the Back2Future hot path at 1024x448 on N B200s.
+
+Workload (BASELINE.json configs[1]): CostVolMulti (past + future) and BilinearSamplerBHWD forward +
+backward over the full pyramid of the Ours-Hard architecture, batch 8 triplets per GPU, 1024x448,
+synthetic N(0,1) features, flow ~ N(0, 4 px):
+  * cost volume, levels 3..7 (C = 32,64,96,128,192; 112x256 .. 7x16), both directions, forward into
+    the 162-channel joined buffer and backward from a narrow of the 162-channel gradient;
+  * feature warps at levels 6..3 (C = 128,96,64,32) x 2 frames, forward + backward (image + flow grad);
+  * image warps (C = 3) at 28x64 .. 448x1024 x 2 frames, forward + backward.
+A "step" is one pass of all of that over one batch.  Triplets are independent, so ranks shard them
+with no data-path collective (weak scaling).
+
+  value : device-resident throughput (inputs already in HBM), C-ABI calls on one stream.
+  e2e   : the same pass through the reference-facing module API (back2future_b200.nn) with HOST
+          buffers: every step copies its inputs from pinned host memory and reads every result back.
+  --impl reference : the CPU restatement of the reference algorithm (oracle/c, OpenMP, all host
+          threads) on a bounded sample of the same workload.  Torch7 itself cannot be installed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H_FULL, W_FULL = 448, 1024
+LEVEL_C = {3: 32, 4: 64, 5: 96, 6: 128, 7: 192}
+BATCH = 8
+METRIC = "frame_triplets_per_sec_1024x448"
+UNIT = "triplets/s"
+WORKLOAD = ("configs[1]: CostVolMulti + BilinearSamplerBHWD fwd/bwd microbench, full pyramid "
+            "(levels 3-7, both directions; feature warps L6-L3; image warps 28x64..448x1024), "
+            "batch 8 per GPU, 1024x448 synthetic")
+
+
+def level_hw(l):
+    return H_FULL >> (l - 1), W_FULL >> (l - 1)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks (recipe: sample DURING the timed region)
+# ----------------------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------
+# the workload on one GPU
+# ----------------------------------------------------------------------------------------
+
+class Op:
+    __slots__ = ("name", "kind", "call", "bytes", "flops", "zero")
+
+    def __init__(self, name, kind, call, nbytes, flops=0, zero=None):
+        self.name, self.kind, self.call, self.bytes, self.flops, self.zero = name, kind, call, nbytes, flops, zero
+
+
+class Workload:
+    """Device buffers + the ordered list of C-ABI calls of one step."""
+
+    def __init__(self, torch, lib, dev, B=BATCH, seed=2):
+        from back2future_b200 import _lib
+        self.torch, self.lib, self.dev, self.B = torch, lib, dev, B
+        g = torch.Generator(device=dev).manual_seed(seed)
+
+        def randn(*shape, scale=1.0):
+            t = torch.randn(shape, device=dev, generator=g, dtype=torch.float32)
+            return t * scale if scale != 1.0 else t
+
+        def empty(*shape):
+            return torch.empty(shape, device=dev, dtype=torch.float32)
+
+        self.keep = []          # every tensor the ops reference
+        self.inputs = []        # (name, tensor) copied H2D per e2e step
+        self.outputs = []       # (name, tensor) copied D2H per e2e step
+        self.fwd_ops, self.bwd_ops = [], []
+        st = None               # stream handle filled in by bind()
+        self._mk = []           # deferred op constructors (need the stream)
+        P = lambda t: C.c_void_p(t.data_ptr())
+
+        # ---- cost volumes -------------------------------------------------------------
+        for l in (7, 6, 5, 4, 3):
+            Cn = LEVEL_C[l]
+            h, w = level_hw(l)
+            ref, past, fut = randn(B, Cn, h, w), randn(B, Cn, h, w), randn(B, Cn, h, w)
+            joined = empty(B, 162, h, w)
+            gjoined = randn(B, 162, h, w)
+            grads = [empty(B, Cn, h, w) for _ in range(4)]
+            self.keep += [ref, past, fut, joined, gjoined] + grads
+            self.inputs += [("cv%d.ref" % l, ref), ("cv%d.past" % l, past), ("cv%d.fut" % l, fut),
+                            ("cv%d.gradJoined" % l, gjoined)]
+            self.outputs += [("cv%d.joined" % l, joined)] + [("cv%d.grad%d" % (l, i), t) for i, t in enumerate(grads)]
+            fb = 4 * B * h * w * (2 * Cn + 81)
+            bb = 4 * B * h * w * (81 + 4 * Cn)
+            fl = 2 * Cn * 81 * B * h * w
+            for d, (frame, fwd, half) in enumerate(((fut, 1, 0), (past, 0, 1))):
+                fptr = _lib.ptr_array([ref.data_ptr(), frame.data_ptr()])
+                out = joined[:, 81 * half:81 * (half + 1)]
+                go = gjoined[:, 81 * half:81 * (half + 1)]
+                gptr = _lib.ptr_array([grads[2 * d].data_ptr(), grads[2 * d + 1].data_ptr()])
+                self.keep += [fptr, gptr]
+                self._mk.append(("f", "costvol_fwd L%d %s" % (l, "fut" if fwd else "past"), "costvol_fwd_L%d" % l,
+                                 lambda s, a=(fptr, 2, B, Cn, h, w, 9, fwd, P(out), joined.stride(0)):
+                                 (lambda: lib.b2f_costvol_forward(*a, s)), fb, fl, None))
+                self._mk.append(("b", "costvol_bwd L%d %s" % (l, "fut" if fwd else "past"), "costvol_bwd_L%d" % l,
+                                 lambda s, a=(fptr, 2, B, Cn, h, w, 9, fwd, P(go), gjoined.stride(0), gptr):
+                                 (lambda: lib.b2f_costvol_backward(*a, s)), bb, 2 * fl, None))
+
+        # ---- warps ---------------------------------------------------------------------
+        warp_cfgs = [("feat L%d" % l, LEVEL_C[l], level_hw(l)) for l in (6, 5, 4, 3)]
+        warp_cfgs += [("img %dx%d" % (H_FULL >> k, W_FULL >> k), 3, (H_FULL >> k, W_FULL >> k)) for k in (4, 3, 2, 1, 0)]
+        for name, Cn, (h, w) in warp_cfgs:
+            for fr in ("past", "fut"):
+                img, grid = randn(B, h, w, Cn), randn(B, h, w, 2, scale=4.0)
+                out, go = empty(B, h, w, Cn), randn(B, h, w, Cn)
+                gimg, ggrid = empty(B, h, w, Cn), empty(B, h, w, 2)
+                self.keep += [img, grid, out, go, gimg, ggrid]
+                tag = "warp %s %s" % (name, fr)
+                self.inputs += [(tag + ".img", img), (tag + ".grid", grid), (tag + ".gradOut", go)]
+                self.outputs += [(tag + ".out", out), (tag + ".gradImg", gimg), (tag + ".gradGrid", ggrid)]
+                fb = 4 * B * h * w * (2 * Cn + 2)
+                bb = 4 * B * h * w * (3 * Cn + 4)
+                kind = "warp_%s" % name.replace(" ", "_")
+                self._mk.append(("f", tag + " fwd", kind + "_fwd",
+                                 lambda s, a=(P(img), P(grid), P(out), B, h, w, Cn, h, w):
+                                 (lambda: lib.b2f_warp_bhwd_forward(*a, s)), fb, 0, None))
+                self._mk.append(("b", tag + " bwd", kind + "_bwd",
+                                 lambda s, a=(P(img), P(grid), P(go), P(gimg), P(ggrid), B, h, w, Cn, h, w):
+                                 (lambda: lib.b2f_warp_bhwd_backward(*a, s)), bb, 0,
+                                 (P(gimg), gimg.numel() * 4)))
+
+    def bind(self, stream_handle):
+        s = C.c_void_p(stream_handle)
+        lib = self.lib
+        self.fwd_ops, self.bwd_ops = [], []
+        for which, name, kind, mk, nbytes, flops, zero in self._mk:
+            z = None
+            if zero is not None:
+                z = (lambda a=zero: lib.b2f_zero_async(a[0], a[1], s))
+            op = Op(name, kind, mk(s), nbytes, flops, z)
+            (self.fwd_ops if which == "f" else self.bwd_ops).append(op)
+        self.ops = self.fwd_ops + self.bwd_ops[::-1]
+
+    def step(self, marks=None):
+        """One pass: forward coarse-to-fine, then backward in reverse.  `marks` maps an op kind to a
+        list receiving (start_event, end_event) pairs for the live roofline measurement."""
+        torch = self.torch
+        for op in self.ops:
+            if op.zero is not None:
+                rc = op.zero()
+                if rc:
+                    raise RuntimeError("b2f_zero_async failed: %d" % rc)
+            if marks is not None and op.kind in marks:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = op.call()
+                e1.record()
+                marks[op.kind].append((e0, e1, op))
+            else:
+                rc = op.call()
+            if rc:
+                raise RuntimeError("%s failed: status %d: %s" % (op.name, rc, self.lib.b2f_last_error().decode()))
+
+    def total_bytes(self):
+        return sum(op.bytes for op in self.ops)
+
+
+def breakdown(torch, wl, iters=10):
+    """Per-kernel device times (separate pass, events around every call; not part of `value`)."""
+    acc = {}
+    for _ in range(iters):
+        evs = []
+        for op in wl.ops:
+            if op.zero is not None:
+                op.zero()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            op.call()
+            e1.record()
+            evs.append((op, e0, e1))
+        torch.cuda.synchronize()
+        for op, e0, e1 in evs:
+            acc.setdefault(op.name, [op, []])[1].append(e0.elapsed_time(e1))
+    rows = []
+    for name, (op, ts) in acc.items():
+        ts = sorted(ts)
+        ms = ts[len(ts) // 2]
+        rows.append({"kernel": name, "ms": round(ms, 5), "alg_MB": round(op.bytes / 1e6, 2),
+                     "GBps": round(op.bytes / ms / 1e6, 1) if ms > 0 else None,
+                     "GFLOPs": round(op.flops / ms / 1e6, 1) if op.flops and ms > 0 else None})
+    return rows
+
+
+# ----------------------------------------------------------------------------------------
+# e2e: module API, host buffers
+# ----------------------------------------------------------------------------------------
+
+class E2E:
+    """The same pass through back2future_b200.nn with pinned HOST inputs and outputs."""
+
+    def __init__(self, torch, dev, B=BATCH, seed=2):
+        from back2future_b200 import nn as bnn
+        self.torch, self.dev, self.B = torch, dev, B
+        g = torch.Generator().manual_seed(seed)
+        self.items = []
+        self.h2d = self.d2h = 0
+
+        def pin(*shape, scale=1.0):
+            t = torch.randn(shape, generator=g, dtype=torch.float32) * scale
+            return t.pin_memory()
+
+        def pin_out(*shape):
+            return torch.empty(shape, dtype=torch.float32).pin_memory()
+
+        for l in (7, 6, 5, 4, 3):
+            Cn = LEVEL_C[l]
+            h, w = level_hw(l)
+            hin = [pin(B, Cn, h, w) for _ in range(3)] + [pin(B, 162, h, w)]
+            hout = [pin_out(B, 162, h, w)] + [pin_out(B, Cn, h, w) for _ in range(4)]
+            self.items.append(("cv", (bnn.CostVolMulti(9, True), bnn.CostVolMulti(9, False)), hin, hout,
+                               torch.empty((B, 162, h, w), device=dev)))
+        cfgs = [(LEVEL_C[l], level_hw(l)) for l in (6, 5, 4, 3)] + [(3, (H_FULL >> k, W_FULL >> k)) for k in (4, 3, 2, 1, 0)]
+        for Cn, (h, w) in cfgs:
+            for _ in range(2):
+                hin = [pin(B, h, w, Cn), pin(B, h, w, 2, scale=4.0), pin(B, h, w, Cn)]
+                hout = [pin_out(B, h, w, Cn), pin_out(B, h, w, Cn), pin_out(B, h, w, 2)]
+                self.items.append(("warp", bnn.BilinearSamplerBHWD(), hin, hout, None))
+        for _, _, hin, hout, _ in self.items:
+            self.h2d += sum(t.numel() * 4 for t in hin)
+            self.d2h += sum(t.numel() * 4 for t in hout)
+
+    def step(self):
+        dev = self.dev
+        for kind, mod, hin, hout, joined in self.items:
+            din = [t.to(dev, non_blocking=True) for t in hin]
+            if kind == "cv":
+                ref, past, fut, gj = din
+                mod[0].updateOutput([ref, fut], out=joined[:, :81])
+                mod[1].updateOutput([ref, past], out=joined[:, 81:])
+                gf = mod[0].updateGradInput([ref, fut], gj[:, :81])
+                gp = mod[1].updateGradInput([ref, past], gj[:, 81:])
+                douts = [joined, gf[0], gf[1], gp[0], gp[1]]
+            else:
+                img, grid, go = din
+                out = mod.updateOutput([img, grid])
+                gi, gg = mod.updateGradInput([img, grid], go)
+                douts = [out, gi, gg]
+            for h, d in zip(hout, douts):
+                h.copy_(d, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the restatement of the reference algorithm (oracle/c) on host cores
+# ----------------------------------------------------------------------------------------
+
+class CpuArm:
+    def __init__(self, frac=1.0, seed=2):
+        import numpy as np
+        path = os.path.join(ROOT, "oracle", "c", "libb2f_cpu.so")
+        if not os.path.exists(path):
+            import __graft_entry__ as ge
+            ge.build_oracle()
+        self.lib = C.CDLL(path)
+        self.lib.b2fcpu_costvol_backward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                     C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        self.cores = self.lib.b2fcpu_num_threads()
+        self.np = np
+        rng = np.random.default_rng(seed)
+        self.frac = frac
+        self.cv, self.warps = [], []
+        self.pixels_full = 0
+        self.pixels = 0
+        f32 = lambda *s: rng.standard_normal(s, dtype=np.float32)
+        B = 1
+        for l in (7, 6, 5, 4, 3):
+            Cn = LEVEL_C[l]
+            hf, w = level_hw(l)
+            h = max(1, int(round(hf * frac)))
+            self.pixels_full += hf * w
+            self.pixels += h * w
+            ref, past, fut = f32(B, Cn, h, w), f32(B, Cn, h, w), f32(B, Cn, h, w)
+            self.cv.append((Cn, h, w, ref, past, fut, np.empty((B, 162, h, w), np.float32), f32(B, 162, h, w),
+                            [np.empty((B, Cn, h, w), np.float32) for _ in range(4)]))
+        cfgs = [(LEVEL_C[l], level_hw(l)) for l in (6, 5, 4, 3)] + [(3, (H_FULL >> k, W_FULL >> k)) for k in (4, 3, 2, 1, 0)]
+        for Cn, (hf, w) in cfgs:
+            h = max(1, int(round(hf * frac)))
+            for _ in range(2):
+                self.warps.append((Cn, h, w, f32(B, h, w, Cn), f32(B, h, w, 2) * 4, f32(B, h, w, Cn),
+                                   np.empty((B, h, w, Cn), np.float32), np.empty((B, h, w, Cn), np.float32),
+                                   np.empty((B, h, w, 2), np.float32)))
+
+    def step(self):
+        L, np = self.lib, self.np
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        for Cn, h, w, ref, past, fut, joined, gj, grads in self.cv:
+            tmp = np.empty((1, 81, h, w), np.float32)
+            for d, (frame, fwd) in enumerate(((fut, 1), (past, 0))):
+                ptrs = (C.c_void_p * 2)(ref.ctypes.data, frame.ctypes.data)
+                L.b2fcpu_costvol_forward(ptrs, 2, 1, Cn, h, w, 9, fwd, vp(tmp))
+                joined[:, 81 * d:81 * (d + 1)] = tmp       # JoinTable copy, as in the reference (pwc.lua:267)
+                g = (C.c_void_p * 2)(grads[2 * d].ctypes.data, grads[2 * d + 1].ctypes.data)
+                go = gj[:, 81 * d:81 * (d + 1)]
+                L.b2fcpu_costvol_backward(ptrs, 2, 1, Cn, h, w, 9, fwd, C.c_void_p(go.ctypes.data), gj.strides[0] // 4, g)
+        for Cn, h, w, img, grid, go, out, gi, gg in self.warps:
+            L.b2fcpu_warp_forward(vp(img), vp(grid), vp(out), 1, h, w, Cn, h, w)
+            gi.fill(0)
+            L.b2fcpu_warp_backward(vp(img), vp(grid), vp(go), vp(gi), vp(gg), 1, h, w, Cn, h, w)
+
+    @property
+    def triplets_per_step(self):
+        return self.pixels / self.pixels_full
+
+
+def time_cpu(budget_s, steps=None, warmup=1):
+    """Time the CPU restatement on a bounded sample.  Returns (triplets/s, cores, description, seconds
+    per step, steps)."""
+    arm = CpuArm(1.0)
+    t0 = time.perf_counter()
+    arm.step()                      # calibration / warm-up on one full triplet
+    t1 = time.perf_counter() - t0
+    n = steps if steps is not None else max(1, min(5, int(budget_s / max(t1, 1e-3))))
+    frac = 1.0
+    if steps is not None and steps * t1 > budget_s:
+        frac = max(0.08, budget_s / (steps * t1))
+        arm = CpuArm(frac)
+        for _ in range(max(1, warmup)):
+            arm.step()
+    else:
+        for _ in range(max(0, warmup - 1)):
+            arm.step()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        arm.step()
+    dt = time.perf_counter() - t0
+    desc = ("%d step(s) of 1 triplet (B=1) through the full pyramid" % n if frac == 1.0 else
+            "%d step(s) of the top %.0f%% of rows of 1 triplet at every pyramid level (%.3f triplet per step)"
+            % (n, frac * 100, arm.triplets_per_step))
+    return arm.triplets_per_step * n / dt, arm.cores, desc, dt / n, n
+
+
+# ----------------------------------------------------------------------------------------
+# main
+# ----------------------------------------------------------------------------------------
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return {}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    value, cores, desc, sps, n = time_cpu(budget_s=120.0, steps=args.steps, warmup=min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "Torch7 is not installable here; this is the C/OpenMP restatement of "
+                   "the reference algorithm (oracle/c/b2f_cpu.c) on the host cores"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work (rank 0, N=1)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from back2future_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    W = max(3, args.warmup)
+    K = args.steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    wl = Workload(torch, lib, dev)
+    stream = torch.cuda.current_stream()
+    wl.bind(stream.cuda_stream)
+    for _ in range(W):
+        wl.step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps ------------------------------------------------
+    dominant = ("costvol_bwd_L3", "costvol_fwd_L3")
+    marks = {k: [] for k in dominant}
+    sampler = ClockSampler(local)
+    lib.b2f_launch_count(1)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        wl.step(marks)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    launches = int(lib.b2f_launch_count(0))
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    value = world * BATCH * K / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel (live events from the timed region) -----------
+    peak, peak_src = load_peaks()
+    roof = None
+    best = None
+    for kind, lst in marks.items():
+        if not lst:
+            continue
+        ts = [a.elapsed_time(b) for a, b, _ in lst]
+        avg = sum(ts) / len(ts)
+        share = sum(ts) / e0.elapsed_time(e1)
+        if best is None or sum(ts) > best[0]:
+            best = (sum(ts), kind, avg, lst[0][2], share)
+    if best:
+        _, kind, avg, op, share = best
+        achieved = op.bytes / (avg / 1e3) / 1e9
+        traffic = load_traffic().get(kind)
+        roof = {"bound": "hbm", "kernel": kind, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": op.bytes, "avg_launch_ms": round(avg, 5),
+                "share_of_step": round(share, 4),
+                "gflops": round(op.flops / (avg / 1e3) / 1e9, 1) if op.flops else None}
+
+    # ---- e2e through the module API with host buffers ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ee = E2E(torch, dev)
+        for _ in range(3):
+            ee.step()
+        barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            ee.step()
+        b.record()
+        torch.cuda.synchronize()
+        barrier()
+        ems = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = t.item()
+        e2e = {"value": round(world * BATCH * args.e2e_steps / (ems / 1e3), 2), "unit": UNIT,
+               "h2d_bytes_per_step": ee.h2d, "d2h_bytes_per_step": ee.d2h, "steps": args.e2e_steps,
+               "ms_per_step": round(ems / args.e2e_steps, 3),
+               "api": "back2future_b200.nn.CostVolMulti / BilinearSamplerBHWD updateOutput+updateGradInput"}
+        del ee
+
+    # ---- per-kernel breakdown (informational) and CPU baseline (rank 0) ----------------
+    rows = breakdown(torch, wl) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, desc, sps, n = time_cpu(args.cpu_budget)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+               "s_per_triplet": round(sps, 3)}
+
+    if rank == 0:
+        if rows:
+            tot = sum(r["ms"] for r in rows)
+            sys.stderr.write("per-kernel (separate pass, median of 10):\n")
+            for r in sorted(rows, key=lambda r: -r["ms"])[:24]:
+                sys.stderr.write("  %-34s %8.4f ms  %6.1f%%  %8s GB/s  %s\n" % (
+                    r["kernel"], r["ms"], 100 * r["ms"] / tot, r["GBps"], ("%s GFLOP/s" % r["GFLOPs"]) if r["GFLOPs"] else ""))
+            sys.stderr.write("  sum of kernels %.4f ms vs %.4f ms per step\n" % (tot, ms / K))
+            if args.breakdown:
+                json.dump(rows, open(args.breakdown, "w"), indent=1)
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sharding": "triplets across ranks, no collective",
+                       "l2": "no explicit flush: one step touches %.2f GB of distinct buffers (> 126 MB L2) before any "
+                             "buffer is reused" % (wl.total_bytes() / 1e9),
+                       "alg_bytes_per_step": wl.total_bytes()},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

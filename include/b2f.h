@@ -65,6 +65,9 @@ B2F_API int b2f_release_scratch(void);             /* frees this thread's scratc
  * their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the grid-size
  * heuristics, with forward strip width 16/8/4 pixels.                                       */
 B2F_API int b2f_debug_costvol_path(int mode);
+/* Stream-ordered zero-fill of a device buffer (what the sampler's Lua wrapper does with
+ * gradInput:zero() before the native call, BilinearSamplerBHWD.lua:99-102).                  */
+B2F_API int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream);
 /* Number of kernels (not memsets/copies) this thread has launched through the library since
  * the last reset; used by bench.py for its `gpu_launches` claim.                            */
 B2F_API int64_t b2f_launch_count(int reset);

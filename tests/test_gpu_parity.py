@@ -49,6 +49,25 @@ def rng(seed=2):
     return np.random.default_rng(seed)
 
 
+def close(kernel, ref64, ref32=None, tol=TOL):
+    """1e-4 relative against the float64 oracle.  Where the function itself is ill-conditioned in
+    fp32 (the L1 penalty's derivative has slope 1000 inside |x| < 1e-3, so the fp32 rounding of a
+    difference of pixel values moves it by > 1e-4) the float64 value is not what an fp32
+    implementation -- the reference included -- can produce; those few elements are compared with
+    the float32-mode oracle (same operation order as the Torch7 kernels) instead, and they must be
+    rare (< 0.1 % of the elements)."""
+    kernel = np.asarray(kernel, np.float64)
+    r64 = np.asarray(ref64, np.float64)
+    scale = np.maximum(np.abs(r64), np.sqrt(np.mean(r64 * r64)) + 1e-30)
+    bad = np.abs(kernel - r64) / scale >= tol
+    if not bad.any():
+        return True
+    if ref32 is None or bad.mean() > 1e-3:
+        return False
+    r32 = np.asarray(ref32, np.float64)
+    return bool((np.abs(kernel - r32)[bad] / scale[bad] < tol).all())
+
+
 # ---------------------------------------------------------------------------------------
 # cost volume
 # ---------------------------------------------------------------------------------------
@@ -494,7 +513,9 @@ def test_criterions_training_sizes(env):
         bf = bflow if gt else None
         assert abs(loss - oc.forward(flow, bf, occ, [w1, w2], tgt)) < TOL * abs(loss)
         ro, rw = oc.backward(flow, bf, occ, [w1, w2], tgt)
-        assert o.rel_err(g_occ, ro) < TOL and o.rel_err(g1, rw[0]) < TOL and o.rel_err(g2, rw[1]) < TOL
+        oc.dtype = np.float32
+        ro32, rw32 = oc.backward(flow, bf, occ, [w1, w2], tgt)
+        assert close(g_occ, ro, ro32) and close(g1, rw[0], rw32[0]) and close(g2, rw[1], rw32[1])
     for order, inp in ((1, flow), (2, flow), (1, occ)):
         pen = 1 if inp is flow else 0
         loss, g = _run_smooth(env, order, pen, 0, 1, inp, tgt)
