@@ -13,12 +13,16 @@
 // The geometry (add, clamp, floor, weight) is evaluated with exactly the reference's fp32 operations
 // because floor() makes it discontinuous; the blend may contract to FMAs (well inside 1e-4).
 //
-// Mapping: BHWD keeps a pixel's C channels contiguous, so for C % 4 == 0 eight lanes share a pixel and
-// stride over its float4 channel chunks (one 128-byte line per tap per 32 channels); the four dot
-// products are reduced with three shuffles.  Other C (the C = 3 image warps) use one thread per
-// (pixel, channel) forward -- consecutive threads write consecutive floats -- and one thread per pixel
-// backward.  The image-gradient scatter uses fire-and-forget reductions (red.global.add, .v4 for the
-// vector path), like the reference's atomicAdd but 4 channels per instruction.
+// Launch shape: grid = (x tiles, output row, batch) so no thread does a 64-bit division.
+//   * C % 4 == 0 (feature warps): 8 lanes share a pixel and stride over its float4 channel chunks --
+//     one 128-byte line per tap per 32 channels; the four dot products of the flow gradient are
+//     reduced with three shuffles; the image-gradient scatter is one red.global.add.v4.f32 per tap
+//     and chunk (the reference issues one scalar atomicAdd per channel).
+//   * C == 3 (image warps): one thread per pixel.  Forward stages the 128 x 3 outputs of a block in
+//     shared memory so every store instruction writes 512 contiguous bytes.  Backward: the TL/TR
+//     (and BL/BR) taps are 6 contiguous floats, scattered with 2-3 vector reductions chosen by the
+//     address alignment instead of 6 scalar ones -- the kernel is bound by the SM's RED issue rate.
+//   * any other C: one thread per pixel, scalar.
 #include "common.cuh"
 
 namespace b2f {
@@ -52,190 +56,204 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-constexpr int LPP = 8;  // lanes per pixel on the vector path
-
-// ---- forward, C % 4 == 0 ---------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-warp_fwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
-              int B, int H, int W, int C, int Hg, int Wg) {
-  const int64_t npix = (int64_t)B * Hg * Wg;
-  const int sub = threadIdx.x & (LPP - 1);
-  const int nch4 = C >> 2;
-  for (int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP; pix < npix;
-       pix += (int64_t)gridDim.x * blockDim.x / LPP) {
-    const int xo = (int)(pix % Wg);
-    const int yo = (int)((pix / Wg) % Hg);
-    const int b = (int)(pix / ((int64_t)Wg * Hg));
-    const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-    const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
-    const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
-    const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
-    const float4* tl = reinterpret_cast<const float4*>(img + (((int64_t)b * H + g.yi) * W + g.xi) * C);
-    const float4* tr = tl + nch4;
-    const float4* bl = tl + (int64_t)W * nch4;
-    const float4* br = bl + nch4;
-    float4* o = reinterpret_cast<float4*>(out + pix * C);
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = sub; q < nch4; q += LPP) {
-      const float4 a = __ldg(tl + q);
-      const float4 c = g.rin ? __ldg(tr + q) : zero;
-      const float4 d = g.bin ? __ldg(bl + q) : zero;
-      const float4 e = (g.rin && g.bin) ? __ldg(br + q) : zero;
-      float4 v;
-      v.x = w_tl * a.x + w_tr * c.x + w_bl * d.x + w_br * e.x;
-      v.y = w_tl * a.y + w_tr * c.y + w_bl * d.y + w_br * e.y;
-      v.z = w_tl * a.z + w_tr * c.z + w_bl * d.z + w_br * e.z;
-      v.w = w_tl * a.w + w_tr * c.w + w_bl * d.w + w_br * e.w;
-      o[q] = v;
+// Scatter-add 6 contiguous floats (two adjacent 3-channel pixels) with the fewest reductions the
+// address alignment allows.  `pad_ok`: p[6] is inside the buffer (a zero may be added to it).
+__device__ __forceinline__ void red_add6(float* p, const float (&v)[6], bool pad_ok) {
+  const unsigned a = (unsigned)((reinterpret_cast<uintptr_t>(p) >> 2) & 3u);
+  if (a == 0) {
+    red_add_v4(p, v[0], v[1], v[2], v[3]);
+    red_add_v2(p + 4, v[4], v[5]);
+  } else if (a == 2) {
+    red_add_v2(p, v[0], v[1]);
+    red_add_v4(p + 2, v[2], v[3], v[4], v[5]);
+  } else if (a == 3) {
+    red_add(p, v[0]);
+    red_add_v4(p + 1, v[1], v[2], v[3], v[4]);
+    red_add(p + 5, v[5]);
+  } else {  // a == 1
+    red_add(p, v[0]);
+    red_add_v2(p + 1, v[1], v[2]);
+    if (pad_ok) {
+      red_add_v4(p + 3, v[3], v[4], v[5], 0.f);
+    } else {
+      red_add_v2(p + 3, v[3], v[4]);
+      red_add(p + 5, v[5]);
     }
   }
 }
+__device__ __forceinline__ void red_add3(float* p, float a, float b, float c) {
+  if ((reinterpret_cast<uintptr_t>(p) & 7u) == 0) {
+    red_add_v2(p, a, b);
+    red_add(p + 2, c);
+  } else {
+    red_add(p, a);
+    red_add_v2(p + 1, b, c);
+  }
+}
 
-// ---- forward, any C: one thread per output float -----------------------------------------
-template <int CT>  // CT > 0: compile-time channel count, 0: runtime
-__global__ void __launch_bounds__(256)
-warp_fwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
-                int B, int H, int W, int Crt, int Hg, int Wg) {
-  const int C = CT > 0 ? CT : Crt;
-  const int64_t total = (int64_t)B * Hg * Wg * C;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pix = idx / C;
-    const int c = (int)(idx - pix * C);
-    const int xo = (int)(pix % Wg);
-    const int yo = (int)((pix / Wg) % Hg);
-    const int b = (int)(pix / ((int64_t)Wg * Hg));
-    const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+constexpr int LPP = 8;           // lanes per pixel on the vector path
+constexpr int VEC_THREADS = 256; // 32 pixels per block
+constexpr int PIX_THREADS = 128; // one thread per pixel
+
+// ---- forward, C % 4 == 0 ---------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+warp_fwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
+              int H, int W, int C, int Hg, int Wg) {
+  const int xo = blockIdx.x * (VEC_THREADS / LPP) + (threadIdx.x >> 3);
+  if (xo >= Wg) return;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const int sub = threadIdx.x & (LPP - 1);
+  const int nch4 = C >> 2;
+  const size_t pix = ((size_t)b * Hg + yo) * Wg + xo;
+  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const float4* tl = reinterpret_cast<const float4*>(img + (((size_t)b * H + g.yi) * W + g.xi) * C);
+  const float4* tr = tl + nch4;
+  const float4* bl = tl + (size_t)W * nch4;
+  const float4* br = bl + nch4;
+  float4* o = reinterpret_cast<float4*>(out + pix * C);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool both = g.rin && g.bin;
+  for (int q = sub; q < nch4; q += LPP) {
+    const float4 a = __ldg(tl + q);
+    const float4 c = g.rin ? __ldg(tr + q) : zero;
+    const float4 d = g.bin ? __ldg(bl + q) : zero;
+    const float4 e = both ? __ldg(br + q) : zero;
+    float4 v;
+    v.x = w_tl * a.x + w_tr * c.x + w_bl * d.x + w_br * e.x;
+    v.y = w_tl * a.y + w_tr * c.y + w_bl * d.y + w_br * e.y;
+    v.z = w_tl * a.z + w_tr * c.z + w_bl * d.z + w_br * e.z;
+    v.w = w_tl * a.w + w_tr * c.w + w_bl * d.w + w_br * e.w;
+    __stcs(o + q, v);
+  }
+}
+
+// ---- forward, C == 3: one thread per pixel, stores staged through shared memory ------------
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_fwd_c3(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
+            int H, int W, int Hg, int Wg) {
+  __shared__ float s_out[PIX_THREADS * 3];
+  const int x0 = blockIdx.x * PIX_THREADS;
+  const int xo = x0 + threadIdx.x;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const size_t row = ((size_t)b * Hg + yo) * Wg;
+  if (xo < Wg) {
+    const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + row + xo);
     const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
-    const float* tl = img + (((int64_t)b * H + g.yi) * W + g.xi) * C + c;
-    const float a = __ldg(tl);
-    const float t = g.rin ? __ldg(tl + C) : 0.f;
-    const float d = g.bin ? __ldg(tl + (int64_t)W * C) : 0.f;
-    const float e = (g.rin && g.bin) ? __ldg(tl + (int64_t)W * C + C) : 0.f;
-    out[idx] = g.wx * g.wy * a + (1.f - g.wx) * g.wy * t + g.wx * (1.f - g.wy) * d +
-               (1.f - g.wx) * (1.f - g.wy) * e;
+    const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+    const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+    const float* tl = img + (((size_t)b * H + g.yi) * W + g.xi) * 3;
+    const float* bl = tl + (size_t)W * 3;
+    const bool both = g.rin && g.bin;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = __ldg(tl + c);
+      const float t = g.rin ? __ldg(tl + 3 + c) : 0.f;
+      const float d = g.bin ? __ldg(bl + c) : 0.f;
+      const float e = both ? __ldg(bl + 3 + c) : 0.f;
+      s_out[threadIdx.x * 3 + c] = w_tl * a + w_tr * t + w_bl * d + w_br * e;
+    }
+  }
+  __syncthreads();
+  const int n = min(PIX_THREADS, Wg - x0) * 3;
+  float* o = out + (row + x0) * 3;
+  for (int i = threadIdx.x; i < n; i += PIX_THREADS) __stcs(o + i, s_out[i]);
+}
+
+// ---- forward, any C: one thread per pixel ---------------------------------------------------
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_fwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
+                int H, int W, int C, int Hg, int Wg) {
+  const int xo = blockIdx.x * PIX_THREADS + threadIdx.x;
+  if (xo >= Wg) return;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const size_t pix = ((size_t)b * Hg + yo) * Wg + xo;
+  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const float* tl = img + (((size_t)b * H + g.yi) * W + g.xi) * C;
+  const float* bl = tl + (size_t)W * C;
+  const bool both = g.rin && g.bin;
+  for (int c = 0; c < C; ++c) {
+    const float a = __ldg(tl + c);
+    const float t = g.rin ? __ldg(tl + C + c) : 0.f;
+    const float d = g.bin ? __ldg(bl + c) : 0.f;
+    const float e = both ? __ldg(bl + C + c) : 0.f;
+    out[pix * C + c] = w_tl * a + w_tr * t + w_bl * d + w_br * e;
   }
 }
 
 // ---- backward, C % 4 == 0 -------------------------------------------------------------
 template <bool ONLY_GRID>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(VEC_THREADS)
 warp_bwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
-              float* __restrict__ gimg, float* __restrict__ ggrid, int B, int H, int W, int C, int Hg, int Wg) {
-  const int64_t npix = (int64_t)B * Hg * Wg;
+              float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W, int C, int Hg, int Wg) {
+  // whole warps stay alive for the shuffles: out-of-range pixels are just not "live"
+  const int xo = blockIdx.x * (VEC_THREADS / LPP) + (threadIdx.x >> 3);
+  const bool live = xo < Wg;
+  const int yo = blockIdx.y, b = blockIdx.z;
   const int sub = threadIdx.x & (LPP - 1);
   const int nch4 = C >> 2;
-  // all lanes of a warp run the same number of iterations (npix is padded per warp) so that the
-  // shuffles below are always executed by full warps
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x / LPP;
-  const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPP;
-  const int64_t warp_first = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LPP;
-  for (int64_t base = warp_first, pix = first; base < npix; base += stride, pix += stride) {
-    const bool live = pix < npix;
-    float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
-    Geo g;
-    g.wx = g.wy = 0.f;
-    if (live) {
-      const int xo = (int)(pix % Wg);
-      const int yo = (int)((pix / Wg) % Hg);
-      const int b = (int)(pix / ((int64_t)Wg * Hg));
-      const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-      g = geometry(gxy.x, gxy.y, xo, yo, H, W);
-      const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
-      const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
-      const int64_t a0 = (((int64_t)b * H + g.yi) * W + g.xi) * C;
-      const float4* tl = reinterpret_cast<const float4*>(img + a0);
-      const float4* tr = tl + nch4;
-      const float4* bl = tl + (int64_t)W * nch4;
-      const float4* br = bl + nch4;
-      const float4* go = reinterpret_cast<const float4*>(gout + pix * C);
-      float* gi = ONLY_GRID ? nullptr : gimg + a0;
-      const bool both = g.rin && g.bin;
-      for (int q = sub; q < nch4; q += LPP) {
-        const float4 v = __ldg(go + q);
-        {
-          const float4 a = __ldg(tl + q);
-          d_tl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-          if (!ONLY_GRID) red_add_v4(gi + 4 * q, w_tl * v.x, w_tl * v.y, w_tl * v.z, w_tl * v.w);
-        }
-        if (g.rin) {
-          const float4 a = __ldg(tr + q);
-          d_tr += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-          if (!ONLY_GRID) red_add_v4(gi + C + 4 * q, w_tr * v.x, w_tr * v.y, w_tr * v.z, w_tr * v.w);
-        }
-        if (g.bin) {
-          const float4 a = __ldg(bl + q);
-          d_bl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-          if (!ONLY_GRID)
-            red_add_v4(gi + (int64_t)W * C + 4 * q, w_bl * v.x, w_bl * v.y, w_bl * v.z, w_bl * v.w);
-        }
-        if (both) {
-          const float4 a = __ldg(br + q);
-          d_br += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-          if (!ONLY_GRID)
-            red_add_v4(gi + (int64_t)W * C + C + 4 * q, w_br * v.x, w_br * v.y, w_br * v.z, w_br * v.w);
-        }
-      }
-    }
-#pragma unroll
-    for (int o = LPP / 2; o > 0; o >>= 1) {
-      d_tl += __shfl_xor_sync(0xffffffffu, d_tl, o);
-      d_tr += __shfl_xor_sync(0xffffffffu, d_tr, o);
-      d_bl += __shfl_xor_sync(0xffffffffu, d_bl, o);
-      d_br += __shfl_xor_sync(0xffffffffu, d_br, o);
-    }
-    if (live && sub == 0) {
-      float2 r;
-      r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
-      r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
-      reinterpret_cast<float2*>(ggrid)[pix] = r;
-    }
-  }
-}
-
-// ---- backward, any C: one thread per pixel --------------------------------------------
-template <bool ONLY_GRID, int CT>
-__global__ void __launch_bounds__(256)
-warp_bwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
-                float* __restrict__ gimg, float* __restrict__ ggrid, int B, int H, int W, int Crt, int Hg,
-                int Wg) {
-  const int C = CT > 0 ? CT : Crt;
-  const int64_t npix = (int64_t)B * Hg * Wg;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
-       pix += (int64_t)gridDim.x * blockDim.x) {
-    const int xo = (int)(pix % Wg);
-    const int yo = (int)((pix / Wg) % Hg);
-    const int b = (int)(pix / ((int64_t)Wg * Hg));
+  const size_t pix = ((size_t)b * Hg + yo) * Wg + (live ? xo : 0);
+  float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
+  Geo g;
+  g.wx = g.wy = 0.f;
+  if (live) {
     const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-    const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+    g = geometry(gxy.x, gxy.y, xo, yo, H, W);
     const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
     const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
-    const int64_t a0 = (((int64_t)b * H + g.yi) * W + g.xi) * C;
-    const int64_t rowC = (int64_t)W * C;
+    const size_t a0 = (((size_t)b * H + g.yi) * W + g.xi) * C;
+    const float4* tl = reinterpret_cast<const float4*>(img + a0);
+    const float4* tr = tl + nch4;
+    const float4* bl = tl + (size_t)W * nch4;
+    const float4* br = bl + nch4;
+    const float4* go = reinterpret_cast<const float4*>(gout + pix * C);
+    float* gi = ONLY_GRID ? nullptr : gimg + a0;
+    const size_t rowC = (size_t)W * C;
     const bool both = g.rin && g.bin;
-    float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float v = __ldg(gout + pix * C + c);
-      d_tl += __ldg(img + a0 + c) * v;
-      if (!ONLY_GRID) red_add(gimg + a0 + c, w_tl * v);
+    for (int q = sub; q < nch4; q += LPP) {
+      const float4 v = __ldcs(go + q);
+      {
+        const float4 a = __ldg(tl + q);
+        d_tl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+        if (!ONLY_GRID) red_add_v4(gi + 4 * q, w_tl * v.x, w_tl * v.y, w_tl * v.z, w_tl * v.w);
+      }
       if (g.rin) {
-        d_tr += __ldg(img + a0 + C + c) * v;
-        if (!ONLY_GRID) red_add(gimg + a0 + C + c, w_tr * v);
+        const float4 a = __ldg(tr + q);
+        d_tr += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+        if (!ONLY_GRID) red_add_v4(gi + C + 4 * q, w_tr * v.x, w_tr * v.y, w_tr * v.z, w_tr * v.w);
       }
       if (g.bin) {
-        d_bl += __ldg(img + a0 + rowC + c) * v;
-        if (!ONLY_GRID) red_add(gimg + a0 + rowC + c, w_bl * v);
+        const float4 a = __ldg(bl + q);
+        d_bl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+        if (!ONLY_GRID) red_add_v4(gi + rowC + 4 * q, w_bl * v.x, w_bl * v.y, w_bl * v.z, w_bl * v.w);
       }
       if (both) {
-        d_br += __ldg(img + a0 + rowC + C + c) * v;
-        if (!ONLY_GRID) red_add(gimg + a0 + rowC + C + c, w_br * v);
+        const float4 a = __ldg(br + q);
+        d_br += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+        if (!ONLY_GRID) red_add_v4(gi + rowC + C + 4 * q, w_br * v.x, w_br * v.y, w_br * v.z, w_br * v.w);
       }
     }
+  }
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) {
+    d_tl += __shfl_xor_sync(0xffffffffu, d_tl, o);
+    d_tr += __shfl_xor_sync(0xffffffffu, d_tr, o);
+    d_bl += __shfl_xor_sync(0xffffffffu, d_bl, o);
+    d_br += __shfl_xor_sync(0xffffffffu, d_br, o);
+  }
+  if (live && sub == 0) {
     float2 r;
     r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
     r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
@@ -243,21 +261,105 @@ warp_bwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, c
   }
 }
 
+// ---- backward, C == 3: one thread per pixel, alignment-aware vector reductions ---------------
+template <bool ONLY_GRID>
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_bwd_c3(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
+            float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W, int Hg, int Wg,
+            size_t gimg_elems) {
+  __shared__ float s_go[PIX_THREADS * 3];
+  const int x0 = blockIdx.x * PIX_THREADS;
+  const int xo = x0 + threadIdx.x;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const size_t row = ((size_t)b * Hg + yo) * Wg;
+  // coalesced read of the block's 128 x 3 gradOut floats
+  const int n = min(PIX_THREADS, Wg - x0) * 3;
+  const float* gsrc = gout + (row + x0) * 3;
+  for (int i = threadIdx.x; i < n; i += PIX_THREADS) s_go[i] = __ldcs(gsrc + i);
+  __syncthreads();
+  if (xo >= Wg) return;
+  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + row + xo);
+  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const size_t a0 = (((size_t)b * H + g.yi) * W + g.xi) * 3;
+  const size_t rowC = (size_t)W * 3;
+  const float v0 = s_go[threadIdx.x * 3], v1 = s_go[threadIdx.x * 3 + 1], v2 = s_go[threadIdx.x * 3 + 2];
+  float d_tl, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
+  d_tl = __ldg(img + a0) * v0 + __ldg(img + a0 + 1) * v1 + __ldg(img + a0 + 2) * v2;
+  if (g.rin) d_tr = __ldg(img + a0 + 3) * v0 + __ldg(img + a0 + 4) * v1 + __ldg(img + a0 + 5) * v2;
+  if (g.bin) {
+    d_bl = __ldg(img + a0 + rowC) * v0 + __ldg(img + a0 + rowC + 1) * v1 + __ldg(img + a0 + rowC + 2) * v2;
+    if (g.rin)
+      d_br = __ldg(img + a0 + rowC + 3) * v0 + __ldg(img + a0 + rowC + 4) * v1 + __ldg(img + a0 + rowC + 5) * v2;
+  }
+  if (!ONLY_GRID) {
+    if (g.rin) {
+      const float top[6] = {w_tl * v0, w_tl * v1, w_tl * v2, w_tr * v0, w_tr * v1, w_tr * v2};
+      red_add6(gimg + a0, top, a0 + 6 < gimg_elems);
+      if (g.bin) {
+        const float bot[6] = {w_bl * v0, w_bl * v1, w_bl * v2, w_br * v0, w_br * v1, w_br * v2};
+        red_add6(gimg + a0 + rowC, bot, a0 + rowC + 6 < gimg_elems);
+      }
+    } else {
+      red_add3(gimg + a0, w_tl * v0, w_tl * v1, w_tl * v2);
+      if (g.bin) red_add3(gimg + a0 + rowC, w_bl * v0, w_bl * v1, w_bl * v2);
+    }
+  }
+  float2 r;
+  r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
+  r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
+  reinterpret_cast<float2*>(ggrid)[row + xo] = r;
+}
+
+// ---- backward, any C: one thread per pixel --------------------------------------------
+template <bool ONLY_GRID>
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_bwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
+                float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W, int C, int Hg, int Wg) {
+  const int xo = blockIdx.x * PIX_THREADS + threadIdx.x;
+  if (xo >= Wg) return;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const size_t pix = ((size_t)b * Hg + yo) * Wg + xo;
+  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const size_t a0 = (((size_t)b * H + g.yi) * W + g.xi) * C;
+  const size_t rowC = (size_t)W * C;
+  const bool both = g.rin && g.bin;
+  float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(gout + pix * C + c);
+    d_tl += __ldg(img + a0 + c) * v;
+    if (!ONLY_GRID) red_add(gimg + a0 + c, w_tl * v);
+    if (g.rin) {
+      d_tr += __ldg(img + a0 + C + c) * v;
+      if (!ONLY_GRID) red_add(gimg + a0 + C + c, w_tr * v);
+    }
+    if (g.bin) {
+      d_bl += __ldg(img + a0 + rowC + c) * v;
+      if (!ONLY_GRID) red_add(gimg + a0 + rowC + c, w_bl * v);
+    }
+    if (both) {
+      d_br += __ldg(img + a0 + rowC + C + c) * v;
+      if (!ONLY_GRID) red_add(gimg + a0 + rowC + C + c, w_br * v);
+    }
+  }
+  float2 r;
+  r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
+  r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
+  reinterpret_cast<float2*>(ggrid)[pix] = r;
+}
+
 int check_args(const float* img, const float* grid, int B, int H, int W, int C, int Hg, int Wg) {
   if (!img || !grid) return fail(B2F_EINVAL, "warp: NULL img/grid");
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || Hg <= 0 || Wg <= 0)
     return fail(B2F_EINVAL, "warp: bad size B=%d H=%d W=%d C=%d Hg=%d Wg=%d", B, H, W, C, Hg, Wg);
+  if (B > 65535 || Hg > 65535) return fail(B2F_EINVAL, "warp: B and Hg must be <= 65535 (grid y/z limits)");
   if (!aligned4(img)) return fail(B2F_EALIGN, "warp: img misaligned");
   if ((reinterpret_cast<uintptr_t>(grid) & 7u) != 0) return fail(B2F_EALIGN, "warp: grid must be 8-byte aligned");
   return B2F_OK;
-}
-
-int blocks_for(int64_t threads_needed) {
-  int64_t blocks = (threads_needed + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
 }
 
 }  // namespace
@@ -273,16 +375,18 @@ extern "C" int b2f_warp_bhwd_forward(const float* img, const float* grid, float*
   if (!aligned4(out)) return fail(B2F_EALIGN, "warp_forward: out misaligned");
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t npix = (int64_t)B * Hg * Wg;
   if ((C & 3) == 0 && aligned16(img) && aligned16(out)) {
-    warp_fwd_vec4<<<blocks_for(npix * LPP), 256, 0, st>>>(img, grid, out, B, H, W, C, Hg, Wg);
+    dim3 grid_dim((Wg + 31) / 32, Hg, B);
+    warp_fwd_vec4<<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, out, H, W, C, Hg, Wg);
     B2F_CHECK_LAUNCH("warp_fwd_vec4");
   } else if (C == 3) {
-    warp_fwd_scalar<3><<<blocks_for(npix * 3), 256, 0, st>>>(img, grid, out, B, H, W, C, Hg, Wg);
-    B2F_CHECK_LAUNCH("warp_fwd_scalar<3>");
+    dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
+    warp_fwd_c3<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg);
+    B2F_CHECK_LAUNCH("warp_fwd_c3");
   } else {
-    warp_fwd_scalar<0><<<blocks_for(npix * C), 256, 0, st>>>(img, grid, out, B, H, W, C, Hg, Wg);
-    B2F_CHECK_LAUNCH("warp_fwd_scalar<0>");
+    dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
+    warp_fwd_scalar<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, C, Hg, Wg);
+    B2F_CHECK_LAUNCH("warp_fwd_scalar");
   }
   return B2F_OK;
 }
@@ -297,22 +401,23 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
   if ((reinterpret_cast<uintptr_t>(gradGrid) & 7u) != 0) return fail(B2F_EALIGN, "warp_backward: gradGrid must be 8-byte aligned");
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t npix = (int64_t)B * Hg * Wg;
   const bool only = gradImg == nullptr;
   if ((C & 3) == 0 && aligned16(img) && aligned16(gradOut) && (only || aligned16(gradImg))) {
-    // pad to whole warps: 4 pixels per warp
-    const int64_t threads = ((npix + 3) / 4) * 32;
-    if (only) warp_bwd_vec4<true><<<blocks_for(threads), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
-    else warp_bwd_vec4<false><<<blocks_for(threads), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
+    dim3 grid_dim((Wg + 31) / 32, Hg, B);
+    if (only) warp_bwd_vec4<true><<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
+    else warp_bwd_vec4<false><<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
     B2F_CHECK_LAUNCH("warp_bwd_vec4");
   } else if (C == 3) {
-    if (only) warp_bwd_scalar<true, 3><<<blocks_for(npix), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
-    else warp_bwd_scalar<false, 3><<<blocks_for(npix), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
-    B2F_CHECK_LAUNCH("warp_bwd_scalar<3>");
+    dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
+    const size_t elems = (size_t)B * H * W * 3;
+    if (only) warp_bwd_c3<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
+    else warp_bwd_c3<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
+    B2F_CHECK_LAUNCH("warp_bwd_c3");
   } else {
-    if (only) warp_bwd_scalar<true, 0><<<blocks_for(npix), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
-    else warp_bwd_scalar<false, 0><<<blocks_for(npix), 256, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, B, H, W, C, Hg, Wg);
-    B2F_CHECK_LAUNCH("warp_bwd_scalar<0>");
+    dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
+    if (only) warp_bwd_scalar<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
+    else warp_bwd_scalar<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
+    B2F_CHECK_LAUNCH("warp_bwd_scalar");
   }
   return B2F_OK;
 }
