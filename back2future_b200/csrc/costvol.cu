@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "tma.cuh"
 
+#include <algorithm>
+
 namespace b2f {
 namespace {
 
@@ -137,9 +139,10 @@ struct Cfg {
 };
 
 template <int A, int SGN>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, A <= 8 ? 2 : 1)
 costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_frm,
-                float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv) {
+                float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv, int nsplit,
+                int chunks_per_split) {
   using cfg = Cfg<A>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer + integer offset keeps the shared address space (LDS, not generic LD)
@@ -149,8 +152,12 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   uint64_t* empty = full + NS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * cfg::TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int nchunks = (C + CK - 1) / CK;
+  const int x0 = blockIdx.x * cfg::TW, y0 = blockIdx.y * TH;
+  // small levels: the channel range is split over nsplit CTAs whose partial sums are reduced with
+  // red.global.add into a pre-zeroed output (enough CTAs to fill 148 SMs from a handful of tiles)
+  const int b = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
+  const int kbeg = split * chunks_per_split;
+  const int nchunks = min((C + CK - 1) / CK - kbeg, chunks_per_split);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -171,8 +178,8 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         float* rs = stages + s * cfg::STAGE_ELEMS;
         float* fs = rs + cfg::REF_ELEMS;
         mbar_arrive_expect_tx(&full[s], cfg::STAGE_BYTES);
-        tma_load_4d(rs, &tm_ref, x0, y0, k * CK, b, &full[s]);
-        tma_load_4d(fs, &tm_frm, x0 - 4, y0 - 4, k * CK, b, &full[s]);
+        tma_load_4d(rs, &tm_ref, x0, y0, (kbeg + k) * CK, b, &full[s]);
+        tma_load_4d(fs, &tm_frm, x0 - 4, y0 - 4, (kbeg + k) * CK, b, &full[s]);
       }
     }
     return;
@@ -234,7 +241,13 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
           float4 v;
           v.x = acc[ix][4 * q] * kinv; v.y = acc[ix][4 * q + 1] * kinv;
           v.z = acc[ix][4 * q + 2] * kinv; v.w = acc[ix][4 * q + 3] * kinv;
-          *reinterpret_cast<float4*>(o + 4 * q) = v;
+          if (nsplit == 1) {
+            *reinterpret_cast<float4*>(o + 4 * q) = v;
+          } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * q), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
         }
       }
     }
@@ -463,7 +476,7 @@ int grid_for(int64_t total, int threads) {
 
 template <int A, int SGN>
 int launch_fwd_tma(const CUtensorMap& tr, const CUtensorMap& tf, float* out, int64_t obs, int B, int C, int H,
-                   int W, float kdiv, cudaStream_t st) {
+                   int W, float kdiv, int nsplit, cudaStream_t st) {
   using cfg = cvf::Cfg<A>;
   auto kern = cvf::costvol_fwd_tma<A, SGN>;
   static thread_local int attr_dev = -1;
@@ -473,8 +486,13 @@ int launch_fwd_tma(const CUtensorMap& tr, const CUtensorMap& tf, float* out, int
     B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
     attr_dev = dev;
   }
-  dim3 grid((W + cfg::TW - 1) / cfg::TW, (H + cvf::TH - 1) / cvf::TH, B);
-  kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, out, obs, C, H, W, kdiv);
+  const int nchunks = (C + cvf::CK - 1) / cvf::CK;
+  const int cps = (nchunks + nsplit - 1) / nsplit;
+  nsplit = (nchunks + cps - 1) / cps;   // no empty splits
+  if (nsplit > 1)  // partial sums are accumulated: zero this instance's (B, 81, H, W) block first
+    B2F_CUDA_TRY(cudaMemset2DAsync(out, (size_t)obs * 4, 0, (size_t)81 * H * W * 4, (size_t)B, st));
+  dim3 grid((W + cfg::TW - 1) / cfg::TW, (H + cvf::TH - 1) / cvf::TH, B * nsplit);
+  kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, out, obs, C, H, W, kdiv, nsplit, cps);
   B2F_CHECK_LAUNCH("costvol_fwd_tma");
   return B2F_OK;
 }
@@ -520,24 +538,32 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
                       aligned16(frames[1]) && aligned16(out) && (obs % 4) == 0 && get_encode_fn() != nullptr;
   if (tma_ok) {
     // largest strip width whose grid still fills the machine
-    int A = 0;
+    // Measured on B200 (tools/time_cv.py): the 32-column tiles with two CTAs per SM beat the 64-column
+    // ones at level 3 (60 vs 75 us); below one tile per SM the 16-column tiles win, and when even those do
+    // not fill the machine the channel range is split across CTAs (path 5 forces a split in tests).
+    int A = 0, nsplit = 1;
     const int sms = num_sms();
-    if (path >= 2) A = path == 2 ? 16 : (path == 3 ? 8 : 4);
-    else if (W >= 64 && tiles_for(16, B, H, W) >= sms) A = 16;
+    if (path >= 2 && path <= 4) A = path == 2 ? 16 : (path == 3 ? 8 : 4);
     else if (W >= 32 && tiles_for(8, B, H, W) >= sms) A = 8;
-    else if (tiles_for(4, B, H, W) >= 64) A = 4;
+    else A = 4;
+    if (A == 4 && (path == 0 || path == 5)) {
+      const int64_t t = tiles_for(4, B, H, W);
+      const int nchunks = (C + cvf::CK - 1) / cvf::CK;
+      if (2 * t <= sms || path == 5) nsplit = (int)std::min<int64_t>(nchunks, std::max<int64_t>(path == 5 ? 2 : 1, sms / t));
+      if ((int64_t)B * nsplit > 65535) nsplit = 1;
+    }
     if (A) {
       CUtensorMap tr, tf;
       if (A == 16) rc = make_fwd_maps<16>(&tr, &tf, frames[0], frames[1], B, C, H, W);
       else if (A == 8) rc = make_fwd_maps<8>(&tr, &tf, frames[0], frames[1], B, C, H, W);
       else rc = make_fwd_maps<4>(&tr, &tf, frames[0], frames[1], B, C, H, W);
       if (rc) return rc;
-      if (A == 16) return sgn > 0 ? launch_fwd_tma<16, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
-                                  : launch_fwd_tma<16, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
-      if (A == 8) return sgn > 0 ? launch_fwd_tma<8, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
-                                 : launch_fwd_tma<8, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
-      return sgn > 0 ? launch_fwd_tma<4, 1>(tr, tf, out, obs, B, C, H, W, kdiv, st)
-                     : launch_fwd_tma<4, -1>(tr, tf, out, obs, B, C, H, W, kdiv, st);
+      if (A == 16) return sgn > 0 ? launch_fwd_tma<16, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
+                                  : launch_fwd_tma<16, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
+      if (A == 8) return sgn > 0 ? launch_fwd_tma<8, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
+                                 : launch_fwd_tma<8, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
+      return sgn > 0 ? launch_fwd_tma<4, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
+                     : launch_fwd_tma<4, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
     }
   }
 

@@ -63,7 +63,8 @@ B2F_API int b2f_release_scratch(void);             /* frees this thread's scratc
 /* Test hook selecting the cost-volume kernel family (thread-local; returns the previous mode):
  * 0 = automatic (default), 1 = generic direct kernels, 2/3/4 = the tiled TMA kernels whenever
  * their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the grid-size
- * heuristics, with forward strip width 16/8/4 pixels.                                       */
+ * heuristics, with forward strip width 16/8/4 pixels; 5 = strip width 4 with the channel range
+ * split over at least two CTAs per tile (the small-level path).                              */
 B2F_API int b2f_debug_costvol_path(int mode);
 /* Stream-ordered zero-fill of a device buffer (what the sampler's Lua wrapper does with
  * gradInput:zero() before the native call, BilinearSamplerBHWD.lua:99-102).                  */

@@ -111,6 +111,8 @@ def _costvol_bwd(env, frames, go_wide, sl, win, fwd, skip=()):
 TILED_CASES = [
     (2, 2, 32, 16, 128), (2, 1, 20, 13, 72), (3, 2, 32, 16, 64), (3, 1, 12, 9, 44), (4, 2, 24, 14, 32),
     (4, 1, 7, 7, 16), (4, 1, 3, 5, 4),
+    # mode 5: channel range split across CTAs, partial sums reduced into a pre-zeroed output
+    (5, 2, 24, 14, 32), (5, 1, 192, 7, 16), (5, 2, 20, 9, 20), (5, 1, 3, 5, 4),
 ]
 
 
