@@ -98,49 +98,104 @@ __device__ __forceinline__ void red_add3(float* p, float a, float b, float c) {
   }
 }
 
+// Six contiguous floats (two adjacent 3-channel pixels) starting at a 4-byte aligned address, fetched as
+// 2-3 aligned 16-byte loads plus a register selection instead of 6 scalar loads: the C = 3 kernels are
+// bound by L1/LSU transactions (a scalar warp request touches ~28 sectors), not by bytes.  [lo, hi) is the
+// tensor's extent; chunks that would cross it fall back to scalar loads.
+// The loads and the selection are separate calls so that a thread can have both tap rows (and the taps of
+// several pixels) in flight before it consumes any of them -- these kernels are latency-bound.
+struct Raw6 {
+  float4 c0, c1, c2;
+  unsigned a;
+};
+__device__ __forceinline__ void load6_issue(Raw6& r, const float* p, const float* lo, const float* hi) {
+  r.a = (unsigned)((reinterpret_cast<uintptr_t>(p) >> 2) & 3u);
+  const float* base = p - r.a;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (base >= lo && base + 12 <= hi) {
+    r.c0 = __ldg(reinterpret_cast<const float4*>(base));
+    r.c1 = __ldg(reinterpret_cast<const float4*>(base) + 1);
+    r.c2 = (r.a == 3) ? __ldg(reinterpret_cast<const float4*>(base) + 2) : zero;
+  } else {  // first / last bytes of the tensor: element-wise, never outside [lo, hi)
+    float t[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) t[i] = (base + i >= lo && base + i < hi) ? __ldg(base + i) : 0.f;
+    r.c0 = make_float4(t[0], t[1], t[2], t[3]);
+    r.c1 = make_float4(t[4], t[5], t[6], t[7]);
+    r.c2 = make_float4(t[8], t[9], t[10], t[11]);
+  }
+}
+__device__ __forceinline__ void load6_select(const Raw6& r, float (&v)[6]) {
+  const float4 c0 = r.c0, c1 = r.c1, c2 = r.c2;
+  if (r.a == 0) { v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; }
+  else if (r.a == 1) { v[0] = c0.y; v[1] = c0.z; v[2] = c0.w; v[3] = c1.x; v[4] = c1.y; v[5] = c1.z; }
+  else if (r.a == 2) { v[0] = c0.z; v[1] = c0.w; v[2] = c1.x; v[3] = c1.y; v[4] = c1.z; v[5] = c1.w; }
+  else { v[0] = c0.w; v[1] = c1.x; v[2] = c1.y; v[3] = c1.z; v[4] = c1.w; v[5] = c2.x; }
+}
+
 constexpr int LPP = 8;           // lanes per pixel on the vector path
 constexpr int VEC_THREADS = 256; // 32 pixels per block
 constexpr int PIX_THREADS = 128; // one thread per pixel
 
 // ---- forward, C % 4 == 0 ---------------------------------------------------------------
+// Each 8-lane group handles two pixels of the row (x and x + 32): both grid values are fetched first,
+// then all eight tap loads are in flight together -- the kernel is latency-bound, not byte-bound.
+constexpr int VEC_PPT = 2;
 __global__ void __launch_bounds__(VEC_THREADS)
 warp_fwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
               int H, int W, int C, int Hg, int Wg) {
-  const int xo = blockIdx.x * (VEC_THREADS / LPP) + (threadIdx.x >> 3);
-  if (xo >= Wg) return;
+  const int xa = blockIdx.x * (VEC_THREADS / LPP) * VEC_PPT + (threadIdx.x >> 3);
   const int yo = blockIdx.y, b = blockIdx.z;
   const int sub = threadIdx.x & (LPP - 1);
   const int nch4 = C >> 2;
-  const size_t pix = ((size_t)b * Hg + yo) * Wg + xo;
-  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
-  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
-  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
-  const float4* tl = reinterpret_cast<const float4*>(img + (((size_t)b * H + g.yi) * W + g.xi) * C);
-  const float4* tr = tl + nch4;
-  const float4* bl = tl + (size_t)W * nch4;
-  const float4* br = bl + nch4;
-  float4* o = reinterpret_cast<float4*>(out + pix * C);
+  const size_t row = ((size_t)b * Hg + yo) * Wg;
+  int xo[VEC_PPT];
+  bool live[VEC_PPT];
+  float2 gxy[VEC_PPT];
+#pragma unroll
+  for (int p = 0; p < VEC_PPT; ++p) {
+    xo[p] = xa + p * (VEC_THREADS / LPP);
+    live[p] = xo[p] < Wg;
+    gxy[p] = live[p] ? __ldg(reinterpret_cast<const float2*>(grid) + row + xo[p]) : make_float2(0.f, 0.f);
+  }
+  Geo g[VEC_PPT];
+  const float4* tl[VEC_PPT];
+#pragma unroll
+  for (int p = 0; p < VEC_PPT; ++p) {
+    g[p] = geometry(gxy[p].x, gxy[p].y, live[p] ? xo[p] : 0, yo, H, W);
+    tl[p] = reinterpret_cast<const float4*>(img + (((size_t)b * H + g[p].yi) * W + g[p].xi) * C);
+  }
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool both = g.rin && g.bin;
+  const size_t rowq = (size_t)W * nch4;
   for (int q = sub; q < nch4; q += LPP) {
-    const float4 a = __ldg(tl + q);
-    const float4 c = g.rin ? __ldg(tr + q) : zero;
-    const float4 d = g.bin ? __ldg(bl + q) : zero;
-    const float4 e = both ? __ldg(br + q) : zero;
-    float4 v;
-    v.x = w_tl * a.x + w_tr * c.x + w_bl * d.x + w_br * e.x;
-    v.y = w_tl * a.y + w_tr * c.y + w_bl * d.y + w_br * e.y;
-    v.z = w_tl * a.z + w_tr * c.z + w_bl * d.z + w_br * e.z;
-    v.w = w_tl * a.w + w_tr * c.w + w_bl * d.w + w_br * e.w;
-    __stcs(o + q, v);
+    float4 a[VEC_PPT], c[VEC_PPT], d[VEC_PPT], e[VEC_PPT];
+#pragma unroll
+    for (int p = 0; p < VEC_PPT; ++p) {
+      const bool rin = g[p].rin && live[p], bin = g[p].bin && live[p];
+      a[p] = live[p] ? __ldg(tl[p] + q) : zero;
+      c[p] = rin ? __ldg(tl[p] + nch4 + q) : zero;
+      d[p] = bin ? __ldg(tl[p] + rowq + q) : zero;
+      e[p] = (rin && bin) ? __ldg(tl[p] + rowq + nch4 + q) : zero;
+    }
+#pragma unroll
+    for (int p = 0; p < VEC_PPT; ++p) {
+      if (!live[p]) continue;
+      const float w_tl = g[p].wx * g[p].wy, w_tr = (1.f - g[p].wx) * g[p].wy;
+      const float w_bl = g[p].wx * (1.f - g[p].wy), w_br = (1.f - g[p].wx) * (1.f - g[p].wy);
+      float4 v;
+      v.x = w_tl * a[p].x + w_tr * c[p].x + w_bl * d[p].x + w_br * e[p].x;
+      v.y = w_tl * a[p].y + w_tr * c[p].y + w_bl * d[p].y + w_br * e[p].y;
+      v.z = w_tl * a[p].z + w_tr * c[p].z + w_bl * d[p].z + w_br * e[p].z;
+      v.w = w_tl * a[p].w + w_tr * c[p].w + w_bl * d[p].w + w_br * e[p].w;
+      __stcs(reinterpret_cast<float4*>(out + (row + xo[p]) * C) + q, v);
+    }
   }
 }
 
 // ---- forward, C == 3: one thread per pixel, stores staged through shared memory ------------
 __global__ void __launch_bounds__(PIX_THREADS)
 warp_fwd_c3(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
-            int H, int W, int Hg, int Wg) {
+            int H, int W, int Hg, int Wg, const float* img_end) {
   __shared__ float s_out[PIX_THREADS * 3];
   const int x0 = blockIdx.x * PIX_THREADS;
   const int xo = x0 + threadIdx.x;
@@ -152,16 +207,19 @@ warp_fwd_c3(const float* __restrict__ img, const float* __restrict__ grid, float
     const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
     const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
     const float* tl = img + (((size_t)b * H + g.yi) * W + g.xi) * 3;
-    const float* bl = tl + (size_t)W * 3;
+    // a right tap at index W (a bottom tap at index H) contributes 0: give it a zero weight and let the
+    // six-float load run over into the neighbouring row, which is inside the tensor or guarded by load6
+    Raw6 rt, rb;
+    load6_issue(rt, tl, img, img_end);
+    load6_issue(rb, g.bin ? tl + (size_t)W * 3 : tl, img, img_end);
+    float top[6], bot[6];
+    load6_select(rt, top);
+    load6_select(rb, bot);
     const bool both = g.rin && g.bin;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float a = __ldg(tl + c);
-      const float t = g.rin ? __ldg(tl + 3 + c) : 0.f;
-      const float d = g.bin ? __ldg(bl + c) : 0.f;
-      const float e = both ? __ldg(bl + 3 + c) : 0.f;
-      s_out[threadIdx.x * 3 + c] = w_tl * a + w_tr * t + w_bl * d + w_br * e;
-    }
+    for (int c = 0; c < 3; ++c)
+      s_out[threadIdx.x * 3 + c] = w_tl * top[c] + w_tr * (g.rin ? top[3 + c] : 0.f) +
+                                   w_bl * (g.bin ? bot[c] : 0.f) + w_br * (both ? bot[3 + c] : 0.f);
   }
   __syncthreads();
   const int n = min(PIX_THREADS, Wg - x0) * 3;
@@ -285,14 +343,17 @@ warp_bwd_c3(const float* __restrict__ img, const float* __restrict__ grid, const
   const size_t a0 = (((size_t)b * H + g.yi) * W + g.xi) * 3;
   const size_t rowC = (size_t)W * 3;
   const float v0 = s_go[threadIdx.x * 3], v1 = s_go[threadIdx.x * 3 + 1], v2 = s_go[threadIdx.x * 3 + 2];
-  float d_tl, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
-  d_tl = __ldg(img + a0) * v0 + __ldg(img + a0 + 1) * v1 + __ldg(img + a0 + 2) * v2;
-  if (g.rin) d_tr = __ldg(img + a0 + 3) * v0 + __ldg(img + a0 + 4) * v1 + __ldg(img + a0 + 5) * v2;
-  if (g.bin) {
-    d_bl = __ldg(img + a0 + rowC) * v0 + __ldg(img + a0 + rowC + 1) * v1 + __ldg(img + a0 + rowC + 2) * v2;
-    if (g.rin)
-      d_br = __ldg(img + a0 + rowC + 3) * v0 + __ldg(img + a0 + rowC + 4) * v1 + __ldg(img + a0 + rowC + 5) * v2;
-  }
+  const float* img_end = img + gimg_elems;
+  Raw6 rt, rb;
+  load6_issue(rt, img + a0, img, img_end);
+  load6_issue(rb, g.bin ? img + a0 + rowC : img + a0, img, img_end);
+  float top[6], bot[6];
+  load6_select(rt, top);
+  load6_select(rb, bot);
+  const float d_tl = top[0] * v0 + top[1] * v1 + top[2] * v2;
+  const float d_tr = g.rin ? top[3] * v0 + top[4] * v1 + top[5] * v2 : 0.f;
+  const float d_bl = g.bin ? bot[0] * v0 + bot[1] * v1 + bot[2] * v2 : 0.f;
+  const float d_br = (g.rin && g.bin) ? bot[3] * v0 + bot[4] * v1 + bot[5] * v2 : 0.f;
   if (!ONLY_GRID) {
     if (g.rin) {
       const float top[6] = {w_tl * v0, w_tl * v1, w_tl * v2, w_tr * v0, w_tr * v1, w_tr * v2};
@@ -376,12 +437,12 @@ extern "C" int b2f_warp_bhwd_forward(const float* img, const float* grid, float*
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((C & 3) == 0 && aligned16(img) && aligned16(out)) {
-    dim3 grid_dim((Wg + 31) / 32, Hg, B);
+    dim3 grid_dim((Wg + 32 * VEC_PPT - 1) / (32 * VEC_PPT), Hg, B);
     warp_fwd_vec4<<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, out, H, W, C, Hg, Wg);
     B2F_CHECK_LAUNCH("warp_fwd_vec4");
   } else if (C == 3) {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
-    warp_fwd_c3<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg);
+    warp_fwd_c3<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg, img + (size_t)B * H * W * 3);
     B2F_CHECK_LAUNCH("warp_fwd_c3");
   } else {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
