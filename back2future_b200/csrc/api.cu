@@ -55,19 +55,7 @@ const char* b2f_status_string(int status) {
   return "unknown status";
 }
 
-int b2f_release_scratch(void) {
-  // Scratch is stream-ordered (cudaMallocAsync per criterion call); trimming the default pool
-  // returns it to the driver.
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return b2f::cuda_fail(e, "cudaGetDevice");
-  cudaMemPool_t pool;
-  e = cudaDeviceGetDefaultMemPool(&pool, dev);
-  if (e != cudaSuccess) return b2f::cuda_fail(e, "cudaDeviceGetDefaultMemPool");
-  e = cudaMemPoolTrimTo(pool, 0);
-  if (e != cudaSuccess) return b2f::cuda_fail(e, "cudaMemPoolTrimTo");
-  return B2F_OK;
-}
+int b2f_release_scratch(void) { return b2f::release_scratch_for_thread(); }
 
 int b2f_debug_costvol_path(int mode) {
   int prev = b2f::g_force_generic;

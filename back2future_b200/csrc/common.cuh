@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 int fail(int status, const char* fmt, ...);          // sets the message, returns status
 int cuda_fail(cudaError_t e, const char* where);     // positive cudaError_t + message
 void count_launch(int n = 1);
+int release_scratch_for_thread();   // criterions.cu
 int costvol_path();   // 0 auto, 1 generic, 2/3/4 force the tiled kernels (fwd strip width 16/8/4)
 
 #define B2F_CUDA_TRY(expr)                                              \

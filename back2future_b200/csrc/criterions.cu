@@ -9,7 +9,7 @@
 namespace b2f {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;   // one thread per pixel of a row segment; grid = (x tiles, row, batch)
 
 struct LossOut {
   double* partials;   // [gridDim.x]
@@ -28,20 +28,22 @@ __device__ __forceinline__ void finish_loss(float local, const LossOut& lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) s_warp[warp] = v;
   __syncthreads();
+  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < kThreads / 32; ++i) t += s_warp[i];
-    lo.partials[blockIdx.x] = t;
+    lo.partials[bid] = t;
     __threadfence();
     const unsigned ticket = atomicAdd(lo.counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
+    s_last = (ticket == nblocks - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   // last block: fixed-order sum of the block partials
   double t = 0.0;
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) t += __ldcg(lo.partials + i);
+  for (unsigned i = threadIdx.x; i < nblocks; i += kThreads) t += __ldcg(lo.partials + i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   __syncthreads();
@@ -56,39 +58,103 @@ __device__ __forceinline__ void finish_loss(float local, const LossOut& lo) {
   }
 }
 
-// Host side of the loss delivery: stream-ordered scratch, optional synchronous read-back.
+// Host side of the loss delivery.  The scratch for the block partials is owned by the library: one
+// buffer per (host thread, device, stream), grown on demand and reused by later calls on that stream
+// (calls on one stream are ordered, so reuse is safe); b2f_release_scratch() frees the calling thread's
+// buffers.  (A per-call cudaMallocAsync/cudaFreeAsync pair cost milliseconds: the default pool's release
+// threshold is 0, so every synchronisation handed the memory back to the driver.)
+struct ScratchEntry {
+  int dev;
+  cudaStream_t st;
+  void* mem;
+  size_t bytes;
+};
+struct ScratchCache {
+  ScratchEntry e[16];
+  int n = 0;
+  ~ScratchCache() {}   // device memory is released explicitly (b2f_release_scratch) or at process exit
+};
+thread_local ScratchCache g_scratch;
+
+int get_scratch(size_t bytes, cudaStream_t st, void** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  ScratchCache& c = g_scratch;
+  int slot = -1;
+  for (int i = 0; i < c.n; ++i)
+    if (c.e[i].dev == dev && c.e[i].st == st) slot = i;
+  if (slot < 0) {
+    if (c.n == 16) {   // evict the oldest entry
+      cudaFree(c.e[0].mem);
+      for (int i = 1; i < 16; ++i) c.e[i - 1] = c.e[i];
+      c.n = 15;
+    }
+    slot = c.n++;
+    c.e[slot] = {dev, st, nullptr, 0};
+  }
+  ScratchEntry& s = c.e[slot];
+  if (s.bytes < bytes) {
+    if (s.mem) {
+      // earlier kernels on this stream may still be using the old buffer
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(scratch grow)");
+      cudaFree(s.mem);
+      s.mem = nullptr;
+      s.bytes = 0;
+    }
+    size_t want = bytes < (size_t)(1 << 20) ? (size_t)(1 << 20) : bytes * 2;
+    e = cudaMalloc(&s.mem, want);
+    if (e != cudaSuccess) {
+      s.mem = nullptr;
+      return fail(B2F_ENOMEM, "criterion scratch: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    s.bytes = want;
+  }
+  *out = s.mem;
+  return B2F_OK;
+}
+
 struct LossScratch {
-  void* mem = nullptr;
   LossOut lo{};
   cudaStream_t st = nullptr;
 
   int begin(int blocks, double scale, double* loss_dev, cudaStream_t stream) {
     st = stream;
     const size_t bytes = (size_t)blocks * sizeof(double) + 2 * sizeof(double);
-    cudaError_t e = cudaMallocAsync(&mem, bytes, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(loss scratch)");
+    void* mem = nullptr;
+    int rc = get_scratch(bytes, st, &mem);
+    if (rc) return rc;
     lo.result = reinterpret_cast<double*>(mem);
     lo.counter = reinterpret_cast<unsigned*>(lo.result + 1);
     lo.partials = lo.result + 2;
     lo.loss_dev = loss_dev;
     lo.scale = scale;
-    e = cudaMemsetAsync(lo.counter, 0, sizeof(double), st);
+    cudaError_t e = cudaMemsetAsync(lo.counter, 0, sizeof(double), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(loss counter)");
     return B2F_OK;
   }
   int end(double* loss_host) {
-    cudaError_t e = cudaSuccess;
     if (loss_host) {
-      e = cudaMemcpyAsync(loss_host, lo.result, sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaMemcpyAsync(loss_host, lo.result, sizeof(double), cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "loss read-back");
     }
-    cudaError_t e2 = cudaFreeAsync(mem, st);
-    mem = nullptr;
-    if (e != cudaSuccess) return cuda_fail(e, "loss read-back");
-    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync(loss scratch)");
     return B2F_OK;
   }
 };
+
+}  // namespace
+
+int release_scratch_for_thread() {
+  ScratchCache& c = g_scratch;
+  for (int i = 0; i < c.n; ++i)
+    if (c.e[i].mem) cudaFree(c.e[i].mem);
+  c.n = 0;
+  return B2F_OK;
+}
+
+namespace {
 
 // =======================================================================================
 // OBCC / OBGCC  (criterions/OBCCriterion.lua, criterions/OBGCCriterion.lua), F = 3
@@ -110,13 +176,10 @@ template <int PEN, bool GT>
 __global__ void __launch_bounds__(kThreads)
 ob_kernel(ObArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
-  const int64_t npix = (int64_t)a.B * hw;
-  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
   float loss = 0.f;
-  if (pix < npix) {
-    const int x = (int)(pix % a.w);
-    const int y = (int)((pix / a.w) % a.h);
-    const int b = (int)(pix / hw);
+  if (x < a.w) {
     const int64_t o = (int64_t)y * a.w + x;
     const int w = a.w, h = a.h;
 #pragma unroll
@@ -202,6 +265,7 @@ struct SmArgs {
   int alias;        // order 1: reproduce the view-resize aliasing (only matters when Cin != Ct)
   int64_t n_dy;     // B*Ct*(h-1)*w, elements of the contiguous y-difference array
   int64_t n_dx;     // B*Ct*h*(w-1)
+  int small;        // all flat indices fit in 32 bits
 };
 
 // order-1 edge weights -----------------------------------------------------------------
@@ -211,16 +275,14 @@ __device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
   if (a.alias) {
     // igy(b,j,y,x) = flat(D_y)[((b*Cin+j)*h+y)*w+x], D_y contiguous (B,Ct,h-1,w)   (Q9)
     for (int j = 0; j < a.Cin; ++j) {
-      const int64_t idx = (((int64_t)b * a.Cin + j) * a.h + y) * a.w + x;
+      // idx = t*w + x with t = (b*Cin+j)*h + y, so idx % w == x and idx / w == t: only the small
+      // row counter t has to be decomposed (32-bit)
+      const unsigned t = ((unsigned)b * a.Cin + j) * a.h + y;
       float v = 0.f;
-      if (idx < a.n_dy) {
-        const int xx = (int)(idx % a.w);
-        int64_t t = idx / a.w;
-        const int r = (int)(t % (a.h - 1));
-        t /= (a.h - 1);
-        const int cc = (int)(t % a.Ct);
-        const int bb = (int)(t / a.Ct);
-        const float* p = a.tgt + ((int64_t)bb * a.Ct + cc) * hw + (int64_t)r * a.w + xx;
+      if ((int64_t)t * a.w + x < a.n_dy) {
+        const unsigned r = t % (unsigned)(a.h - 1);
+        const unsigned t2 = t / (unsigned)(a.h - 1);   // = bb*Ct + cc
+        const float* p = a.tgt + (int64_t)t2 * hw + (int64_t)r * a.w + x;
         v = __ldg(p + a.w) - __ldg(p);
       }
       s += fabsf(v);
@@ -244,13 +306,17 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
       const int64_t idx = (((int64_t)b * a.Cin + j) * a.h + y) * a.w + x;
       float v = 0.f;
       if (idx < a.n_dx) {
-        const int xx = (int)(idx % (a.w - 1));
-        int64_t t = idx / (a.w - 1);
-        const int yy = (int)(t % a.h);
-        t /= a.h;
-        const int cc = (int)(t % a.Ct);
-        const int bb = (int)(t / a.Ct);
-        const float* p = a.tgt + ((int64_t)bb * a.Ct + cc) * hw + (int64_t)yy * a.w + xx;
+        // rows of the contiguous x-difference array are w-1 long: row = idx / (w-1), 32-bit when it fits
+        unsigned rowi, xx;
+        if (a.small) {
+          rowi = (unsigned)idx / (unsigned)(a.w - 1);
+          xx = (unsigned)idx - rowi * (unsigned)(a.w - 1);
+        } else {
+          rowi = (unsigned)(idx / (a.w - 1));
+          xx = (unsigned)(idx - (int64_t)rowi * (a.w - 1));
+        }
+        // rowi = (bb*Ct + cc)*h + yy and the target rows are contiguous, so the source offset is rowi*w + xx
+        const float* p = a.tgt + (int64_t)rowi * a.w + xx;
         v = __ldg(p + 1) - __ldg(p);
       }
       s += fabsf(v);
@@ -270,13 +336,10 @@ template <int PEN>
 __global__ void __launch_bounds__(kThreads)
 smooth1_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
-  const int64_t npix = (int64_t)a.B * hw;
-  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
   float loss = 0.f;
-  if (pix < npix) {
-    const int x = (int)(pix % a.w);
-    const int y = (int)((pix / a.w) % a.h);
-    const int b = (int)(pix / hw);
+  if (x < a.w) {
     const int w = a.w, h = a.h;
     const float wx0 = w1_x(a, b, y, x), wy0 = w1_y(a, b, y, x);
     const bool need_g = a.grad != nullptr;
@@ -329,13 +392,10 @@ template <int PEN>
 __global__ void __launch_bounds__(kThreads)
 smooth2_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
-  const int64_t npix = (int64_t)a.B * hw;
-  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
   float loss = 0.f;
-  if (pix < npix) {
-    const int x = (int)(pix % a.w);
-    const int y = (int)((pix / a.w) % a.h);
-    const int b = (int)(pix / hw);
+  if (x < a.w) {
     const int w = a.w, h = a.h;
     const bool need_g = a.grad != nullptr;
     // weights at the three positions each direction needs
@@ -388,12 +448,10 @@ smooth2_kernel(SmArgs a, LossOut lo) {
 __global__ void __launch_bounds__(kThreads)
 constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float* __restrict__ gf,
                 float* __restrict__ gb, int B, int C, int64_t hw, float gnorm, LossOut lo) {
-  const int64_t npix = (int64_t)B * hw;
-  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;   // pixel inside the image
+  const int b = blockIdx.y;
   float loss = 0.f;
-  if (pix < npix) {
-    const int b = (int)(pix / hw);
-    const int64_t o = pix - (int64_t)b * hw;
+  if (o < hw) {
     float s = 0.f;
     for (int c = 0; c < C; ++c) {
       const int64_t p = ((int64_t)b * C + c) * hw + o;
@@ -418,12 +476,10 @@ constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float
 __global__ void __launch_bounds__(kThreads)
 occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, int C, int64_t hw,
                 float penalty, float norm, LossOut lo) {
-  const int64_t npix = (int64_t)B * hw;
-  const int64_t pix = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int b = blockIdx.y;
   float loss = 0.f;
-  if (pix < npix) {
-    const int b = (int)(pix / hw);
-    const int64_t o = pix - (int64_t)b * hw;
+  if (o < hw) {
     const int64_t p0 = ((int64_t)b * C) * hw + o;
     const float o1 = __ldg(occ + p0), o2 = __ldg(occ + p0 + hw);
     if (C == 3) {
@@ -445,17 +501,29 @@ occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, 
   finish_loss(loss, lo);
 }
 
-int blocks_for_pixels(int64_t npix, int* blocks) {
-  const int64_t nb = (npix + kThreads - 1) / kThreads;
-  if (nb > 0x7fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
-  *blocks = (int)(nb < 1 ? 1 : nb);
+// grid = (x tiles, rows, batch) for the stencil kernels
+int grid_rows(int B, int h, int w, dim3* g, int* blocks) {
+  if (B > 65535 || h > 65535) return fail(B2F_EINVAL, "criterion: B and h must be <= 65535");
+  *g = dim3((w + kThreads - 1) / kThreads, h, B);
+  const int64_t nb = (int64_t)g->x * g->y * g->z;
+  if (nb > 0x3fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
+  *blocks = (int)nb;
+  return B2F_OK;
+}
+// grid = (pixel tiles, batch) for the pointwise kernels
+int grid_flat(int B, int64_t hw, dim3* g, int* blocks) {
+  if (B > 65535) return fail(B2F_EINVAL, "criterion: B must be <= 65535");
+  const int64_t gx = (hw + kThreads - 1) / kThreads;
+  if (gx * B > 0x3fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
+  *g = dim3((unsigned)gx, B, 1);
+  *blocks = (int)(gx * B);
   return B2F_OK;
 }
 
 bool valid_penalty(int p) { return p == B2F_PENALTY_QUADRATIC || p == B2F_PENALTY_L1 || p == B2F_PENALTY_LORENTZIAN; }
 
 template <bool GT>
-void launch_ob(int pen, int blocks, cudaStream_t st, const ObArgs& a, const LossOut& lo) {
+void launch_ob(int pen, dim3 blocks, cudaStream_t st, const ObArgs& a, const LossOut& lo) {
   if (pen == B2F_PENALTY_QUADRATIC) ob_kernel<B2F_PENALTY_QUADRATIC, GT><<<blocks, kThreads, 0, st>>>(a, lo);
   else if (pen == B2F_PENALTY_L1) ob_kernel<B2F_PENALTY_L1, GT><<<blocks, kThreads, 0, st>>>(a, lo);
   else ob_kernel<B2F_PENALTY_LORENTZIAN, GT><<<blocks, kThreads, 0, st>>>(a, lo);
@@ -479,7 +547,8 @@ extern "C" int b2f_ob_criterion(const b2f_ob_params* prm, const float* flow, con
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t npix = (int64_t)B * h * w;
   int blocks;
-  int rc = blocks_for_pixels(npix, &blocks);
+  dim3 grid;
+  int rc = grid_rows(B, h, w, &grid, &blocks);
   if (rc) return rc;
   const int F = 3;
   double scale = 1.0 / ((double)C * (F - 1));
@@ -503,8 +572,8 @@ extern "C" int b2f_ob_criterion(const b2f_ob_params* prm, const float* flow, con
   a.grad_check = prm->grad_check;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
-  if (prm->gradient_terms) launch_ob<true>(prm->penalty, blocks, st, a, ls.lo);
-  else launch_ob<false>(prm->penalty, blocks, st, a, ls.lo);
+  if (prm->gradient_terms) launch_ob<true>(prm->penalty, grid, st, a, ls.lo);
+  else launch_ob<false>(prm->penalty, grid, st, a, ls.lo);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
@@ -523,7 +592,8 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t npix = (int64_t)B * h * w;
   int blocks;
-  int rc = blocks_for_pixels(npix, &blocks);
+  dim3 grid;
+  int rc = grid_rows(B, h, w, &grid, &blocks);
   if (rc) return rc;
   const double scale = prm->size_average ? 1.0 / ((double)npix * Cin) : 1.0;
   SmArgs a;
@@ -535,17 +605,18 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   a.alias = (prm->alias_weights && Cin != Ct) ? 1 : 0;
   a.n_dy = (int64_t)B * Ct * (h - 1) * w;
   a.n_dx = (int64_t)B * Ct * h * (w - 1);
+  a.small = ((int64_t)B * (Cin > Ct ? Cin : Ct) * h * w) < ((int64_t)1 << 31) ? 1 : 0;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
   const int pen = prm->penalty;
   if (prm->order == 1) {
-    if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<blocks, kThreads, 0, st>>>(a, ls.lo);
-    else if (pen == B2F_PENALTY_L1) smooth1_kernel<B2F_PENALTY_L1><<<blocks, kThreads, 0, st>>>(a, ls.lo);
-    else smooth1_kernel<B2F_PENALTY_LORENTZIAN><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else if (pen == B2F_PENALTY_L1) smooth1_kernel<B2F_PENALTY_L1><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else smooth1_kernel<B2F_PENALTY_LORENTZIAN><<<grid, kThreads, 0, st>>>(a, ls.lo);
   } else {
-    if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<blocks, kThreads, 0, st>>>(a, ls.lo);
-    else if (pen == B2F_PENALTY_L1) smooth2_kernel<B2F_PENALTY_L1><<<blocks, kThreads, 0, st>>>(a, ls.lo);
-    else smooth2_kernel<B2F_PENALTY_LORENTZIAN><<<blocks, kThreads, 0, st>>>(a, ls.lo);
+    if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else if (pen == B2F_PENALTY_L1) smooth2_kernel<B2F_PENALTY_L1><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else smooth2_kernel<B2F_PENALTY_LORENTZIAN><<<grid, kThreads, 0, st>>>(a, ls.lo);
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
@@ -562,14 +633,15 @@ extern "C" int b2f_constvel_criterion(const float* f, const float* b, int B, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
   int blocks;
-  int rc = blocks_for_pixels(npix, &blocks);
+  dim3 grid;
+  int rc = grid_flat(B, hw, &grid, &blocks);
   if (rc) return rc;
   // forward: 1/nElement (ConstVelCriterion.lua:33, 41-43); backward: 1/npixels (:58, 69-72)  (Q11)
   const double scale = size_average ? 1.0 / ((double)npix * C) : 1.0;
   const float gnorm = size_average ? (float)(1.0 / (double)npix) : 1.f;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
-  constvel_kernel<<<blocks, kThreads, 0, st>>>(f, b, grad_f, grad_b, B, C, hw, gnorm, ls.lo);
+  constvel_kernel<<<grid, kThreads, 0, st>>>(f, b, grad_f, grad_b, B, C, hw, gnorm, ls.lo);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
@@ -586,12 +658,13 @@ extern "C" int b2f_occprior_criterion(const float* occ, int B, int C, int h, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
   int blocks;
-  int rc = blocks_for_pixels(npix, &blocks);
+  dim3 grid;
+  int rc = grid_flat(B, hw, &grid, &blocks);
   if (rc) return rc;
   const double scale = size_average ? 1.0 / (double)npix : 1.0;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
-  occprior_kernel<<<blocks, kThreads, 0, st>>>(occ, grad, B, C, hw, penalty, (float)scale, ls.lo);
+  occprior_kernel<<<grid, kThreads, 0, st>>>(occ, grad, B, C, hw, penalty, (float)scale, ls.lo);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
