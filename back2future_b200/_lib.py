@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2f_cuda.so")
+# B2F_LIB_PATH selects another build of the same library (kernel experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("B2F_LIB_PATH") or os.path.join(_HERE, "libb2f_cuda.so")
 
 B2F_OK = 0
 PENALTY_QUADRATIC, PENALTY_L1, PENALTY_LORENTZIAN = 0, 1, 2

@@ -15,7 +15,8 @@ int fail(int status, const char* fmt, ...);          // sets the message, return
 int cuda_fail(cudaError_t e, const char* where);     // positive cudaError_t + message
 void count_launch(int n = 1);
 int release_scratch_for_thread();   // criterions.cu
-int costvol_path();   // 0 auto, 1 generic, 2/3/4 force the tiled kernels (fwd strip width 16/8/4)
+int costvol_path();   // 0 auto, 1 generic, 2/3: tiled (32-column fwd tiles), 4: 16-column tiles, 5: channel split,
+                      // 6/7: force / forbid the software-pipelined forward
 
 #define B2F_CUDA_TRY(expr)                                              \
   do {                                                                  \

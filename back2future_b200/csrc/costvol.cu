@@ -17,6 +17,7 @@
 #include "tma.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace b2f {
 namespace {
@@ -119,12 +120,15 @@ costvol_bwd_generic(FramePtrs fr, int F, int which, int B, int C, int H, int W, 
 namespace cvf {
 constexpr int TH = 8;    // tile rows
 constexpr int CK = 8;    // channels per pipeline stage
-constexpr int NS = 3;    // pipeline stages
 constexpr int NCW = 9;   // compute warps = window rows
 constexpr int THREADS = (NCW + 1) * 32;
 
-template <int A>
+// PIPE = true : one CTA per SM, up to 168 registers, operand registers double-buffered (the loads of
+//               channel c+1 are in flight under the FFMAs of channel c), 6-stage ring.
+// PIPE = false: two CTAs per SM, 96 registers, 3-stage ring (small levels: more CTAs, latency-bound anyway).
+template <int A, bool PIPE>
 struct Cfg {
+  static constexpr int NS = PIPE ? 4 : 3;   // pipeline stages
   static constexpr int TW = 4 * A;
   static constexpr int RW = TW + 4;         // ref box width   (RW/4 odd)
   static constexpr int FW = TW + 12;        // frame box width (FW/4 odd), covers the +-4 halo
@@ -133,36 +137,138 @@ struct Cfg {
   static constexpr int FRM_ELEMS = CK * FR * FW;
   static constexpr int STAGE_ELEMS = REF_ELEMS + FRM_ELEMS;
   static constexpr int STAGE_BYTES = STAGE_ELEMS * 4;
-  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 2 * NS * 8 + 128;
+  // PIPE: the 81 x 8 x 32 output tile is staged in shared memory (128-byte swizzle) and written by one TMA
+  // store, so the compute warps go straight on to the next tile
+  static constexpr int OUT_BYTES = PIPE ? 81 * TH * TW * 4 : 0;
+  static constexpr int SMEM_BYTES = OUT_BYTES + NS * STAGE_BYTES + 2 * NS * 8 + 1024;
+  static constexpr int CTAS_PER_SM = PIPE ? 1 : 2;
+  // register budget: the register file is 16K per scheduler and warps are placed four at a time, so
+  // 2 CTAs x 10 warps -> 5 warps per scheduler x 96; 1 CTA x 10 warps -> 3 per scheduler x 168
+  static constexpr int MAXREG = PIPE ? 168 : 96;
   static_assert((RW / 4) % 2 == 1 && (FW / 4) % 2 == 1, "row pitch must be odd*16B");
   static_assert((REF_ELEMS * 4) % 128 == 0 && (FRM_ELEMS * 4) % 128 == 0, "TMA dst alignment");
+  static_assert(SMEM_BYTES * CTAS_PER_SM <= 227 * 1024, "shared memory budget");
+  static_assert(!PIPE || TW * 4 == 128, "the swizzled staging tile needs 128-byte rows");
+  static_assert(OUT_BYTES % 1024 == 0 && STAGE_BYTES % 128 == 0, "alignment");
 };
 
+template <int A>
+struct Operands {
+  float rv[A], fv[A + 8];
+};
+
+template <int A>
+__device__ __forceinline__ void load_operands(Operands<A>& o, uint32_t rs, uint32_t fs) {
+#pragma unroll
+  for (int q = 0; q < A / 4; ++q) {
+    const float4 v = lds128(rs + 16u * q);
+    o.rv[4 * q] = v.x; o.rv[4 * q + 1] = v.y; o.rv[4 * q + 2] = v.z; o.rv[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int q = 0; q < (A + 8) / 4; ++q) {
+    const float4 v = lds128(fs + 16u * q);
+    o.fv[4 * q] = v.x; o.fv[4 * q + 1] = v.y; o.fv[4 * q + 2] = v.z; o.fv[4 * q + 3] = v.w;
+  }
+}
+
 template <int A, int SGN>
-__global__ void __launch_bounds__(THREADS, A <= 8 ? 2 : 1)
+__device__ __forceinline__ void fma_window_row(float (&acc)[9][A], const Operands<A>& o) {
+#pragma unroll
+  for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+    for (int j = 0; j < A; ++j)
+      acc[ix][j] = fmaf(o.rv[j], o.fv[j + (SGN > 0 ? 8 - ix : ix)], acc[ix][j]);
+}
+
+// FFMA2 form (PIPE kernels).  For pixel j the nine window columns read the nine consecutive frame values
+// fv[j + d], d = 0..8 (d = ix when SGN < 0, 8 - ix when SGN > 0), all multiplied by the same ref value rv[j].
+// Two neighbouring d form one FFMA2 whose multiplicand pair is a LOADED, even-aligned frame pair and whose
+// multiplier is rv[j] broadcast (the scalar-operand form of FFMA2): d pairs (0,1)(2,3)(4,5)(6,7) + scalar d = 8
+// for even j, scalar d = 0 + pairs (1,2)(3,4)(5,6)(7,8) for odd j.  No register shuffling at all; per channel
+// 32 FFMA2 + 8 FFMA instead of 72 FFMA: about half the issue slots and register-file reads per FMA (measured on
+// B200: 102 vs 87 FMA/clk/SM, tools/ubench/smem_fma.cu).  Each half is an fp32 fma, rounded exactly as fmaf.
+template <int A>
+struct Operands2 {
+  float rv[A];
+  f32x2 fe[(A + 8) / 2];   // fe[m] = (fv[2m], fv[2m+1])
+};
+
+template <int A>
+__device__ __forceinline__ void load_operands2(Operands2<A>& o, uint32_t rs, uint32_t fs) {
+#pragma unroll
+  for (int q = 0; q < A / 4; ++q) {
+    const float4 v = lds128(rs + 16u * q);
+    o.rv[4 * q] = v.x; o.rv[4 * q + 1] = v.y; o.rv[4 * q + 2] = v.z; o.rv[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int q = 0; q < (A + 8) / 4; ++q) lds128_pairs(fs + 16u * q, o.fe[2 * q], o.fe[2 * q + 1]);
+}
+
+// accumulators of one thread: A pixels x 9 frame offsets d
+template <int A>
+struct Acc2 {
+  f32x2 pair[A][4];   // pixel j, offsets (2m + (j&1), 2m + 1 + (j&1))
+  float single[A];    // pixel j, offset 8 (j even) or 0 (j odd)
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) pair[j][m] = 0ull;
+      single[j] = 0.f;
+    }
+  }
+  // value for pixel j at frame offset d (compile-time indices only)
+  __device__ __forceinline__ float get(int j, int d) const {
+    const int odd = j & 1;
+    if (d == (odd ? 0 : 8)) return single[j];
+    float lo, hi;
+    unpack2(pair[j][(d - odd) >> 1], lo, hi);
+    return ((d - odd) & 1) ? hi : lo;
+  }
+};
+
+template <int A>
+__device__ __forceinline__ void fma2_window_row(Acc2<A>& acc, const Operands2<A>& o) {
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    const int odd = j & 1;
+    const f32x2 s = pack2(o.rv[j], o.rv[j]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc.pair[j][m] = fma2(s, o.fe[(j + odd + 2 * m) >> 1], acc.pair[j][m]);
+    float lo, hi;
+    unpack2(o.fe[odd ? (j - 1) >> 1 : (j + 8) >> 1], lo, hi);
+    acc.single[j] = fmaf(o.rv[j], odd ? hi : lo, acc.single[j]);
+  }
+}
+
+// Persistent kernel: CTA c takes tiles c, c + gridDim.x, ... in raster order (x fastest), so the CTAs active
+// at any moment sit on neighbouring tiles and share their halos in L2.  The channel chunks of a CTA's
+// consecutive tiles flow through ONE ring: the producer is already fetching the next tile while the consumers
+// finish (and store) the current one.
+// Small levels: the channel range is split over nsplit work items whose partial sums are reduced with
+// red.global.add into a pre-zeroed output (enough items to fill 148 SMs from a handful of tiles).
+template <int A, int SGN, bool PIPE>
+__global__ void __maxnreg__((Cfg<A, PIPE>::MAXREG))
 costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_frm,
-                float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv, int nsplit,
-                int chunks_per_split) {
-  using cfg = Cfg<A>;
+                const __grid_constant__ CUtensorMap tm_out, float* __restrict__ out, int64_t obs, int C, int H, int W, float kdiv, int nsplit,
+                int chunks_per_split, int ntx, int nty, int ntiles, int dbg) {
+  using cfg = Cfg<A, PIPE>;
+  constexpr int NS = cfg::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // pointer + integer offset keeps the shared address space (LDS, not generic LD)
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float* stages = reinterpret_cast<float*>(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * cfg::STAGE_BYTES);
-  uint64_t* empty = full + NS;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // 32-bit shared addresses throughout (a generic pointer costs an S2R + LEA per access in the loop)
+  const uint32_t obase = smem_u32(smem);               // output staging tile (PIPE), 1024-byte aligned
+  const uint32_t sbase = obase + cfg::OUT_BYTES;       // ring stages
+  const uint32_t full0 = sbase + NS * cfg::STAGE_BYTES, empty0 = full0 + 8u * NS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * cfg::TW, y0 = blockIdx.y * TH;
-  // small levels: the channel range is split over nsplit CTAs whose partial sums are reduced with
-  // red.global.add into a pre-zeroed output (enough CTAs to fill 148 SMs from a handful of tiles)
-  const int b = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
-  const int kbeg = split * chunks_per_split;
-  const int nchunks = min((C + CK - 1) / CK - kbeg, chunks_per_split);
+  const int nchunks_all = (C + CK - 1) / CK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NCW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::OUT_BYTES + NS * cfg::STAGE_BYTES);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(bars + i, 1);
+      mbar_init(bars + NS + i, NCW);
     }
     mbar_fence_init();
   }
@@ -172,86 +278,156 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tm_ref);
       tma_prefetch_desc(&tm_frm);
-      for (int k = 0; k < nchunks; ++k) {
-        const int s = k % NS, it = k / NS;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        float* rs = stages + s * cfg::STAGE_ELEMS;
-        float* fs = rs + cfg::REF_ELEMS;
-        mbar_arrive_expect_tx(&full[s], cfg::STAGE_BYTES);
-        tma_load_4d(rs, &tm_ref, x0, y0, (kbeg + k) * CK, b, &full[s]);
-        tma_load_4d(fs, &tm_frm, x0 - 4, y0 - 4, (kbeg + k) * CK, b, &full[s]);
+      int s = 0;
+      uint32_t ph = 0;
+      bool wrapped = false;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = t % ntx, tq = t / ntx;
+        const int ty = tq % nty, bz = tq / nty;
+        const int b = bz / nsplit, split = bz - b * nsplit;
+        const int x0 = tx * cfg::TW, y0 = ty * TH;
+        const int kbeg = split * chunks_per_split;
+        const int nchunks = min(nchunks_all - kbeg, chunks_per_split);
+        for (int k = 0; k < nchunks; ++k) {
+          if (wrapped) mbar_wait_addr(empty0 + 8u * s, ph);
+          const uint32_t rs = sbase + (uint32_t)s * cfg::STAGE_BYTES;
+          const uint32_t fs = rs + 4u * cfg::REF_ELEMS;
+          mbar_expect_tx_addr(full0 + 8u * s, cfg::STAGE_BYTES);
+          tma_load_4d_addr(rs, &tm_ref, x0, y0, (kbeg + k) * CK, b, full0 + 8u * s);
+          tma_load_4d_addr(fs, &tm_frm, x0 - 4, y0 - 4, (kbeg + k) * CK, b, full0 + 8u * s);
+          if (++s == NS) {
+            s = 0;
+            if (wrapped) ph ^= 1u;
+            wrapped = true;
+          }
+        }
       }
     }
     return;
   }
 
   // ---- consumers ----
-  const int r = lane & 7, st = lane >> 3;
   const int iy = warp;
+  const int r = lane & 7, st = lane >> 3;
   const int frow = r + 4 - SGN * (iy - 4);  // frame box row of this thread's source pixels
+  // THC's div(scalar) multiplies floats by the reciprocal; so do we.
+  const float kinv = 1.f / kdiv;
+  const int64_t hw = (int64_t)H * W;
+  const uint32_t roff = sbase + 4u * (r * cfg::RW + A * st);
+  const uint32_t foff = sbase + 4u * (cfg::REF_ELEMS + frow * cfg::FW + A * st);
+  constexpr uint32_t RSTEP = 4u * (TH * cfg::RW), FSTEP = 4u * (cfg::FR * cfg::FW);
 
-  float acc[9][A];
-#pragma unroll
-  for (int ix = 0; ix < 9; ++ix)
-#pragma unroll
-    for (int j = 0; j < A; ++j) acc[ix][j] = 0.f;
+  int s = 0;            // ring position of the next chunk
+  uint32_t ph = 0;      // its phase parity
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tx = t % ntx, tq = t / ntx;
+    const int ty = tq % nty, bz = tq / nty;
+    const int b = bz / nsplit, split = bz - b * nsplit;
+    const int nchunks = min(nchunks_all - split * chunks_per_split, chunks_per_split);
 
-  for (int k = 0; k < nchunks; ++k) {
-    const int s = k % NS, it = k / NS;
-    mbar_wait(&full[s], it & 1);
-    const float* rs = stages + s * cfg::STAGE_ELEMS + r * cfg::RW + A * st;
-    const float* fs = stages + s * cfg::STAGE_ELEMS + cfg::REF_ELEMS + frow * cfg::FW + A * st;
-#pragma unroll 1
-    for (int cc = 0; cc < CK; ++cc) {
-      float rv[A], fv[A + 8];
-#pragma unroll
-      for (int q = 0; q < A / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(rs + cc * (TH * cfg::RW) + 4 * q);
-        rv[4 * q] = v.x; rv[4 * q + 1] = v.y; rv[4 * q + 2] = v.z; rv[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int q = 0; q < (A + 8) / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(fs + cc * (cfg::FR * cfg::FW) + 4 * q);
-        fv[4 * q] = v.x; fv[4 * q + 1] = v.y; fv[4 * q + 2] = v.z; fv[4 * q + 3] = v.w;
-      }
+    // PIPE: packed accumulators (FFMA2 form); else scalar (FFMA form)
+    Acc2<PIPE ? A : 4> acc2;
+    float acc[PIPE ? 1 : 9][PIPE ? 1 : A];
+    if constexpr (PIPE) {
+      acc2.clear();
+    } else {
 #pragma unroll
       for (int ix = 0; ix < 9; ++ix)
 #pragma unroll
-        for (int j = 0; j < A; ++j)
-          acc[ix][j] = fmaf(rv[j], fv[j + (SGN > 0 ? 8 - ix : ix)], acc[ix][j]);
+        for (int j = 0; j < A; ++j) acc[ix][j] = 0.f;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
 
-  // ---- epilogue: out[b, ix*9+iy, y, x0 + A*st + j] ----
-  // THC's div(scalar) multiplies floats by the reciprocal; so do we.
-  const float kinv = 1.f / kdiv;
-  const int y = y0 + r;
-  if (y < H) {
-    const int64_t hw = (int64_t)H * W;
-    const int xb = x0 + A * st;
-    float* ob = out + (int64_t)b * obs + (int64_t)y * W + xb;
+    for (int k = 0; k < nchunks; ++k) {
+      mbar_wait_addr(full0 + 8u * s, ph);
+      uint32_t rs = roff + (uint32_t)s * cfg::STAGE_BYTES;
+      uint32_t fs = foff + (uint32_t)s * cfg::STAGE_BYTES;
+      if (dbg & 1) {
+        // measurement aid (b2f_debug_costvol_path 8/10): TMA feed only, no arithmetic
+      } else if constexpr (PIPE) {
+        // two operand sets: the loads of the next channel are issued before the FFMAs of the current one
+        Operands2<A> o0, o1;
+        load_operands2<A>(o0, rs, fs);
+#pragma unroll 1
+        for (int cc = 0; cc < CK; cc += 2) {
+          load_operands2<A>(o1, rs + RSTEP, fs + FSTEP);
+          fma2_window_row<A>(acc2, o0);
+          rs += 2 * RSTEP;
+          fs += 2 * FSTEP;
+          if (cc + 2 < CK) load_operands2<A>(o0, rs, fs);
+          fma2_window_row<A>(acc2, o1);
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < CK; ++cc) {
+          Operands<A> o;
+          load_operands<A>(o, rs, fs);
+          rs += RSTEP;
+          fs += FSTEP;
+          fma_window_row<A, SGN>(acc, o);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(empty0 + 8u * s);
+      if (++s == NS) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+
+    // ---- epilogue: out[b, ix*9+iy, y, x0 + A*st + j] ----
+    if constexpr (PIPE) {
+      // stage the tile as [channel][row][32 columns] with the TMA 128-byte swizzle (16-byte chunk c of row R
+      // sits at chunk c ^ (R & 7)): the eight rows of a quarter-warp hit eight different bank groups
+      if (warp == 0) {   // the previous tile's TMA store must have finished reading the staging tile
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      named_bar_sync(1, NCW * 32);
 #pragma unroll
-    for (int ix = 0; ix < 9; ++ix) {
-      float* o = ob + (int64_t)(ix * 9 + iy) * hw;
+      for (int ix = 0; ix < 9; ++ix) {
+        const uint32_t rowaddr = obase + (uint32_t)(((ix * 9 + iy) * TH + r) * 128);
 #pragma unroll
-      for (int q = 0; q < A / 4; ++q) {
-        if (xb + 4 * q < W) {
-          float4 v;
-          v.x = acc[ix][4 * q] * kinv; v.y = acc[ix][4 * q + 1] * kinv;
-          v.z = acc[ix][4 * q + 2] * kinv; v.w = acc[ix][4 * q + 3] * kinv;
-          if (nsplit == 1) {
-            *reinterpret_cast<float4*>(o + 4 * q) = v;
-          } else {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * q), "f"(v.x), "f"(v.y),
-                         "f"(v.z), "f"(v.w)
-                         : "memory");
+        for (int q = 0; q < A / 4; ++q) {
+          const int d = SGN > 0 ? 8 - ix : ix;
+          const float4 v = make_float4(acc2.get(4 * q, d) * kinv, acc2.get(4 * q + 1, d) * kinv,
+                                       acc2.get(4 * q + 2, d) * kinv, acc2.get(4 * q + 3, d) * kinv);
+          sts128(rowaddr + 16u * (uint32_t)(((A / 4) * st + q) ^ r), v);
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, NCW * 32);
+      if (warp == 0 && lane == 0 && !(dbg & 2)) {
+        if (nsplit == 1) tma_store_4d_addr(obase, &tm_out, tx * cfg::TW, ty * TH, 0, b);
+        else tma_reduce_add_4d_addr(obase, &tm_out, tx * cfg::TW, ty * TH, 0, b);
+        tma_store_commit();
+      }
+    } else {
+      const int y = ty * TH + r;
+      if (y < H && !(dbg & 2)) {
+        const int xb = tx * cfg::TW + A * st;
+        float* ob = out + (int64_t)b * obs + (int64_t)y * W + xb + (int64_t)iy * hw;
+#pragma unroll
+        for (int ix = 0; ix < 9; ++ix) {
+          float* o = ob + (int64_t)(ix * 9) * hw;
+#pragma unroll
+          for (int q = 0; q < A / 4; ++q) {
+            if (xb + 4 * q < W) {
+              const float4 v = make_float4(acc[ix][4 * q] * kinv, acc[ix][4 * q + 1] * kinv,
+                                           acc[ix][4 * q + 2] * kinv, acc[ix][4 * q + 3] * kinv);
+              if (nsplit == 1) {
+                *reinterpret_cast<float4*>(o + 4 * q) = v;
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * q), "f"(v.x), "f"(v.y),
+                             "f"(v.z), "f"(v.w)
+                             : "memory");
+              }
+            }
           }
         }
       }
     }
   }
+  if (PIPE && warp == 0 && lane == 0) tma_store_wait_read();   // shared memory must outlive the last store
 }
 }  // namespace cvf
 
@@ -333,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
                 const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_go1,
                 float* __restrict__ grad_ref, float* __restrict__ grad_frame, int nroles, int role0,
-                int nchunk, int C, int H, int W, float kdiv) {
+                int nchunk, int C, int H, int W, float kdiv, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer + integer offset keeps the shared address space (LDS, not generic LD)
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -423,6 +599,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     // producer refills it a whole window row earlier
     __syncwarp();
     if (lane == 0) mbar_arrive(&gempty[s]);
+    if (dbg & 1) continue;   // measurement aid: feed only
     if (T > 0) slab_fma<1>(acc, g, xs);
     else       slab_fma<-1>(acc, g, xs);
   }
@@ -432,7 +609,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   float* outp = (role == 0) ? grad_ref : grad_frame;
   const int y = y0 + r;
   const int xb = x0 + 8 * st;
-  if (y < H && xb < W) {
+  if (y < H && xb < W && !(dbg & 2)) {
     const int64_t hw = (int64_t)H * W;
 #pragma unroll
     for (int c = 0; c < CG; ++c) {
@@ -474,11 +651,26 @@ int grid_for(int64_t total, int threads) {
   return (int)blocks;
 }
 
-template <int A, int SGN>
-int launch_fwd_tma(const CUtensorMap& tr, const CUtensorMap& tf, float* out, int64_t obs, int B, int C, int H,
-                   int W, float kdiv, int nsplit, cudaStream_t st) {
-  using cfg = cvf::Cfg<A>;
-  auto kern = cvf::costvol_fwd_tma<A, SGN>;
+template <int A, int SGN, bool PIPE>
+int launch_fwd_tma(const float* ref, const float* frm, float* out, int64_t obs, int B, int C, int H, int W,
+                   float kdiv, int nsplit, cudaStream_t st) {
+  using cfg = cvf::Cfg<A, PIPE>;
+  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+  const uint64_t str[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)W * H * C};
+  const uint32_t box_r[4] = {(uint32_t)cfg::RW, (uint32_t)cvf::TH, (uint32_t)cvf::CK, 1};
+  const uint32_t box_f[4] = {(uint32_t)cfg::FW, (uint32_t)cfg::FR, (uint32_t)cvf::CK, 1};
+  CUtensorMap tr, tf;
+  int rc = make_tmap4(&tr, ref, dims, str, box_r);
+  if (rc) return rc;
+  if ((rc = make_tmap4(&tf, frm, dims, str, box_f))) return rc;
+  CUtensorMap to = tr;   // PIPE only: (W, H, 81, B) view of the output, 128-byte swizzled 32 x 8 x 81 boxes
+  if (PIPE) {
+    const uint64_t odims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+    const uint64_t ostr[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)obs};
+    const uint32_t box_o[4] = {(uint32_t)cfg::TW, (uint32_t)cvf::TH, 81, 1};
+    if ((rc = make_tmap4(&to, out, odims, ostr, box_o, true))) return rc;
+  }
+  auto kern = cvf::costvol_fwd_tma<A, SGN, PIPE>;
   static thread_local int attr_dev = -1;
   int dev = 0;
   B2F_CUDA_TRY(cudaGetDevice(&dev));
@@ -491,23 +683,23 @@ int launch_fwd_tma(const CUtensorMap& tr, const CUtensorMap& tf, float* out, int
   nsplit = (nchunks + cps - 1) / cps;   // no empty splits
   if (nsplit > 1)  // partial sums are accumulated: zero this instance's (B, 81, H, W) block first
     B2F_CUDA_TRY(cudaMemset2DAsync(out, (size_t)obs * 4, 0, (size_t)81 * H * W * 4, (size_t)B, st));
-  dim3 grid((W + cfg::TW - 1) / cfg::TW, (H + cvf::TH - 1) / cvf::TH, B * nsplit);
-  kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, out, obs, C, H, W, kdiv, nsplit, cps);
+  const int ntx = (W + cfg::TW - 1) / cfg::TW, nty = (H + cvf::TH - 1) / cvf::TH;
+  const int64_t ntiles = (int64_t)ntx * nty * B * nsplit;
+  if (ntiles > 0x3fffffff) return fail(B2F_EINVAL, "costvol_forward: too many tiles");
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * cfg::CTAS_PER_SM);
+  const int path = costvol_path();
+  const int dbg = (path >= 8 && path <= 10) ? path - 7 : 0;   // 8: no arithmetic, 9: no stores, 10: neither
+  kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, to, out, obs, C, H, W, kdiv, nsplit, cps, ntx, nty,
+                                                    (int)ntiles, dbg);
   B2F_CHECK_LAUNCH("costvol_fwd_tma");
   return B2F_OK;
 }
 
-template <int A>
-int make_fwd_maps(CUtensorMap* tr, CUtensorMap* tf, const float* ref, const float* frm, int B, int C, int H,
-                  int W) {
-  using cfg = cvf::Cfg<A>;
-  const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
-  const uint64_t str[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)W * H * C};
-  const uint32_t box_r[4] = {(uint32_t)cfg::RW, (uint32_t)cvf::TH, (uint32_t)cvf::CK, 1};
-  const uint32_t box_f[4] = {(uint32_t)cfg::FW, (uint32_t)cfg::FR, (uint32_t)cvf::CK, 1};
-  int rc = make_tmap4(tr, ref, dims, str, box_r);
-  if (rc) return rc;
-  return make_tmap4(tf, frm, dims, str, box_f);
+template <int A, bool PIPE>
+int launch_fwd_sgn(int sgn, const float* ref, const float* frm, float* out, int64_t obs, int B, int C, int H,
+                   int W, float kdiv, int nsplit, cudaStream_t st) {
+  return sgn > 0 ? launch_fwd_tma<A, 1, PIPE>(ref, frm, out, obs, B, C, H, W, kdiv, nsplit, st)
+                 : launch_fwd_tma<A, -1, PIPE>(ref, frm, out, obs, B, C, H, W, kdiv, nsplit, st);
 }
 
 int64_t tiles_for(int A, int B, int H, int W) {
@@ -543,7 +735,8 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
     // not fill the machine the channel range is split across CTAs (path 5 forces a split in tests).
     int A = 0, nsplit = 1;
     const int sms = num_sms();
-    if (path >= 2 && path <= 4) A = path == 2 ? 16 : (path == 3 ? 8 : 4);
+    if (path >= 2 && path <= 4) A = path == 4 ? 4 : 8;   // 2 and 3: 32-column tiles, 4: 16-column tiles
+    else if (path >= 6 && path <= 10) A = 8;
     else if (W >= 32 && tiles_for(8, B, H, W) >= sms) A = 8;
     else A = 4;
     if (A == 4 && (path == 0 || path == 5)) {
@@ -552,19 +745,12 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
       if (2 * t <= sms || path == 5) nsplit = (int)std::min<int64_t>(nchunks, std::max<int64_t>(path == 5 ? 2 : 1, sms / t));
       if ((int64_t)B * nsplit > 65535) nsplit = 1;
     }
-    if (A) {
-      CUtensorMap tr, tf;
-      if (A == 16) rc = make_fwd_maps<16>(&tr, &tf, frames[0], frames[1], B, C, H, W);
-      else if (A == 8) rc = make_fwd_maps<8>(&tr, &tf, frames[0], frames[1], B, C, H, W);
-      else rc = make_fwd_maps<4>(&tr, &tf, frames[0], frames[1], B, C, H, W);
-      if (rc) return rc;
-      if (A == 16) return sgn > 0 ? launch_fwd_tma<16, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
-                                  : launch_fwd_tma<16, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
-      if (A == 8) return sgn > 0 ? launch_fwd_tma<8, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
-                                 : launch_fwd_tma<8, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
-      return sgn > 0 ? launch_fwd_tma<4, 1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st)
-                     : launch_fwd_tma<4, -1>(tr, tf, out, obs, B, C, H, W, kdiv, nsplit, st);
-    }
+    // software-pipelined single-CTA form once every SM gets at least two tiles (path 6 forces it, 7 forbids)
+    const bool pipe = path == 6 || path >= 8 || (path != 7 && tiles_for(A, B, H, W) * nsplit >= 2 * (int64_t)sms);
+    if (A == 8)
+      return pipe ? launch_fwd_sgn<8, true>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st)
+                  : launch_fwd_sgn<8, false>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st);
+    return launch_fwd_sgn<4, false>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st);
   }
 
   FramePtrs fp;
@@ -624,13 +810,14 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
         attr_dev = dev;
       }
       const int role0 = gradFrames[0] ? 0 : 1;
+      const int bdbg = (path >= 8 && path <= 10) ? path - 7 : 0;   // 8: no arithmetic, 9: no stores, 10: neither
       dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
       if (sgn > 0)
         cvb::costvol_bwd_tma<1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv, bdbg);
       else
         cvb::costvol_bwd_tma<-1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv);
+            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv, bdbg);
       B2F_CHECK_LAUNCH("costvol_bwd_tma");
       return B2F_OK;
     }

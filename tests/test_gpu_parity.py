@@ -113,6 +113,9 @@ TILED_CASES = [
     (4, 1, 7, 7, 16), (4, 1, 3, 5, 4),
     # mode 5: channel range split across CTAs, partial sums reduced into a pre-zeroed output
     (5, 2, 24, 14, 32), (5, 1, 192, 7, 16), (5, 2, 20, 9, 20), (5, 1, 3, 5, 4),
+    # mode 6: persistent software-pipelined kernel, output tile staged in shared memory and written by TMA
+    # (ragged right / bottom tiles are clipped by the store; several tiles per CTA at B = 40)
+    (6, 2, 32, 16, 128), (6, 1, 20, 13, 72), (6, 1, 12, 9, 44), (6, 40, 8, 24, 96), (6, 1, 3, 5, 4),
 ]
 
 
