@@ -48,6 +48,22 @@ inline int make_tmap4(CUtensorMap* tm, const float* base, const uint64_t dims[4]
   return B2F_OK;
 }
 
+// 5-D variant (the gradOut slab: x, y, window row, window column, batch)
+inline int make_tmap5(CUtensorMap* tm, const float* base, const uint64_t dims[5],
+                      const uint64_t strides_elems[4], const uint32_t box[5]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2F_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5] = {dims[0], dims[1], dims[2], dims[3], dims[4]};
+  cuuint64_t gstr[4] = {strides_elems[0] * 4, strides_elems[1] * 4, strides_elems[2] * 4, strides_elems[3] * 4};
+  cuuint32_t bx[5] = {box[0], box[1], box[2], box[3], box[4]};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2F_EINVAL, "cuTensorMapEncodeTiled (5-D) failed with CUresult %d", (int)r);
+  return B2F_OK;
+}
+
 // ---- device: mbarrier ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -174,6 +190,14 @@ __device__ __forceinline__ f32x2 straddle2(f32x2 a, f32x2 b) {
 // 16-byte shared-memory load as two packed pairs
 __device__ __forceinline__ void lds128_pairs(uint32_t addr, f32x2& p0, f32x2& p1) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "r"(addr));
+}
+__device__ __forceinline__ void tma_load_5d_addr(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                                 int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
 }
 // 16-byte shared-memory load from a 32-bit shared address (no generic-pointer conversion in the loop)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {

@@ -216,6 +216,50 @@ class Workload:
     def total_bytes(self):
         return sum(op.bytes for op in self.ops)
 
+    # -- CUDA graph of one step -------------------------------------------------------------
+    def capture(self, main, side):
+        """Capture one step as a CUDA graph.  The past and the future branch of every stage are independent
+        in the network (two CostVolMulti / sampler instances feeding one decoder), so each (future, past)
+        pair of calls is forked onto two streams and joined before the next stage; stages stay in the
+        forward-then-backward order of `step`.  Replaying the graph removes the per-call launch gaps that
+        dominate the small pyramid levels."""
+        torch, lib = self.torch, self.lib
+        pairs = {}
+        order = []
+        for which, name, kind, mk, nbytes, flops, zero in self._mk:
+            key = (which, kind)
+            if key not in pairs:
+                pairs[key] = []
+                order.append(key)
+            pairs[key].append((name, mk, zero))
+        fwd = [k for k in order if k[0] == "f"]
+        bwd = [k for k in order if k[0] == "b"][::-1]
+        sm, ss = C.c_void_p(main.cuda_stream), C.c_void_p(side.cuda_stream)
+        calls = []
+        for key in fwd + bwd:
+            group = pairs[key]
+            row = []
+            for i, (name, mk, zero) in enumerate(group):
+                sh = sm if i % 2 == 0 else ss
+                z = (lambda a=zero, sh=sh: lib.b2f_zero_async(a[0], a[1], sh)) if zero is not None else None
+                row.append((i % 2, z, mk(sh), name))
+            calls.append(row)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=main):
+            for row in calls:
+                forked = any(b for b, _, _, _ in row)
+                if forked:
+                    side.wait_stream(main)
+                for b, z, call, name in row:
+                    if z is not None and z():
+                        raise RuntimeError("b2f_zero_async failed during capture")
+                    rc = call()
+                    if rc:
+                        raise RuntimeError("%s failed during capture: %d: %s" % (name, rc, lib.b2f_last_error().decode()))
+                if forked:
+                    main.wait_stream(side)
+        return graph
+
 
 def breakdown(torch, wl, iters=10):
     """Per-kernel device times (separate pass, events around every call; not part of `value`)."""
@@ -251,9 +295,9 @@ class E2E:
     """The same pass through back2future_b200.nn with pinned HOST inputs and outputs.
 
     Every step copies every input from pinned host memory and reads every result back.  Copies and
-    kernels are pipelined over three streams (H2D / compute / D2H) with events, the way a caller of
-    the reference's modules would overlap its data movement; device staging buffers are allocated
-    once."""
+    kernels are pipelined over three streams (H2D / compute / D2H) with per-item events, the way a
+    caller streaming triplets through the reference's modules would overlap its data movement; device
+    staging buffers are allocated once."""
 
     def __init__(self, torch, dev, B=BATCH, seed=2):
         from back2future_b200 import nn as bnn
@@ -289,18 +333,28 @@ class E2E:
         for it in self.items:
             self.h2d += sum(t.numel() * 4 for t in it[2])
             self.d2h += sum(t.numel() * 4 for t in it[3])
+        self.ev_cmp = [None] * len(self.items)
+        self.ev_out = [None] * len(self.items)
 
     def step(self):
+        """One pass.  Nothing here waits for the host: the three streams are ordered by per-item events only
+        (inputs of item i are not overwritten before the previous step's kernels on item i have run; its
+        device results are not overwritten before the previous step's read-back of item i has finished), so
+        consecutive steps overlap the way a caller streaming triplets through the modules would run them.
+        `drain()` ends the timed region."""
         torch = self.torch
-        keep = []
-        for kind, mod, hin, hout, din, joined in self.items:
+        for i, (kind, mod, hin, hout, din, joined) in enumerate(self.items):
             with torch.cuda.stream(self.s_in):
+                if self.ev_cmp[i] is not None:
+                    self.s_in.wait_event(self.ev_cmp[i])
                 for d, h in zip(din, hin):
                     d.copy_(h, non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record()
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ev_in)
+                if self.ev_out[i] is not None:
+                    self.s_cmp.wait_event(self.ev_out[i])
                 if kind == "cv":
                     ref, past, fut, gj = din
                     mod[0].updateOutput([ref, fut], out=joined[:, :81])
@@ -315,15 +369,19 @@ class E2E:
                     douts = [out, gi, gg]
                 ev_cmp = torch.cuda.Event()
                 ev_cmp.record()
+                self.ev_cmp[i] = ev_cmp
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp)
                 for h, d in zip(hout, douts):
                     h.copy_(d, non_blocking=True)
-            keep.append(douts)
+                ev_out = torch.cuda.Event()
+                ev_out.record()
+                self.ev_out[i] = ev_out
+
+    def drain(self):
         self.s_out.synchronize()
         self.s_cmp.synchronize()
-        # the next step's H2D must not overwrite inputs still in use: everything above is finished here
-        return keep
+        self.s_in.synchronize()
 
 
 # ----------------------------------------------------------------------------------------
@@ -463,11 +521,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work (rank 0, N=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
+    ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls on one stream instead of the CUDA graph")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -503,24 +562,48 @@ def main():
         wl.step()
     torch.cuda.synchronize()
 
+    # launches of one step (counted on an eager pass; the graph replays exactly these)
+    lib.b2f_launch_count(1)
+    wl.step()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.b2f_launch_count(0))
+
     # ---- timed region: exactly K steps ------------------------------------------------
+    # default: each step is one replay of the captured CUDA graph (future / past branches on two streams);
+    # --eager: the same calls issued one by one on one stream
     dominant = ("costvol_bwd_L3", "costvol_fwd_L3")
     marks = {k: [] for k in dominant}
+    graph = None
+    if not args.eager:
+        gmain, gside = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        graph = wl.capture(gmain, gside)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    lib.b2f_launch_count(1)
     barrier()
     torch.cuda.synchronize()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        wl.step(marks)
+        if graph is not None:
+            graph.replay()
+        else:
+            wl.step(marks)
     e1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     barrier()
-    launches = int(lib.b2f_launch_count(0))
+    launches = launches_per_step * K
     ms = e0.elapsed_time(e1)
+    ms_local = ms
+    if graph is not None:
+        # live roofline sample of the dominant kernels: K more eager steps with events around those calls (the
+        # graph has no per-kernel events); these steps are outside the timed region
+        for _ in range(min(K, 20)):
+            wl.step(marks)
+        torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -539,7 +622,7 @@ def main():
             continue
         ts = [a.elapsed_time(b) for a, b, _ in lst]
         avg = sum(ts) / len(ts)
-        share = sum(ts) / e0.elapsed_time(e1)
+        share = (sum(ts) / len(ts)) * sum(1 for o_ in wl.ops if o_.kind == kind) / (ms_local / K)
         if best is None or sum(ts) > best[0]:
             best = (sum(ts), kind, avg, lst[0][2], share)
     if best:
@@ -558,6 +641,7 @@ def main():
         ee = E2E(torch, dev)
         for _ in range(3):
             ee.step()
+        ee.drain()
         barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -565,8 +649,13 @@ def main():
         for st_ in (ee.s_in, ee.s_cmp, ee.s_out):
             st_.wait_event(a)
         for _ in range(args.e2e_steps):
-            ee.step()                    # ends with the D2H and compute streams drained
+            ee.step()
+        for st_ in (ee.s_in, ee.s_cmp, ee.s_out):   # the end mark waits for the last read-back
+            ev_ = torch.cuda.Event()
+            ev_.record(st_)
+            torch.cuda.current_stream().wait_event(ev_)
         b.record()
+        ee.drain()
         torch.cuda.synchronize()
         barrier()
         ems = a.elapsed_time(b)
@@ -605,7 +694,9 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sharding": "triplets across ranks, no collective",
                        "l2": "no explicit flush: one step touches %.2f GB of distinct buffers (> 126 MB L2) before any "
                              "buffer is reused" % (wl.total_bytes() / 1e9),
-                       "alg_bytes_per_step": wl.total_bytes()},
+                       "alg_bytes_per_step": wl.total_bytes(),
+                       "launch": "eager, one stream" if args.eager else
+                                 "one CUDA-graph replay per step; future / past branch of each stage on two streams"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
