@@ -252,70 +252,103 @@ warp_fwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, f
 }
 
 // ---- backward, C % 4 == 0 -------------------------------------------------------------
+// Like the forward, an 8-lane group handles two pixels (x and x + 32), and per channel chunk ALL ten loads
+// (gradOut + four taps, both pixels) are issued before the first reduction: a red.global is a compiler
+// memory barrier, so interleaving "load tap, reduce, load next tap" serialises four L2 round trips per
+// pixel (measured: 76 % of the stall samples on the long scoreboard, 25 % issue utilisation).
 template <bool ONLY_GRID>
 __global__ void __launch_bounds__(VEC_THREADS)
 warp_bwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
               float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W, int C, int Hg, int Wg) {
   // whole warps stay alive for the shuffles: out-of-range pixels are just not "live"
-  const int xo = blockIdx.x * (VEC_THREADS / LPP) + (threadIdx.x >> 3);
-  const bool live = xo < Wg;
-  const int yo = blockIdx.y, b = blockIdx.z;
+  const int xa = blockIdx.x * (VEC_THREADS / LPP) * VEC_PPT + (threadIdx.x >> 3);
+  const int b = blockIdx.z;
   const int sub = threadIdx.x & (LPP - 1);
   const int nch4 = C >> 2;
-  const size_t pix = ((size_t)b * Hg + yo) * Wg + (live ? xo : 0);
-  float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
-  Geo g;
-  g.wx = g.wy = 0.f;
-  if (live) {
-    const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-    g = geometry(gxy.x, gxy.y, xo, yo, H, W);
-    const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
-    const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
-    const size_t a0 = (((size_t)b * H + g.yi) * W + g.xi) * C;
-    const float4* tl = reinterpret_cast<const float4*>(img + a0);
-    const float4* tr = tl + nch4;
-    const float4* bl = tl + (size_t)W * nch4;
-    const float4* br = bl + nch4;
-    const float4* go = reinterpret_cast<const float4*>(gout + pix * C);
-    float* gi = ONLY_GRID ? nullptr : gimg + a0;
-    const size_t rowC = (size_t)W * C;
-    const bool both = g.rin && g.bin;
+  int xo[VEC_PPT];
+  bool live[VEC_PPT];
+#pragma unroll
+  for (int p = 0; p < VEC_PPT; ++p) {
+    xo[p] = xa + p * (VEC_THREADS / LPP);
+    live[p] = xo[p] < Wg;
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t rowq = (size_t)W * nch4;
+  const size_t rowC = (size_t)W * C;
+  // rows blockIdx.y, blockIdx.y + gridDim.y, ... with the next row's grid values prefetched (see the forward)
+  float2 gnext[VEC_PPT];
+#pragma unroll
+  for (int p = 0; p < VEC_PPT; ++p)
+    gnext[p] = live[p] ? __ldg(reinterpret_cast<const float2*>(grid) + ((size_t)b * Hg + blockIdx.y) * Wg + xo[p])
+                       : make_float2(0.f, 0.f);
+  for (int yo = blockIdx.y; yo < Hg; yo += gridDim.y) {
+    const size_t row = ((size_t)b * Hg + yo) * Wg;
+    float2 gxy[VEC_PPT];
+#pragma unroll
+    for (int p = 0; p < VEC_PPT; ++p) {
+      gxy[p] = gnext[p];
+      if (yo + (int)gridDim.y < Hg && live[p])
+        gnext[p] = __ldg(reinterpret_cast<const float2*>(grid) + row + (size_t)gridDim.y * Wg + xo[p]);
+    }
+    Geo g[VEC_PPT];
+    const float4* tl[VEC_PPT];
+    const float4* go[VEC_PPT];
+    float* gi[VEC_PPT];
+    float dot[VEC_PPT][4];
+#pragma unroll
+    for (int p = 0; p < VEC_PPT; ++p) {
+      g[p] = geometry(gxy[p].x, gxy[p].y, live[p] ? xo[p] : 0, yo, H, W);
+      const size_t a0 = (((size_t)b * H + g[p].yi) * W + g[p].xi) * C;
+      tl[p] = reinterpret_cast<const float4*>(img + a0);
+      go[p] = reinterpret_cast<const float4*>(gout + (row + (live[p] ? xo[p] : 0)) * C);
+      gi[p] = ONLY_GRID ? nullptr : gimg + a0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dot[p][t] = 0.f;
+    }
     for (int q = sub; q < nch4; q += LPP) {
-      const float4 v = __ldcs(go + q);
-      {
-        const float4 a = __ldg(tl + q);
-        d_tl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-        if (!ONLY_GRID) red_add_v4(gi + 4 * q, w_tl * v.x, w_tl * v.y, w_tl * v.z, w_tl * v.w);
+      float4 v[VEC_PPT], a[VEC_PPT], c[VEC_PPT], d[VEC_PPT], e[VEC_PPT];
+#pragma unroll
+      for (int p = 0; p < VEC_PPT; ++p) {
+        const bool rin = g[p].rin && live[p], bin = g[p].bin && live[p];
+        v[p] = live[p] ? __ldcs(go[p] + q) : zero;
+        a[p] = live[p] ? __ldg(tl[p] + q) : zero;
+        c[p] = rin ? __ldg(tl[p] + nch4 + q) : zero;
+        d[p] = bin ? __ldg(tl[p] + rowq + q) : zero;
+        e[p] = (rin && bin) ? __ldg(tl[p] + rowq + nch4 + q) : zero;
       }
-      if (g.rin) {
-        const float4 a = __ldg(tr + q);
-        d_tr += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-        if (!ONLY_GRID) red_add_v4(gi + C + 4 * q, w_tr * v.x, w_tr * v.y, w_tr * v.z, w_tr * v.w);
-      }
-      if (g.bin) {
-        const float4 a = __ldg(bl + q);
-        d_bl += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-        if (!ONLY_GRID) red_add_v4(gi + rowC + 4 * q, w_bl * v.x, w_bl * v.y, w_bl * v.z, w_bl * v.w);
-      }
-      if (both) {
-        const float4 a = __ldg(br + q);
-        d_br += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-        if (!ONLY_GRID) red_add_v4(gi + rowC + C + 4 * q, w_br * v.x, w_br * v.y, w_br * v.z, w_br * v.w);
+#pragma unroll
+      for (int p = 0; p < VEC_PPT; ++p) {
+        if (!live[p]) continue;
+        const float4 w = v[p];
+        dot[p][0] += a[p].x * w.x + a[p].y * w.y + a[p].z * w.z + a[p].w * w.w;
+        dot[p][1] += c[p].x * w.x + c[p].y * w.y + c[p].z * w.z + c[p].w * w.w;
+        dot[p][2] += d[p].x * w.x + d[p].y * w.y + d[p].z * w.z + d[p].w * w.w;
+        dot[p][3] += e[p].x * w.x + e[p].y * w.y + e[p].z * w.z + e[p].w * w.w;
+        if (!ONLY_GRID) {
+          const float w_tl = g[p].wx * g[p].wy, w_tr = (1.f - g[p].wx) * g[p].wy;
+          const float w_bl = g[p].wx * (1.f - g[p].wy), w_br = (1.f - g[p].wx) * (1.f - g[p].wy);
+          float* o = gi[p] + 4 * q;
+          red_add_v4(o, w_tl * w.x, w_tl * w.y, w_tl * w.z, w_tl * w.w);
+          if (g[p].rin) red_add_v4(o + C, w_tr * w.x, w_tr * w.y, w_tr * w.z, w_tr * w.w);
+          if (g[p].bin) red_add_v4(o + rowC, w_bl * w.x, w_bl * w.y, w_bl * w.z, w_bl * w.w);
+          if (g[p].rin && g[p].bin) red_add_v4(o + rowC + C, w_br * w.x, w_br * w.y, w_br * w.z, w_br * w.w);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = LPP / 2; o > 0; o >>= 1) {
-    d_tl += __shfl_xor_sync(0xffffffffu, d_tl, o);
-    d_tr += __shfl_xor_sync(0xffffffffu, d_tr, o);
-    d_bl += __shfl_xor_sync(0xffffffffu, d_bl, o);
-    d_br += __shfl_xor_sync(0xffffffffu, d_br, o);
-  }
-  if (live && sub == 0) {
-    float2 r;
-    r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
-    r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
-    reinterpret_cast<float2*>(ggrid)[pix] = r;
+    for (int p = 0; p < VEC_PPT; ++p) {
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dot[p][t] += __shfl_xor_sync(0xffffffffu, dot[p][t], o);
+      if (live[p] && sub == 0) {
+        // taps outside the image contributed zero (their loads were replaced by zeros)
+        float2 r;
+        r.x = -g[p].wy * dot[p][0] + g[p].wy * dot[p][1] - (1.f - g[p].wy) * dot[p][2] + (1.f - g[p].wy) * dot[p][3];
+        r.y = -g[p].wx * dot[p][0] + g[p].wx * dot[p][2] - (1.f - g[p].wx) * dot[p][1] + (1.f - g[p].wx) * dot[p][3];
+        reinterpret_cast<float2*>(ggrid)[row + xo[p]] = r;
+      }
+    }
   }
 }
 
@@ -413,6 +446,19 @@ warp_bwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, c
   reinterpret_cast<float2*>(ggrid)[pix] = r;
 }
 
+// gridDim.y of the vector backward kernel: a block walks every gridDim.y-th row (the forward measured
+// slower with the row loop: its extra registers cost a resident block).  Enough blocks for ~2-3 waves of
+// resident CTAs (2-3 per SM), at most 8 rows per block so the tail stays short.
+int vec_rows_grid(int Wg, int Hg, int B) {
+  const int64_t cols = (int64_t)((Wg + 32 * VEC_PPT - 1) / (32 * VEC_PPT)) * B;
+  const int64_t want = (int64_t)num_sms() * 6;
+  int64_t gy = (want + cols - 1) / cols;
+  const int64_t gmin = (Hg + 7) / 8;
+  if (gy < gmin) gy = gmin;
+  if (gy > Hg) gy = Hg;
+  return (int)gy;
+}
+
 int check_args(const float* img, const float* grid, int B, int H, int W, int C, int Hg, int Wg) {
   if (!img || !grid) return fail(B2F_EINVAL, "warp: NULL img/grid");
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || Hg <= 0 || Wg <= 0)
@@ -464,7 +510,7 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool only = gradImg == nullptr;
   if ((C & 3) == 0 && aligned16(img) && aligned16(gradOut) && (only || aligned16(gradImg))) {
-    dim3 grid_dim((Wg + 31) / 32, Hg, B);
+    dim3 grid_dim((Wg + 32 * VEC_PPT - 1) / (32 * VEC_PPT), vec_rows_grid(Wg, Hg, B), B);
     if (only) warp_bwd_vec4<true><<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
     else warp_bwd_vec4<false><<<grid_dim, VEC_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
     B2F_CHECK_LAUNCH("warp_bwd_vec4");
