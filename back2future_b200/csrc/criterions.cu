@@ -172,14 +172,10 @@ struct ObArgs {
   int grad_check;
 };
 
+// One pixel, any channel count: the reference's formulas channel by channel (loads, arithmetic and the gradient
+// store of a channel follow each other, so the memory round trips of the channels are serialised).
 template <int PEN, bool GT>
-__global__ void __launch_bounds__(kThreads)
-ob_kernel(ObArgs a, LossOut lo) {
-  const int64_t hw = (int64_t)a.h * a.w;
-  const int x = blockIdx.x * kThreads + threadIdx.x;
-  const int y = blockIdx.y, b = blockIdx.z;
-  float loss = 0.f;
-  if (x < a.w) {
+__device__ __forceinline__ void ob_pixel_generic(const ObArgs& a, int b, int y, int x, int64_t hw, float& loss) {
     const int64_t o = (int64_t)y * a.w + x;
     const int w = a.w, h = a.h;
 #pragma unroll
@@ -249,6 +245,126 @@ ob_kernel(ObArgs a, LossOut lo) {
         a.g_occ[((int64_t)b * 2 + oc) * hw + o] = buf * a.norm;
       }
     }
+}
+
+// One pixel, C = 3 (every criterion call of the model): ALL loads of both frames are issued first -- 2 occlusion,
+// 4 flow, 3 target and 6 warped values, plus their four neighbours with the gradient terms -- so a pixel costs
+// one memory round trip instead of one per channel and frame; the arithmetic and its order are unchanged.
+template <int PEN, bool GT>
+__device__ __forceinline__ void ob_pixel_c3(const ObArgs& a, int b, int y, int x, int64_t hw, float& loss) {
+  const int64_t o = (int64_t)y * a.w + x;
+  const int w = a.w, h = a.h;
+  float occv[2], fx[2] = {0.f, 0.f}, fy[2] = {0.f, 0.f};
+#pragma unroll
+  for (int fr = 0; fr < 2; ++fr) {
+    const int oc = fr == 0 ? 1 : 0;
+    const float* fl = fr == 0 ? a.bflow : a.flow;
+    occv[fr] = __ldg(a.occ + ((int64_t)b * 2 + oc) * hw + o);
+    if (!a.grad_check) {
+      fx[fr] = __ldg(fl + ((int64_t)b * 2) * hw + o);
+      fy[fr] = __ldg(fl + ((int64_t)b * 2 + 1) * hw + o);
+    }
+  }
+  // centre and (GT) the four neighbours of target and of both warped frames; index 0 = target, 1/2 = frames
+  float v0[3][3], vxp[3][3], vyp[3][3], vxm[3][3], vym[3][3];
+#pragma unroll
+  for (int s3 = 0; s3 < 3; ++s3) {
+    const float* src = s3 == 0 ? a.target : a.warp[s3 - 1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* q = src + ((int64_t)b * 3 + c) * hw + o;
+      v0[s3][c] = __ldg(q);
+      if (GT) {
+        vxp[s3][c] = (x < w - 1) ? __ldg(q + 1) : 0.f;
+        vyp[s3][c] = (y < h - 1) ? __ldg(q + w) : 0.f;
+        vxm[s3][c] = (x > 0) ? __ldg(q - 1) : 0.f;
+        vym[s3][c] = (y > 0) ? __ldg(q - w) : 0.f;
+      }
+    }
+  }
+  float gout[2][3], gocc[2];
+#pragma unroll
+  for (int fr = 0; fr < 2; ++fr) {
+    // fr 0: past frame, k = -1, occ channel 2 (index 1); fr 1: future, k = +1, occ channel 1
+    const float k = fr == 0 ? -1.f : 1.f;
+    bool m = true;
+    if (!a.grad_check) {
+      // tcoord = fl(coord + fl(fl(k*flow)*scale)), 1-based coords (OBCCriterion.lua:81-100, Q14)
+      const float tx = __fadd_rn((float)(x + 1), __fmul_rn(__fmul_rn(fx[fr], k), a.scale));
+      const float ty = __fadd_rn((float)(y + 1), __fmul_rn(__fmul_rn(fy[fr], k), a.scale));
+      m = (tx >= 1.f) && (ty >= 1.f) && (tx <= (float)w) && (ty <= (float)h);
+    }
+    float e = 0.f, ex = 0.f, ey = 0.f, exm = 0.f, eym = 0.f;
+    const float gscale = m ? occv[fr] * a.norm : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float iv = v0[fr + 1][c], tv = v0[0][c];
+      const float d = iv - tv;
+      e += pen_apply<PEN>(d, a.eps2);
+      float gi;
+      if (GT) {
+        const float dgx = (x < w - 1) ? (vxp[fr + 1][c] - iv) - (vxp[0][c] - tv) : 0.f;
+        const float dgy = (y < h - 1) ? (vyp[fr + 1][c] - iv) - (vyp[0][c] - tv) : 0.f;
+        ex += pen_apply<PEN>(dgx, a.eps2);
+        ey += pen_apply<PEN>(dgy, a.eps2);
+        gi = pen_der<PEN>(d, a.eps2) * a.alpha;
+        gi -= pen_der<PEN>(dgy, a.eps2) * a.gamma;
+        if (y > 0) {
+          const float dm = (iv - vym[fr + 1][c]) - (tv - vym[0][c]);
+          gi += pen_der<PEN>(dm, a.eps2) * a.gamma;
+          eym += pen_apply<PEN>(dm, a.eps2);
+        }
+        gi -= pen_der<PEN>(dgx, a.eps2) * a.beta;
+        if (x > 0) {
+          const float dm = (iv - vxm[fr + 1][c]) - (tv - vxm[0][c]);
+          gi += pen_der<PEN>(dm, a.eps2) * a.beta;
+          exm += pen_apply<PEN>(dm, a.eps2);
+        }
+      } else {
+        gi = pen_der<PEN>(d, a.eps2);
+      }
+      gout[fr][c] = gi * gscale;
+    }
+    // forward energy (alpha is not applied here: OBGCCriterion.lua:97)
+    float tmp = GT ? e + ex * a.beta + ey * a.gamma : e;
+    tmp *= occv[fr];
+    loss += m ? tmp : a.penalty_out;
+    // occlusion gradient (Q6, Q7)
+    float buf = e;
+    if (GT) {
+      buf = e * a.alpha;
+      buf -= ey * a.gamma;
+      buf += eym * a.gamma;
+      buf -= ex * a.beta;
+      buf += exm * a.beta;
+    }
+    buf = m ? buf : a.penalty_out;
+    gocc[fr] = buf * a.norm;
+  }
+#pragma unroll
+  for (int fr = 0; fr < 2; ++fr) {
+    if (a.g_warp[fr]) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.g_warp[fr][((int64_t)b * 3 + c) * hw + o] = gout[fr][c];
+    }
+    if (a.g_occ) a.g_occ[((int64_t)b * 2 + (fr == 0 ? 1 : 0)) * hw + o] = gocc[fr];
+  }
+}
+
+template <int PEN, bool GT>
+__global__ void __launch_bounds__(kThreads)
+ob_kernel(ObArgs a, LossOut lo) {
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int x = blockIdx.x * kThreads + threadIdx.x;
+  const int b = blockIdx.z;
+  float loss = 0.f;
+  // a block walks rows blockIdx.y, blockIdx.y + gridDim.y, ...
+  if (x < a.w) {
+    if (a.C == 3) {
+      for (int y = blockIdx.y; y < a.h; y += gridDim.y) ob_pixel_c3<PEN, GT>(a, b, y, x, hw, loss);
+    } else {
+      for (int y = blockIdx.y; y < a.h; y += gridDim.y) ob_pixel_generic<PEN, GT>(a, b, y, x, hw, loss);
+    }
   }
   finish_loss(loss, lo);
 }
@@ -269,15 +385,19 @@ struct SmArgs {
 };
 
 // order-1 edge weights -----------------------------------------------------------------
+template <int CIN, int CT>
 __device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
   const int64_t hw = (int64_t)a.h * a.w;
+  const int Cin = CIN ? CIN : a.Cin, Ct = CT ? CT : a.Ct;
+  (void)Cin; (void)Ct;
   float s = 0.f;
   if (a.alias) {
     // igy(b,j,y,x) = flat(D_y)[((b*Cin+j)*h+y)*w+x], D_y contiguous (B,Ct,h-1,w)   (Q9)
-    for (int j = 0; j < a.Cin; ++j) {
+    #pragma unroll
+    for (int j = 0; j < Cin; ++j) {
       // idx = t*w + x with t = (b*Cin+j)*h + y, so idx % w == x and idx / w == t: only the small
       // row counter t has to be decomposed (32-bit)
-      const unsigned t = ((unsigned)b * a.Cin + j) * a.h + y;
+      const unsigned t = ((unsigned)b * Cin + j) * a.h + y;
       float v = 0.f;
       if ((int64_t)t * a.w + x < a.n_dy) {
         const unsigned r = t % (unsigned)(a.h - 1);
@@ -287,23 +407,28 @@ __device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
       }
       s += fabsf(v);
     }
-    return expf(-a.cs * (s / (float)a.Cin));
+    return expf(-a.cs * (s / (float)Cin));
   }
   if (y < a.h - 1) {
-    for (int c = 0; c < a.Ct; ++c) {
-      const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+#pragma unroll
+    for (int c = 0; c < Ct; ++c) {
+      const float* p = a.tgt + ((int64_t)b * Ct + c) * hw + (int64_t)y * a.w + x;
       s += fabsf(__ldg(p + a.w) - __ldg(p));
     }
   }
-  return expf(-a.cs * (s / (float)a.Ct));
+  return expf(-a.cs * (s / (float)Ct));
 }
 
+template <int CIN, int CT>
 __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
   const int64_t hw = (int64_t)a.h * a.w;
+  const int Cin = CIN ? CIN : a.Cin, Ct = CT ? CT : a.Ct;
+  (void)Cin; (void)Ct;
   float s = 0.f;
   if (a.alias) {
-    for (int j = 0; j < a.Cin; ++j) {
-      const int64_t idx = (((int64_t)b * a.Cin + j) * a.h + y) * a.w + x;
+    #pragma unroll
+    for (int j = 0; j < Cin; ++j) {
+      const int64_t idx = (((int64_t)b * Cin + j) * a.h + y) * a.w + x;
       float v = 0.f;
       if (idx < a.n_dx) {
         // rows of the contiguous x-difference array are w-1 long: row = idx / (w-1), 32-bit when it fits
@@ -321,32 +446,43 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
       }
       s += fabsf(v);
     }
-    return expf(-a.cs * (s / (float)a.Cin));
+    return expf(-a.cs * (s / (float)Cin));
   }
   if (x < a.w - 1) {
-    for (int c = 0; c < a.Ct; ++c) {
-      const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+#pragma unroll
+    for (int c = 0; c < Ct; ++c) {
+      const float* p = a.tgt + ((int64_t)b * Ct + c) * hw + (int64_t)y * a.w + x;
       s += fabsf(__ldg(p + 1) - __ldg(p));
     }
   }
-  return expf(-a.cs * (s / (float)a.Ct));
+  return expf(-a.cs * (s / (float)Ct));
 }
 
-template <int PEN>
+// CIN / CT: compile-time channel counts (2, 3 = every call of the model) or 0 = run-time.  With constant trip
+// counts the loads of a pixel are straight-line code and the gradient stores are deferred to the end, so they
+// all overlap (with run-time loops every channel costs its own memory round trip).
+template <int PEN, int CIN, int CT>
 __global__ void __launch_bounds__(kThreads)
 smooth1_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
   const int x = blockIdx.x * kThreads + threadIdx.x;
-  const int y = blockIdx.y, b = blockIdx.z;
+  const int b = blockIdx.z;
   float loss = 0.f;
-  if (x < a.w) {
+  // a block walks rows blockIdx.y, blockIdx.y + gridDim.y, ...: long-lived blocks keep the SM full (one-row
+  // blocks spent their life being launched: 42 % achieved occupancy) and there is one loss hand-off per block
+  if (x < a.w)
+  for (int y = blockIdx.y; y < a.h; y += gridDim.y) {
     const int w = a.w, h = a.h;
-    const float wx0 = w1_x(a, b, y, x), wy0 = w1_y(a, b, y, x);
+    const float wx0 = w1_x<CIN, CT>(a, b, y, x), wy0 = w1_y<CIN, CT>(a, b, y, x);
     const bool need_g = a.grad != nullptr;
-    const float wxm = (need_g && x > 0) ? w1_x(a, b, y, x - 1) : 0.f;
-    const float wym = (need_g && y > 0) ? w1_y(a, b, y - 1, x) : 0.f;
-    for (int ch = 0; ch < a.Cin; ++ch) {
-      const int64_t p = ((int64_t)b * a.Cin + ch) * hw + (int64_t)y * w + x;
+    const float wxm = (need_g && x > 0) ? w1_x<CIN, CT>(a, b, y, x - 1) : 0.f;
+    const float wym = (need_g && y > 0) ? w1_y<CIN, CT>(a, b, y - 1, x) : 0.f;
+    constexpr int NG = CIN ? CIN : 1;
+    const int Cin = CIN ? CIN : a.Cin;
+    float gsave[NG];
+#pragma unroll
+    for (int ch = 0; ch < Cin; ++ch) {
+      const int64_t p = ((int64_t)b * Cin + ch) * hw + (int64_t)y * w + x;
       const float v = __ldg(a.in + p);
       const float gx = (x < w - 1) ? __ldg(a.in + p + 1) - v : 0.f;
       const float gy = (y < h - 1) ? __ldg(a.in + p + w) - v : 0.f;
@@ -357,45 +493,61 @@ smooth1_kernel(SmArgs a, LossOut lo) {
         if (x > 0) g += pen_der<PEN>(v - __ldg(a.in + p - 1), a.eps2) * wxm;
         g -= pen_der<PEN>(gy, a.eps2) * wy0;
         if (y > 0) g += pen_der<PEN>(v - __ldg(a.in + p - w), a.eps2) * wym;
-        a.grad[p] = g * a.norm;
+        if (CIN) gsave[ch] = g * a.norm;
+        else a.grad[p] = g * a.norm;
       }
+    }
+    if (CIN && need_g) {
+#pragma unroll
+      for (int ch = 0; ch < NG; ++ch) a.grad[((int64_t)b * Cin + ch) * hw + (int64_t)y * w + x] = gsave[ch];
     }
   }
   finish_loss(loss, lo);
 }
 
 // order-2 weights (SecondOrderSmoothnessCriterion.lua:49-61) ------------------------------
+template <int CIN, int CT>
 __device__ __forceinline__ float w2_y(const SmArgs& a, int b, int y, int x) {
   const int64_t hw = (int64_t)a.h * a.w;
+  const int Cin = CIN ? CIN : a.Cin, Ct = CT ? CT : a.Ct;
+  (void)Cin; (void)Ct;
   float s1 = 0.f, s2 = 0.f;
-  for (int c = 0; c < a.Ct; ++c) {
-    const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+#pragma unroll
+  for (int c = 0; c < Ct; ++c) {
+    const float* p = a.tgt + ((int64_t)b * Ct + c) * hw + (int64_t)y * a.w + x;
     const float t = __ldg(p);
     if (y >= 1) s1 += fabsf(t - __ldg(p - a.w));
     if (y >= 1 && y <= a.h - 2) s2 += fabsf(t - __ldg(p + a.w));
   }
-  return expf(-a.cs * (s1 / (float)a.Ct + s2 / (float)a.Ct));
+  return expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
 }
+template <int CIN, int CT>
 __device__ __forceinline__ float w2_x(const SmArgs& a, int b, int y, int x) {
   const int64_t hw = (int64_t)a.h * a.w;
+  const int Cin = CIN ? CIN : a.Cin, Ct = CT ? CT : a.Ct;
+  (void)Cin; (void)Ct;
   float s1 = 0.f, s2 = 0.f;
-  for (int c = 0; c < a.Ct; ++c) {
-    const float* p = a.tgt + ((int64_t)b * a.Ct + c) * hw + (int64_t)y * a.w + x;
+#pragma unroll
+  for (int c = 0; c < Ct; ++c) {
+    const float* p = a.tgt + ((int64_t)b * Ct + c) * hw + (int64_t)y * a.w + x;
     const float t = __ldg(p);
     if (x >= 1) s1 += fabsf(t - __ldg(p - 1));
     if (x >= 1 && x <= a.w - 2) s2 += fabsf(t - __ldg(p + 1));
   }
-  return expf(-a.cs * (s1 / (float)a.Ct + s2 / (float)a.Ct));
+  return expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
 }
 
-template <int PEN>
+template <int PEN, int CIN, int CT>
 __global__ void __launch_bounds__(kThreads)
 smooth2_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
   const int x = blockIdx.x * kThreads + threadIdx.x;
-  const int y = blockIdx.y, b = blockIdx.z;
+  const int b = blockIdx.z;
   float loss = 0.f;
-  if (x < a.w) {
+  // a block walks rows blockIdx.y, blockIdx.y + gridDim.y, ...: long-lived blocks keep the SM full (one-row
+  // blocks spent their life being launched: 42 % achieved occupancy) and there is one loss hand-off per block
+  if (x < a.w)
+  for (int y = blockIdx.y; y < a.h; y += gridDim.y) {
     const int w = a.w, h = a.h;
     const bool need_g = a.grad != nullptr;
     // weights at the three positions each direction needs
@@ -403,11 +555,15 @@ smooth2_kernel(SmArgs a, LossOut lo) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int yy = y + k - 1, xx = x + k - 1;
-      wy[k] = (yy >= 0 && yy < h && (k == 1 || need_g)) ? w2_y(a, b, yy, x) : 0.f;
-      wx[k] = (xx >= 0 && xx < w && (k == 1 || need_g)) ? w2_x(a, b, y, xx) : 0.f;
+      wy[k] = (yy >= 0 && yy < h && (k == 1 || need_g)) ? w2_y<CIN, CT>(a, b, yy, x) : 0.f;
+      wx[k] = (xx >= 0 && xx < w && (k == 1 || need_g)) ? w2_x<CIN, CT>(a, b, y, xx) : 0.f;
     }
-    for (int ch = 0; ch < a.Cin; ++ch) {
-      const float* I = a.in + ((int64_t)b * a.Cin + ch) * hw;
+    constexpr int NG = CIN ? CIN : 1;
+    const int Cin = CIN ? CIN : a.Cin;
+    float gsave[NG];
+#pragma unroll
+    for (int ch = 0; ch < Cin; ++ch) {
+      const float* I = a.in + ((int64_t)b * Cin + ch) * hw;
       const int64_t o = (int64_t)y * w + x;
       // second differences at y-1, y, y+1 (zero outside the interior 1..h-2)
       float gy[3], gx[3];
@@ -435,8 +591,13 @@ smooth2_kernel(SmArgs a, LossOut lo) {
         if (x + 1 >= 1 && x + 1 <= w - 2) g -= pen_der<PEN>(gx[2], a.eps2) * wx[2];
         if (y - 1 >= 1 && y - 1 <= h - 2) g -= pen_der<PEN>(gy[0], a.eps2) * wy[0];
         if (x - 1 >= 1 && x - 1 <= w - 2) g -= pen_der<PEN>(gx[0], a.eps2) * wx[0];
-        a.grad[((int64_t)b * a.Cin + ch) * hw + o] = g * a.norm;
+        if (CIN) gsave[ch] = g * a.norm;
+        else a.grad[((int64_t)b * Cin + ch) * hw + o] = g * a.norm;
       }
+    }
+    if (CIN && need_g) {
+#pragma unroll
+      for (int ch = 0; ch < NG; ++ch) a.grad[((int64_t)b * Cin + ch) * hw + (int64_t)y * w + x] = gsave[ch];
     }
   }
   finish_loss(loss, lo);
@@ -448,10 +609,10 @@ smooth2_kernel(SmArgs a, LossOut lo) {
 __global__ void __launch_bounds__(kThreads)
 constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float* __restrict__ gf,
                 float* __restrict__ gb, int B, int C, int64_t hw, float gnorm, LossOut lo) {
-  const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;   // pixel inside the image
   const int b = blockIdx.y;
   float loss = 0.f;
-  if (o < hw) {
+  // pixel inside the image; a block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < hw; o += (int64_t)gridDim.x * kThreads) {
     float s = 0.f;
     for (int c = 0; c < C; ++c) {
       const int64_t p = ((int64_t)b * C + c) * hw + o;
@@ -459,7 +620,7 @@ constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float
       s += d * d;
     }
     const float nrm = sqrtf(s);
-    loss = nrm;
+    loss += nrm;
     if (gf || gb) {
       const float den = nrm + 1e-12f;
       for (int c = 0; c < C; ++c) {
@@ -476,22 +637,21 @@ constvel_kernel(const float* __restrict__ f, const float* __restrict__ bb, float
 __global__ void __launch_bounds__(kThreads)
 occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, int C, int64_t hw,
                 float penalty, float norm, LossOut lo) {
-  const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int b = blockIdx.y;
   float loss = 0.f;
-  if (o < hw) {
+  for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < hw; o += (int64_t)gridDim.x * kThreads) {
     const int64_t p0 = ((int64_t)b * C) * hw + o;
     const float o1 = __ldg(occ + p0), o2 = __ldg(occ + p0 + hw);
     if (C == 3) {
       const float o3 = __ldg(occ + p0 + 2 * hw);
-      loss = (1.f - o2) * (o1 + o3) * penalty * 0.05f;
+      loss += (1.f - o2) * (o1 + o3) * penalty * 0.05f;
       if (grad) {
         grad[p0] = (1.f - o2) * penalty * 0.05f * norm;
         grad[p0 + hw] = -(o1 + o3) * penalty * 0.05f * norm;
         grad[p0 + 2 * hw] = (1.f - o2) * penalty * 0.05f * norm;
       }
     } else {
-      loss = (1.f - o1 * o2) * penalty;
+      loss += (1.f - o1 * o2) * penalty;
       if (grad) {
         grad[p0] = (1.f - o2) * penalty * norm;
         grad[p0 + hw] = (1.f - o1) * penalty * norm;
@@ -501,10 +661,22 @@ occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, 
   finish_loss(loss, lo);
 }
 
+// Number of row (or tile) slots in the grid when `cols` blocks exist per slot and there are `n` rows: about one
+// wave of resident blocks (16 x 128 threads per SM), at most 16 rows per block.
+int rows_per_grid(int64_t cols, int n) {
+  const int64_t want = (int64_t)num_sms() * 16;
+  int64_t gy = (want + cols - 1) / cols;
+  const int64_t gmin = (n + 15) / 16;
+  if (gy < gmin) gy = gmin;
+  if (gy > n) gy = n;
+  return (int)(gy < 1 ? 1 : gy);
+}
+
 // grid = (x tiles, rows, batch) for the stencil kernels
 int grid_rows(int B, int h, int w, dim3* g, int* blocks) {
   if (B > 65535 || h > 65535) return fail(B2F_EINVAL, "criterion: B and h must be <= 65535");
-  *g = dim3((w + kThreads - 1) / kThreads, h, B);
+  const int gx = (w + kThreads - 1) / kThreads;
+  *g = dim3(gx, rows_per_grid((int64_t)gx * B, h), B);
   const int64_t nb = (int64_t)g->x * g->y * g->z;
   if (nb > 0x3fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
   *blocks = (int)nb;
@@ -513,8 +685,9 @@ int grid_rows(int B, int h, int w, dim3* g, int* blocks) {
 // grid = (pixel tiles, batch) for the pointwise kernels
 int grid_flat(int B, int64_t hw, dim3* g, int* blocks) {
   if (B > 65535) return fail(B2F_EINVAL, "criterion: B must be <= 65535");
-  const int64_t gx = (hw + kThreads - 1) / kThreads;
-  if (gx * B > 0x3fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
+  int64_t gx = (hw + kThreads - 1) / kThreads;
+  if (gx > 0x3fffffff) return fail(B2F_EINVAL, "criterion: too many pixels");
+  gx = rows_per_grid(B, (int)gx);
   *g = dim3((unsigned)gx, B, 1);
   *blocks = (int)(gx * B);
   return B2F_OK;
@@ -609,15 +782,22 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
   const int pen = prm->penalty;
+  const bool fixed = Cin == 2 && Ct == 3;   // the model's shapes: flow / occlusion map vs RGB target
+#define B2F_SMOOTH_LAUNCH(KERN, P)                                                        \
+  do {                                                                                    \
+    if (fixed) KERN<P, 2, 3><<<grid, kThreads, 0, st>>>(a, ls.lo);                        \
+    else KERN<P, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);                              \
+  } while (0)
   if (prm->order == 1) {
-    if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<grid, kThreads, 0, st>>>(a, ls.lo);
-    else if (pen == B2F_PENALTY_L1) smooth1_kernel<B2F_PENALTY_L1><<<grid, kThreads, 0, st>>>(a, ls.lo);
-    else smooth1_kernel<B2F_PENALTY_LORENTZIAN><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    if (pen == B2F_PENALTY_QUADRATIC) B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_QUADRATIC);
+    else if (pen == B2F_PENALTY_L1) B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_L1);
+    else B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_LORENTZIAN);
   } else {
-    if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<grid, kThreads, 0, st>>>(a, ls.lo);
-    else if (pen == B2F_PENALTY_L1) smooth2_kernel<B2F_PENALTY_L1><<<grid, kThreads, 0, st>>>(a, ls.lo);
-    else smooth2_kernel<B2F_PENALTY_LORENTZIAN><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    if (pen == B2F_PENALTY_QUADRATIC) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_QUADRATIC);
+    else if (pen == B2F_PENALTY_L1) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_L1);
+    else B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_LORENTZIAN);
   }
+#undef B2F_SMOOTH_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
