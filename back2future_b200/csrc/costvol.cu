@@ -508,8 +508,8 @@ template <int SGN>
 __global__ void __launch_bounds__(THREADS, 2)
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
                 const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_go1,
-                float* __restrict__ grad_ref, float* __restrict__ grad_frame, int nroles, int role0,
-                int nchunk, int C, int H, int W, float kdiv, int dbg) {
+                const __grid_constant__ CUtensorMap tm_gref, const __grid_constant__ CUtensorMap tm_gfrm,
+                int nroles, int role0, int nchunk, int C, int H, int W, float kdiv, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer + integer offset keeps the shared address space (LDS, not generic LD)
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -605,24 +605,30 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   }
 
   // ---- epilogue ----
+  // The warp's X group is dead: its 8 channels x 8 rows x 32 columns of results are staged there with the TMA
+  // 128-byte swizzle (16-byte chunk c of the 128-byte row at address A sits at chunk c ^ ((A >> 7) & 7), so the
+  // eight rows of a quarter-warp hit eight different bank groups) and leave as ONE bulk tensor store; channels
+  // >= C and pixels outside the image are clipped by the TMA.  (Direct STG.128 from this accumulator layout
+  // touches 8 lines per instruction: 33 cycles each, 16 us of the 117 us kernel at level 3.)
   const float kinv = 1.f / kdiv;
-  float* outp = (role == 0) ? grad_ref : grad_frame;
-  const int y = y0 + r;
-  const int xb = x0 + 8 * st;
-  if (y < H && xb < W && !(dbg & 2)) {
-    const int64_t hw = (int64_t)H * W;
+  const uint32_t wbase = smem_u32(xsm) + (uint32_t)(warp * XG_ELEMS) * 4u;
 #pragma unroll
-    for (int c = 0; c < CG; ++c) {
-      const int ch = c0 + warp * CG + c;
-      if (ch < C) {
-        float* o = outp + ((int64_t)b * C + ch) * hw + (int64_t)y * W + xb;
-        float4 v0, v1;
-        v0.x = acc[c][0] * kinv; v0.y = acc[c][1] * kinv; v0.z = acc[c][2] * kinv; v0.w = acc[c][3] * kinv;
-        v1.x = acc[c][4] * kinv; v1.y = acc[c][5] * kinv; v1.z = acc[c][6] * kinv; v1.w = acc[c][7] * kinv;
-        *reinterpret_cast<float4*>(o) = v0;
-        if (xb + 4 < W) *reinterpret_cast<float4*>(o + 4) = v1;
-      }
-    }
+  for (int c = 0; c < CG; ++c) {
+    const uint32_t rowaddr = wbase + (uint32_t)((c * TH + r) * 128);
+    const uint32_t sw = (rowaddr >> 7) & 7u;
+    float4 v0, v1;
+    v0.x = acc[c][0] * kinv; v0.y = acc[c][1] * kinv; v0.z = acc[c][2] * kinv; v0.w = acc[c][3] * kinv;
+    v1.x = acc[c][4] * kinv; v1.y = acc[c][5] * kinv; v1.z = acc[c][6] * kinv; v1.w = acc[c][7] * kinv;
+    sts128(rowaddr + 16u * ((uint32_t)(2 * st) ^ sw), v0);
+    sts128(rowaddr + 16u * ((uint32_t)(2 * st + 1) ^ sw), v1);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && !(dbg & 2)) {
+    if (role == 0) tma_store_4d_addr(wbase, &tm_gref, x0, y0, c0 + warp * CG, b);
+    else           tma_store_4d_addr(wbase, &tm_gfrm, x0, y0, c0 + warp * CG, b);
+    tma_store_commit();
+    tma_store_wait_read();   // shared memory must outlive the store's read
   }
 }
 }  // namespace cvb
@@ -801,6 +807,12 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
       if ((rc = make_tmap4(&tref, frames[0], dims, str, box_x))) return rc;
       if ((rc = make_tmap4(&tgo, gradOut, gdims, gstr, box_g0))) return rc;
       if ((rc = make_tmap4(&tgo1, gradOut, gdims, gstr, box_g1))) return rc;
+      // results: 32 x 8 x 8-channel boxes, 128-byte swizzled staging (a missing role reuses the other map)
+      const uint32_t box_o[4] = {(uint32_t)cvb::TW, (uint32_t)cvb::TH, (uint32_t)cvb::CG, 1};
+      CUtensorMap tgr, tgf;
+      float* any = gradFrames[0] ? gradFrames[0] : gradFrames[1];
+      if ((rc = make_tmap4(&tgr, gradFrames[0] ? gradFrames[0] : any, dims, str, box_o, true))) return rc;
+      if ((rc = make_tmap4(&tgf, gradFrames[1] ? gradFrames[1] : any, dims, str, box_o, true))) return rc;
       static thread_local int attr_dev = -1;
       int dev = 0;
       B2F_CUDA_TRY(cudaGetDevice(&dev));
@@ -814,10 +826,10 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
       dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
       if (sgn > 0)
         cvb::costvol_bwd_tma<1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv, bdbg);
+            tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg);
       else
         cvb::costvol_bwd_tma<-1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, gradFrames[0], gradFrames[1], nroles, role0, nchunk, C, H, W, kdiv, bdbg);
+            tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg);
       B2F_CHECK_LAUNCH("costvol_bwd_tma");
       return B2F_OK;
     }
