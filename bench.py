@@ -217,49 +217,54 @@ class Workload:
         return sum(op.bytes for op in self.ops)
 
     # -- CUDA graph of one step -------------------------------------------------------------
-    def capture(self, main, side):
-        """Capture one step as a CUDA graph.  The past and the future branch of every stage are independent
-        in the network (two CostVolMulti / sampler instances feeding one decoder), so each (future, past)
-        pair of calls is forked onto two streams and joined before the next stage; stages stay in the
-        forward-then-backward order of `step`.  Replaying the graph removes the per-call launch gaps that
-        dominate the small pyramid levels."""
+    def capture(self, streams):
+        """Capture one step as a CUDA graph over `streams` (the first one is the capture stream).
+
+        Stages keep the forward-then-backward order of `step`; calls that are independent in the network run
+        concurrently inside a stage and are joined before the next one:
+          * the past and the future branch of a level (two CostVolMulti / sampler instances feeding one decoder);
+          * the image warps of the five output levels: each only needs its own level's flow (forward) or its
+            own level's loss gradient (backward) -- they are the leaves of the loss, one stage each way.
+        Replaying the graph also removes the per-call launch gaps that dominate the small pyramid levels."""
         torch, lib = self.torch, self.lib
-        pairs = {}
+        groups = {}
         order = []
         for which, name, kind, mk, nbytes, flops, zero in self._mk:
-            key = (which, kind)
-            if key not in pairs:
-                pairs[key] = []
+            key = (which, "warp_img" if kind.startswith("warp_img") else kind)
+            if key not in groups:
+                groups[key] = []
                 order.append(key)
-            pairs[key].append((name, mk, zero))
+            groups[key].append((name, mk, zero))
         fwd = [k for k in order if k[0] == "f"]
         bwd = [k for k in order if k[0] == "b"][::-1]
-        sm, ss = C.c_void_p(main.cuda_stream), C.c_void_p(side.cuda_stream)
-        calls = []
+        main = streams[0]
+        handles = [C.c_void_p(st.cuda_stream) for st in streams]
+        stages = []
         for key in fwd + bwd:
-            group = pairs[key]
             row = []
-            for i, (name, mk, zero) in enumerate(group):
-                sh = sm if i % 2 == 0 else ss
+            members = groups[key] if key[0] == "f" else groups[key][::-1]
+            for i, (name, mk, zero) in enumerate(members):
+                si = i % len(streams)
+                sh = handles[si]
                 z = (lambda a=zero, sh=sh: lib.b2f_zero_async(a[0], a[1], sh)) if zero is not None else None
-                row.append((i % 2, z, mk(sh), name))
-            calls.append(row)
+                row.append((si, z, mk(sh), name))
+            stages.append(row)
+        self.graph_stages = [[name for _, _, _, name in row] for row in stages]
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=main):
-            for row in calls:
-                forked = any(b for b, _, _, _ in row)
-                if forked:
-                    side.wait_stream(main)
-                for b, z, call, name in row:
+            for row in stages:
+                used = sorted({si for si, _, _, _ in row if si != 0})
+                for si in used:
+                    streams[si].wait_stream(main)
+                for si, z, call, name in row:
                     if z is not None and z():
                         raise RuntimeError("b2f_zero_async failed during capture")
                     rc = call()
                     if rc:
                         raise RuntimeError("%s failed during capture: %d: %s" % (name, rc, lib.b2f_last_error().decode()))
-                if forked:
-                    main.wait_stream(side)
+                for si in used:
+                    main.wait_stream(streams[si])
         return graph
-
 
 def breakdown(torch, wl, iters=10):
     """Per-kernel device times (separate pass, events around every call; not part of `value`)."""
@@ -575,8 +580,8 @@ def main():
     marks = {k: [] for k in dominant}
     graph = None
     if not args.eager:
-        gmain, gside = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        graph = wl.capture(gmain, gside)
+        gstreams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        graph = wl.capture(gstreams)
         for _ in range(3):
             graph.replay()
         torch.cuda.synchronize()
@@ -696,7 +701,9 @@ def main():
                              "buffer is reused" % (wl.total_bytes() / 1e9),
                        "alg_bytes_per_step": wl.total_bytes(),
                        "launch": "eager, one stream" if args.eager else
-                                 "one CUDA-graph replay per step; future / past branch of each stage on two streams"},
+                                 "one CUDA-graph replay per step; calls that are independent in the network (future / past "
+                                 "branch of a level; the image warps of the five output levels) run concurrently on up "
+                                 "to four streams inside a stage, stages in forward-then-backward order"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
