@@ -60,11 +60,14 @@ B2F_API int b2f_abi_version(void);
 B2F_API const char* b2f_last_error(void);          /* thread-local, never NULL                      */
 B2F_API const char* b2f_status_string(int status);
 B2F_API int b2f_release_scratch(void);             /* frees this thread's scratch on the current device */
-/* Test hook selecting the cost-volume kernel family (thread-local; returns the previous mode):
- * 0 = automatic (default), 1 = generic direct kernels, 2/3/4 = the tiled TMA kernels whenever
- * their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the grid-size
- * heuristics, with forward strip width 16/8/4 pixels; 5 = strip width 4 with the channel range
- * split over at least two CTAs per tile (the small-level path).                              */
+/* Test / measurement hook selecting the cost-volume kernel family (thread-local; returns the
+ * previous mode): 0 = automatic (default), 1 = generic direct kernels, 2/3/4 = the tiled TMA
+ * kernels whenever their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the
+ * grid-size heuristics, with 32- (2, 3) or 16-column (4) forward tiles; 5 = 16-column tiles with
+ * the channel range split over at least two work items per tile (the small-level path);
+ * 6 / 7 = force / forbid the persistent software-pipelined forward (FFMA2 + TMA-store epilogue).
+ * 8, 9, 10 are measurement aids that produce WRONG results: the tiled kernels without their
+ * arithmetic (8), without their stores (9), or with neither (10) -- they time the TMA feed.       */
 B2F_API int b2f_debug_costvol_path(int mode);
 /* Stream-ordered zero-fill of a device buffer (what the sampler's Lua wrapper does with
  * gradInput:zero() before the native call, BilinearSamplerBHWD.lua:99-102).                  */
