@@ -457,8 +457,12 @@ constexpr int X_ELEMS = NCW * XG_ELEMS;
 constexpr int GBOX_ELEMS = TH * GW1;           // slab geometry is sized for the wider role
 constexpr int SLAB_ELEMS = 9 * GBOX_ELEMS;
 __host__ __device__ constexpr int fdiv4(int v) { return (v >= 0) ? v / 4 : -((3 - v) / 4); }
-constexpr int NBAR = NCW + 4;
-constexpr int SMEM_BYTES = (X_ELEMS + 2 * SLAB_ELEMS) * 4 + NBAR * 8 + 128;
+// NSLAB = 2: double-buffered slab ring, two CTAs per SM (large levels).  NSLAB = 9: every slab has its own
+// buffer and all nine are requested at once, one CTA per SM: a small level is a chain of memory round trips,
+// and this turns nine of them into one.
+template <int NSLAB>
+constexpr int smem_bytes() { return (X_ELEMS + NSLAB * SLAB_ELEMS) * 4 + (NCW + 2 * NSLAB) * 8 + 128; }
+static_assert(smem_bytes<2>() * 2 <= 228 * 1024 - 2048 && smem_bytes<9>() <= 227 * 1024, "shared memory budget");
 static_assert((XW / 4) % 2 == 1 && (GW0 / 4) % 2 == 1 && (GW1 / 4) % 2 == 1, "row pitch must be odd*16B");
 static_assert((XG_ELEMS * 4) % 128 == 0 && (GBOX_ELEMS * 4) % 128 == 0, "TMA dst alignment");
 
@@ -504,8 +508,8 @@ __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float (&g)[9
   }
 }
 
-template <int SGN>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int SGN, int NSLAB>
+__global__ void __launch_bounds__(THREADS, NSLAB == 2 ? 2 : 1)
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
                 const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_go1,
                 const __grid_constant__ CUtensorMap tm_gref, const __grid_constant__ CUtensorMap tm_gfrm,
@@ -515,9 +519,9 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* xsm = reinterpret_cast<float*>(smem);
   float* gsm = xsm + X_ELEMS;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (X_ELEMS + 2 * SLAB_ELEMS) * 4);
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (X_ELEMS + NSLAB * SLAB_ELEMS) * 4);
   uint64_t* gfull = xfull + NCW;
-  uint64_t* gempty = gfull + 2;
+  uint64_t* gempty = gfull + NSLAB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -530,7 +534,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NCW; ++i) mbar_init(&xfull[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSLAB; ++i) {
       mbar_init(&gfull[i], 1);
       mbar_init(&gempty[i], NCW);
     }
@@ -543,7 +547,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     // pointer is not a constant-bank address any more and the TMA faults).
     if (lane == 0) {
       auto load_slab = [&](int iy) {
-        const int s = iy & 1;
+        const int s = iy % NSLAB;
         float* dst = gsm + s * SLAB_ELEMS;
         if (role == 0) {
           mbar_arrive_expect_tx(&gfull[s], 9 * TH * GW0 * 4);
@@ -569,9 +573,8 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
           tma_load_4d(xsm + w * XG_ELEMS, &tm_ref, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
         }
       }
-      load_slab(1);
-      for (int iy = 2; iy < 9; ++iy) {
-        mbar_wait(&gempty[iy & 1], ((iy >> 1) - 1) & 1);
+      for (int iy = 1; iy < 9; ++iy) {
+        if (iy >= NSLAB) mbar_wait(&gempty[iy % NSLAB], ((iy / NSLAB) - 1) & 1);
         load_slab(iy);
       }
     }
@@ -589,8 +592,8 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   mbar_wait(&xfull[warp], 0);
   const float* xbase = xsm + warp * XG_ELEMS + 8 * st;
   for (int iy = 0; iy < 9; ++iy) {
-    const int s = iy & 1;
-    mbar_wait(&gfull[s], (iy >> 1) & 1);
+    const int s = iy % NSLAB;
+    mbar_wait(&gfull[s], (iy / NSLAB) & 1);
     const float* xs = xbase + (r + 4 + T * (iy - 4)) * XW;
     float g[9][8];
     if (role == 0) slab_load_g<0>(g, gsm + s * SLAB_ELEMS, r, st);
@@ -743,16 +746,17 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
     const int sms = num_sms();
     if (path >= 2 && path <= 4) A = path == 4 ? 4 : 8;   // 2 and 3: 32-column tiles, 4: 16-column tiles
     else if (path >= 6 && path <= 10) A = 8;
+    // 13 / 14 select the backward variant only: automatic forward
     else if (W >= 32 && tiles_for(8, B, H, W) >= sms) A = 8;
     else A = 4;
-    if (A == 4 && (path == 0 || path == 5)) {
+    if (A == 4 && (path == 0 || path == 5 || path >= 13)) {
       const int64_t t = tiles_for(4, B, H, W);
       const int nchunks = (C + cvf::CK - 1) / cvf::CK;
       if (2 * t <= sms || path == 5) nsplit = (int)std::min<int64_t>(nchunks, std::max<int64_t>(path == 5 ? 2 : 1, sms / t));
       if ((int64_t)B * nsplit > 65535) nsplit = 1;
     }
     // software-pipelined single-CTA form once every SM gets at least two tiles (path 6 forces it, 7 forbids)
-    const bool pipe = path == 6 || path >= 8 || (path != 7 && tiles_for(A, B, H, W) * nsplit >= 2 * (int64_t)sms);
+    const bool pipe = path == 6 || (path >= 8 && path <= 10) || (path != 7 && tiles_for(A, B, H, W) * nsplit >= 2 * (int64_t)sms);
     if (A == 8)
       return pipe ? launch_fwd_sgn<8, true>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st)
                   : launch_fwd_sgn<8, false>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st);
@@ -817,19 +821,28 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
       int dev = 0;
       B2F_CUDA_TRY(cudaGetDevice(&dev));
       if (attr_dev != dev) {
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::SMEM_BYTES));
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::SMEM_BYTES));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<2>()));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<2>()));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<9>()));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<9>()));
         attr_dev = dev;
       }
+      // up to ~3 CTAs per SM in total: one CTA per SM with all nine slabs in flight (path 13 / 14 force either)
+      const bool deep = path == 13 || (path != 14 && ctas <= (int64_t)num_sms() * 3);
       const int role0 = gradFrames[0] ? 0 : 1;
       const int bdbg = (path >= 8 && path <= 10) ? path - 7 : 0;   // 8: no arithmetic, 9: no stores, 10: neither
       dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
-      if (sgn > 0)
-        cvb::costvol_bwd_tma<1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg);
-      else
-        cvb::costvol_bwd_tma<-1><<<grid, cvb::THREADS, cvb::SMEM_BYTES, st>>>(
-            tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg);
+#define B2F_BWD_LAUNCH(SG, NS)                                                                        \
+  cvb::costvol_bwd_tma<SG, NS><<<grid, cvb::THREADS, cvb::smem_bytes<NS>(), st>>>(                     \
+      tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg)
+      if (deep) {
+        if (sgn > 0) B2F_BWD_LAUNCH(1, 9);
+        else B2F_BWD_LAUNCH(-1, 9);
+      } else {
+        if (sgn > 0) B2F_BWD_LAUNCH(1, 2);
+        else B2F_BWD_LAUNCH(-1, 2);
+      }
+#undef B2F_BWD_LAUNCH
       B2F_CHECK_LAUNCH("costvol_bwd_tma");
       return B2F_OK;
     }

@@ -148,12 +148,13 @@ def test_costvol_forward_generic(env, win, F, B, Cn, h, w, fwd):
 
 @pytest.mark.parametrize("B,Cn,h,w", [(2, 32, 16, 64), (1, 40, 13, 36), (2, 8, 7, 16), (1, 70, 9, 100), (1, 3, 5, 4)])
 @pytest.mark.parametrize("fwd", [True, False])
-def test_costvol_backward_tiled(env, B, Cn, h, w, fwd):
+@pytest.mark.parametrize("mode", [13, 14])   # 13: nine slab buffers, one CTA per SM; 14: double-buffered ring
+def test_costvol_backward_tiled(env, mode, B, Cn, h, w, fwd):
     r = rng(4)
     frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(2)]
     wide = r.standard_normal((B, 162, h, w)).astype(np.float32)
     sl = slice(0, 81) if fwd else slice(81, 162)
-    env.lib.b2f_debug_costvol_path(2)
+    env.lib.b2f_debug_costvol_path(mode)
     try:
         grads = _costvol_bwd(env, frames, wide, sl, 9, fwd)
         only_ref = _costvol_bwd(env, frames, wide, sl, 9, fwd, skip=(1,))
