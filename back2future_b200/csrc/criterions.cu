@@ -382,7 +382,13 @@ struct SmArgs {
   int64_t n_dy;     // B*Ct*(h-1)*w, elements of the contiguous y-difference array
   int64_t n_dx;     // B*Ct*h*(w-1)
   int small;        // all flat indices fit in 32 bits
+  // exact division of n < 2^31 by the loop-invariant h-1 / w-1: q = umulhi(n, mul) >> shr (d > 1), else n
+  uint32_t mul_h1, shr_h1, mul_w1, shr_w1;
 };
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t mul, uint32_t shr) {
+  return d == 1u ? n : (__umulhi(n, mul) >> shr);
+}
 
 // order-1 edge weights -----------------------------------------------------------------
 template <int CIN, int CT>
@@ -400,14 +406,14 @@ __device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
       const unsigned t = ((unsigned)b * Cin + j) * a.h + y;
       float v = 0.f;
       if ((int64_t)t * a.w + x < a.n_dy) {
-        const unsigned r = t % (unsigned)(a.h - 1);
-        const unsigned t2 = t / (unsigned)(a.h - 1);   // = bb*Ct + cc
+        const unsigned t2 = fast_div(t, (unsigned)(a.h - 1), a.mul_h1, a.shr_h1);   // = bb*Ct + cc
+        const unsigned r = t - t2 * (unsigned)(a.h - 1);
         const float* p = a.tgt + (int64_t)t2 * hw + (int64_t)r * a.w + x;
         v = __ldg(p + a.w) - __ldg(p);
       }
       s += fabsf(v);
     }
-    return expf(-a.cs * (s / (float)Cin));
+    return __expf(-a.cs * (s / (float)Cin));
   }
   if (y < a.h - 1) {
 #pragma unroll
@@ -416,7 +422,7 @@ __device__ __forceinline__ float w1_y(const SmArgs& a, int b, int y, int x) {
       s += fabsf(__ldg(p + a.w) - __ldg(p));
     }
   }
-  return expf(-a.cs * (s / (float)Ct));
+  return __expf(-a.cs * (s / (float)Ct));
 }
 
 template <int CIN, int CT>
@@ -434,7 +440,7 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
         // rows of the contiguous x-difference array are w-1 long: row = idx / (w-1), 32-bit when it fits
         unsigned rowi, xx;
         if (a.small) {
-          rowi = (unsigned)idx / (unsigned)(a.w - 1);
+          rowi = fast_div((unsigned)idx, (unsigned)(a.w - 1), a.mul_w1, a.shr_w1);
           xx = (unsigned)idx - rowi * (unsigned)(a.w - 1);
         } else {
           rowi = (unsigned)(idx / (a.w - 1));
@@ -446,7 +452,7 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
       }
       s += fabsf(v);
     }
-    return expf(-a.cs * (s / (float)Cin));
+    return __expf(-a.cs * (s / (float)Cin));
   }
   if (x < a.w - 1) {
 #pragma unroll
@@ -455,7 +461,7 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
       s += fabsf(__ldg(p + 1) - __ldg(p));
     }
   }
-  return expf(-a.cs * (s / (float)Ct));
+  return __expf(-a.cs * (s / (float)Ct));
 }
 
 // CIN / CT: compile-time channel counts (2, 3 = every call of the model) or 0 = run-time.  With constant trip
@@ -463,7 +469,7 @@ __device__ __forceinline__ float w1_x(const SmArgs& a, int b, int y, int x) {
 // all overlap (with run-time loops every channel costs its own memory round trip).
 template <int PEN, int CIN, int CT>
 __global__ void __launch_bounds__(kThreads)
-smooth1_kernel(SmArgs a, LossOut lo) {
+smooth1_generic_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
   const int x = blockIdx.x * kThreads + threadIdx.x;
   const int b = blockIdx.z;
@@ -505,6 +511,87 @@ smooth1_kernel(SmArgs a, LossOut lo) {
   finish_loss(loss, lo);
 }
 
+// Model shapes (2-channel input, RGB target): a block owns `rows` CONSECUTIVE rows of a 128-pixel column strip.
+// Every thread evaluates only its own two edge weights and G = p'(g) * w per row; the two shifted terms of the
+// gradient, shiftR(Gx) and shiftD(Gy) (SmoothnessCriterion.lua:95-103), are the left neighbour's Gx (exchanged
+// through shared memory; only thread 0 recomputes its outside neighbour) and the previous row's Gy (carried
+// in registers; recomputed once at the top of the strip) -- the same operands and operations as evaluating them
+// in place, so the result is bit-identical to the generic kernel, at half the weight / penalty evaluations and
+// two instead of five input loads per channel.
+template <int PEN>
+__global__ void __launch_bounds__(kThreads)
+smooth1_kernel(SmArgs a, LossOut lo, int rows) {
+  constexpr int CIN = 2, CT = 3;
+  __shared__ float s_gx[2][CIN][kThreads];
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int w = a.w, h = a.h;
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x * kThreads + tid;
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * rows, y1 = min(h, y0 + rows);
+  const bool act = x < w;
+  const bool need_g = a.grad != nullptr;
+  const float* in0 = a.in + ((int64_t)b * CIN) * hw + x;
+  float loss = 0.f;
+  float gy_up[CIN] = {0.f, 0.f}, v_cur[CIN] = {0.f, 0.f};
+  if (act) {
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) v_cur[ch] = __ldg(in0 + ch * hw + (int64_t)y0 * w);
+    if (need_g && y0 > 0) {
+      const float wyu = w1_y<CIN, CT>(a, b, y0 - 1, x);
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch)
+        gy_up[ch] = pen_der<PEN>(v_cur[ch] - __ldg(in0 + ch * hw + (int64_t)(y0 - 1) * w), a.eps2) * wyu;
+    }
+  }
+  for (int y = y0; y < y1; ++y) {
+    float Gx[CIN] = {0.f, 0.f}, Gy[CIN] = {0.f, 0.f}, vl[CIN] = {0.f, 0.f};
+    float wxl = 0.f;
+    if (act) {
+      const float wx0 = w1_x<CIN, CT>(a, b, y, x), wy0 = w1_y<CIN, CT>(a, b, y, x);
+      if (need_g && tid == 0 && x > 0) wxl = w1_x<CIN, CT>(a, b, y, x - 1);
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        const float* p = in0 + ch * hw + (int64_t)y * w;
+        const float v = v_cur[ch];
+        const float vr = (x < w - 1) ? __ldg(p + 1) : 0.f;
+        const float vd = (y < h - 1) ? __ldg(p + w) : 0.f;
+        if (need_g && tid == 0 && x > 0) vl[ch] = __ldg(p - 1);
+        const float gx = (x < w - 1) ? vr - v : 0.f;
+        const float gy = (y < h - 1) ? vd - v : 0.f;
+        loss += pen_apply<PEN>(gx, a.eps2) * wx0 + pen_apply<PEN>(gy, a.eps2) * wy0;
+        Gx[ch] = pen_der<PEN>(gx, a.eps2) * wx0;
+        Gy[ch] = pen_der<PEN>(gy, a.eps2) * wy0;
+      }
+    }
+    if (need_g) {   // uniform for the block
+      const int buf = y & 1;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) s_gx[buf][ch][tid] = Gx[ch];
+      __syncthreads();
+      if (act) {
+#pragma unroll
+        for (int ch = 0; ch < CIN; ++ch) {
+          // -Gx + shift(Gx) - Gy + shift(Gy), in the reference's order
+          float g = -Gx[ch];
+          if (x > 0) g += (tid > 0) ? s_gx[buf][ch][tid - 1] : pen_der<PEN>(v_cur[ch] - vl[ch], a.eps2) * wxl;
+          g -= Gy[ch];
+          if (y > 0) g += gy_up[ch];
+          a.grad[((int64_t)b * CIN + ch) * hw + (int64_t)y * w + x] = g * a.norm;
+        }
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        gy_up[ch] = Gy[ch];
+        if (y < h - 1) v_cur[ch] = __ldg(in0 + ch * hw + (int64_t)(y + 1) * w);
+      }
+    }
+  }
+  finish_loss(loss, lo);
+}
+
 // order-2 weights (SecondOrderSmoothnessCriterion.lua:49-61) ------------------------------
 template <int CIN, int CT>
 __device__ __forceinline__ float w2_y(const SmArgs& a, int b, int y, int x) {
@@ -519,7 +606,7 @@ __device__ __forceinline__ float w2_y(const SmArgs& a, int b, int y, int x) {
     if (y >= 1) s1 += fabsf(t - __ldg(p - a.w));
     if (y >= 1 && y <= a.h - 2) s2 += fabsf(t - __ldg(p + a.w));
   }
-  return expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
+  return __expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
 }
 template <int CIN, int CT>
 __device__ __forceinline__ float w2_x(const SmArgs& a, int b, int y, int x) {
@@ -534,7 +621,7 @@ __device__ __forceinline__ float w2_x(const SmArgs& a, int b, int y, int x) {
     if (x >= 1) s1 += fabsf(t - __ldg(p - 1));
     if (x >= 1 && x <= a.w - 2) s2 += fabsf(t - __ldg(p + 1));
   }
-  return expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
+  return __expf(-a.cs * (s1 / (float)Ct + s2 / (float)Ct));
 }
 
 template <int PEN, int CIN, int CT>
@@ -779,6 +866,19 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   a.n_dy = (int64_t)B * Ct * (h - 1) * w;
   a.n_dx = (int64_t)B * Ct * h * (w - 1);
   a.small = ((int64_t)B * (Cin > Ct ? Cin : Ct) * h * w) < ((int64_t)1 << 31) ? 1 : 0;
+  auto find_divisor = [](uint32_t d, uint32_t* mul, uint32_t* shr) {
+    *mul = 0;
+    *shr = 0;
+    if (d > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < d) ++lg;
+      const uint32_t pw = 31 + lg;
+      *mul = (uint32_t)((((uint64_t)1 << pw) + d - 1) / d);
+      *shr = pw - 32;
+    }
+  };
+  find_divisor(h > 1 ? (uint32_t)(h - 1) : 1u, &a.mul_h1, &a.shr_h1);
+  find_divisor(w > 1 ? (uint32_t)(w - 1) : 1u, &a.mul_w1, &a.shr_w1);
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
   const int pen = prm->penalty;
@@ -788,10 +888,16 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
     if (fixed) KERN<P, 2, 3><<<grid, kThreads, 0, st>>>(a, ls.lo);                        \
     else KERN<P, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);                              \
   } while (0)
-  if (prm->order == 1) {
-    if (pen == B2F_PENALTY_QUADRATIC) B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_QUADRATIC);
-    else if (pen == B2F_PENALTY_L1) B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_L1);
-    else B2F_SMOOTH_LAUNCH(smooth1_kernel, B2F_PENALTY_LORENTZIAN);
+  if (prm->order == 1 && fixed) {
+    const int rows = (h + (int)grid.y - 1) / (int)grid.y;   // consecutive rows per block
+    const dim3 g1(grid.x, (h + rows - 1) / rows, grid.z);
+    if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<g1, kThreads, 0, st>>>(a, ls.lo, rows);
+    else if (pen == B2F_PENALTY_L1) smooth1_kernel<B2F_PENALTY_L1><<<g1, kThreads, 0, st>>>(a, ls.lo, rows);
+    else smooth1_kernel<B2F_PENALTY_LORENTZIAN><<<g1, kThreads, 0, st>>>(a, ls.lo, rows);
+  } else if (prm->order == 1) {
+    if (pen == B2F_PENALTY_QUADRATIC) smooth1_generic_kernel<B2F_PENALTY_QUADRATIC, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else if (pen == B2F_PENALTY_L1) smooth1_generic_kernel<B2F_PENALTY_L1, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    else smooth1_generic_kernel<B2F_PENALTY_LORENTZIAN, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
   } else {
     if (pen == B2F_PENALTY_QUADRATIC) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_QUADRATIC);
     else if (pen == B2F_PENALTY_L1) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_L1);
