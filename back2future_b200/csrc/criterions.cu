@@ -6,6 +6,8 @@
 // block to finish (ticket counter) sums the block partials in index order and applies the normaliser.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace b2f {
 namespace {
 
@@ -626,7 +628,7 @@ __device__ __forceinline__ float w2_x(const SmArgs& a, int b, int y, int x) {
 
 template <int PEN, int CIN, int CT>
 __global__ void __launch_bounds__(kThreads)
-smooth2_kernel(SmArgs a, LossOut lo) {
+smooth2_generic_kernel(SmArgs a, LossOut lo) {
   const int64_t hw = (int64_t)a.h * a.w;
   const int x = blockIdx.x * kThreads + threadIdx.x;
   const int b = blockIdx.z;
@@ -685,6 +687,103 @@ smooth2_kernel(SmArgs a, LossOut lo) {
     if (CIN && need_g) {
 #pragma unroll
       for (int ch = 0; ch < NG; ++ch) a.grad[((int64_t)b * Cin + ch) * hw + (int64_t)y * w + x] = gsave[ch];
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+// Model shapes (2-channel input, RGB target).  grad = 2 G[i] - G[i-1] - G[i+1] per direction with G = p'(g) * w
+// (SecondOrderSmoothnessCriterion.lua:87-97): the generic kernel evaluates G at all six neighbours of a pixel.
+// Here a block owns `rows` consecutive rows of a 126-pixel column strip (threads 0 and 127 are halo pixels):
+// every thread evaluates G once per row, Gx of the neighbours comes through shared memory, Gy is computed one
+// row ahead and kept in a three-row register window, and the input rows slide through registers (one new load
+// per channel and row).  Same operands; the six terms are summed in a different order (fp32 rounding only).
+constexpr int kS2Out = kThreads - 2;
+template <int PEN>
+__global__ void __launch_bounds__(kThreads)
+smooth2_kernel(SmArgs a, LossOut lo, int rows) {
+  constexpr int CIN = 2, CT = 3;
+  __shared__ float s_gx[2][CIN][kThreads];
+  const int64_t hw = (int64_t)a.h * a.w;
+  const int w = a.w, h = a.h;
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x * kS2Out + tid - 1;
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * rows, y1 = min(h, y0 + rows);
+  const bool inimg = x >= 0 && x < w;
+  const bool outp = inimg && tid >= 1 && tid <= kS2Out;
+  const bool need_g = a.grad != nullptr;
+  const float* in0 = a.in + ((int64_t)b * CIN) * hw + (inimg ? x : 0);
+  float loss = 0.f;
+  // register window over the input rows r-1, r, r+1 and over Gy(r-2), Gy(r-1)
+  float im1[CIN], i0[CIN], ip1[CIN], gy2[CIN], gy1[CIN], xterm[CIN], gyc[CIN];
+#pragma unroll
+  for (int ch = 0; ch < CIN; ++ch) {
+    im1[ch] = i0[ch] = ip1[ch] = gy2[ch] = gy1[ch] = xterm[ch] = gyc[ch] = 0.f;
+    if (inimg) {
+      const int r = y0 - 1;   // first row whose Gy is needed
+      if (r - 1 >= 0) im1[ch] = __ldg(in0 + ch * hw + (int64_t)(r - 1) * w);
+      if (r >= 0) i0[ch] = __ldg(in0 + ch * hw + (int64_t)r * w);
+      if (r + 1 < h) ip1[ch] = __ldg(in0 + ch * hw + (int64_t)(r + 1) * w);
+    }
+  }
+  const int rbeg = need_g ? y0 - 1 : y0, rend = need_g ? y1 : y1 - 1;
+  if (!need_g && inimg) {   // the window starts one row later
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) {
+      im1[ch] = i0[ch];
+      i0[ch] = ip1[ch];
+      ip1[ch] = (y0 + 1 < h) ? __ldg(in0 + ch * hw + (int64_t)(y0 + 1) * w) : 0.f;
+    }
+  }
+  for (int r = rbeg; r <= rend; ++r) {
+    const bool own = r >= y0 && r < y1;   // a row of this block (loss, x terms); else only Gy is needed
+    float Gx[CIN] = {0.f, 0.f};
+    if (inimg && r >= 0 && r < h) {
+      const float wy = w2_y<CIN, CT>(a, b, r, x);
+      const float wx = own ? w2_x<CIN, CT>(a, b, r, x) : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        const float gy = (r >= 1 && r <= h - 2) ? (2.f * i0[ch] - im1[ch]) - ip1[ch] : 0.f;
+        gyc[ch] = (r >= 1 && r <= h - 2) ? pen_der<PEN>(gy, a.eps2) * wy : 0.f;
+        if (own) {
+          float gx = 0.f;
+          if (x >= 1 && x <= w - 2) {
+            const float* q = in0 + ch * hw + (int64_t)r * w;
+            gx = (2.f * i0[ch] - __ldg(q - 1)) - __ldg(q + 1);
+            Gx[ch] = pen_der<PEN>(gx, a.eps2) * wx;
+          }
+          if (outp) loss += pen_apply<PEN>(gx, a.eps2) * wx + pen_apply<PEN>(gy, a.eps2) * wy;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) gyc[ch] = 0.f;
+    }
+    if (need_g) {   // uniform for the block
+      const int buf = r & 1;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) s_gx[buf][ch][tid] = Gx[ch];
+      __syncthreads();
+      if (outp) {
+#pragma unroll
+        for (int ch = 0; ch < CIN; ++ch) {
+          // row r-1 is complete: 2 Gy(r-1) - Gy(r) - Gy(r-2) + its x terms
+          if (r - 1 >= y0) {
+            const float g = ((2.f * gy1[ch] - gyc[ch]) - gy2[ch]) + xterm[ch];
+            a.grad[((int64_t)b * CIN + ch) * hw + (int64_t)(r - 1) * w + x] = g * a.norm;
+          }
+          if (own) xterm[ch] = (2.f * Gx[ch] - s_gx[buf][ch][tid + 1]) - s_gx[buf][ch][tid - 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) {
+      gy2[ch] = gy1[ch];
+      gy1[ch] = gyc[ch];
+      im1[ch] = i0[ch];
+      i0[ch] = ip1[ch];
+      ip1[ch] = (inimg && r + 2 < h && r + 2 >= 0) ? __ldg(in0 + ch * hw + (int64_t)(r + 2) * w) : 0.f;
     }
   }
   finish_loss(loss, lo);
@@ -880,14 +979,11 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   find_divisor(h > 1 ? (uint32_t)(h - 1) : 1u, &a.mul_h1, &a.shr_h1);
   find_divisor(w > 1 ? (uint32_t)(w - 1) : 1u, &a.mul_w1, &a.shr_w1);
   LossScratch ls;
+  // the second-order fast kernel uses 126-pixel x tiles: size the partials for the larger grid
+  blocks = (int)((int64_t)((w + kS2Out - 1) / kS2Out) * grid.y * grid.z);
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
   const int pen = prm->penalty;
   const bool fixed = Cin == 2 && Ct == 3;   // the model's shapes: flow / occlusion map vs RGB target
-#define B2F_SMOOTH_LAUNCH(KERN, P)                                                        \
-  do {                                                                                    \
-    if (fixed) KERN<P, 2, 3><<<grid, kThreads, 0, st>>>(a, ls.lo);                        \
-    else KERN<P, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);                              \
-  } while (0)
   if (prm->order == 1 && fixed) {
     const int rows = (h + (int)grid.y - 1) / (int)grid.y;   // consecutive rows per block
     const dim3 g1(grid.x, (h + rows - 1) / rows, grid.z);
@@ -899,11 +995,18 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
     else if (pen == B2F_PENALTY_L1) smooth1_generic_kernel<B2F_PENALTY_L1, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
     else smooth1_generic_kernel<B2F_PENALTY_LORENTZIAN, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
   } else {
-    if (pen == B2F_PENALTY_QUADRATIC) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_QUADRATIC);
-    else if (pen == B2F_PENALTY_L1) B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_L1);
-    else B2F_SMOOTH_LAUNCH(smooth2_kernel, B2F_PENALTY_LORENTZIAN);
+    if (fixed) {
+      const int rows = std::max(4, (h + (int)grid.y - 1) / (int)grid.y);   // consecutive rows per block (2 extra per strip)
+      const dim3 g2((w + kS2Out - 1) / kS2Out, (h + rows - 1) / rows, grid.z);
+      if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+      else if (pen == B2F_PENALTY_L1) smooth2_kernel<B2F_PENALTY_L1><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+      else smooth2_kernel<B2F_PENALTY_LORENTZIAN><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+    } else {
+      if (pen == B2F_PENALTY_QUADRATIC) smooth2_generic_kernel<B2F_PENALTY_QUADRATIC, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
+      else if (pen == B2F_PENALTY_L1) smooth2_generic_kernel<B2F_PENALTY_L1, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
+      else smooth2_generic_kernel<B2F_PENALTY_LORENTZIAN, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
+    }
   }
-#undef B2F_SMOOTH_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
