@@ -57,6 +57,7 @@ __device__ __forceinline__ void finish_loss(float local, const LossOut& lo) {
     tot *= lo.scale;
     *lo.result = tot;
     if (lo.loss_dev) *lo.loss_dev = tot;
+    *lo.counter = 0u;   // self-cleaning ticket: the next call on this stream needs no memset
   }
 }
 
@@ -112,6 +113,9 @@ int get_scratch(size_t bytes, cudaStream_t st, void** out) {
       return fail(B2F_ENOMEM, "criterion scratch: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
     }
     s.bytes = want;
+    // the ticket counter starts at zero and every kernel leaves it at zero (finish_loss)
+    e = cudaMemsetAsync(s.mem, 0, 2 * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(loss scratch)");
   }
   *out = s.mem;
   return B2F_OK;
@@ -132,8 +136,6 @@ struct LossScratch {
     lo.partials = lo.result + 2;
     lo.loss_dev = loss_dev;
     lo.scale = scale;
-    cudaError_t e = cudaMemsetAsync(lo.counter, 0, sizeof(double), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(loss counter)");
     return B2F_OK;
   }
   int end(double* loss_host) {

@@ -293,6 +293,68 @@ def breakdown(torch, wl, iters=10):
 
 
 # ----------------------------------------------------------------------------------------
+# criterions (BASELINE configs[2], [3]): informational block, not part of `value`
+# ----------------------------------------------------------------------------------------
+
+def time_criterions(torch, lib, dev, B=BATCH, iters=9):
+    """Device time of the fused criterion calls of a training step at the reference's training pyramid
+    (8 x 320 x 640 ... 20 x 40, RoamingImages / KITTI crops): SURVEY rows a6-a14.  L2 is flushed before every
+    call.  Returns microseconds summed over the five levels and GB/s (algorithmic bytes) at the top level."""
+    from back2future_b200 import _lib
+    P = lambda t: C.c_void_p(t.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def timeit(fn):
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn())
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    names = ("OBCC", "OBGCC", "Smoothness(flow,L1)", "Smoothness(occ,Quadratic)", "SecondOrderSmoothness", "ConstVel",
+             "OcclusionPrior")
+    bpp = (84, 84, 28, 28, 28, 32, 16)
+    tot = dict.fromkeys(names, 0.0)
+    top = {}
+    for k in range(5):
+        h, w = 320 >> k, 640 >> k
+        flow, bflow = torch.randn(B, 2, h, w, device=dev) * 0.2, torch.randn(B, 2, h, w, device=dev) * 0.2
+        occ = torch.softmax(torch.randn(B, 2, h, w, device=dev), 1).contiguous()
+        w1, w2, tgt = (torch.rand(B, 3, h, w, device=dev) * 4.7 - 2.1 for _ in range(3))
+        g2a, g2b, g3a, g3b = torch.empty_like(flow), torch.empty_like(flow), torch.empty_like(w1), torch.empty_like(w1)
+        calls = []
+        for gt in (0, 1):
+            prm = _lib.ObParams(gt, 1, 0.05, 1.0, 0.0 if gt else 1.0, 1.0, 1.0, 20.0 / 2 ** k, gt, 0, 0)
+            calls.append(lambda prm=prm: lib.b2f_ob_criterion(C.byref(prm), P(flow), P(bflow), P(occ), P(w1), P(w2), P(tgt),
+                                                              B, 3, h, w, P(g2a), P(g3a), P(g3b), P(loss), None, None))
+        for order, pen, src in ((1, 1, flow), (1, 0, occ), (2, 1, flow)):
+            prm = _lib.SmoothParams(order, pen, 0.05, 20.0, 0, 1)
+            calls.append(lambda prm=prm, src=src: lib.b2f_smoothness_criterion(C.byref(prm), P(src), P(tgt), B, 2, 3, h, w,
+                                                                               P(g2a), P(loss), None, None))
+        calls.append(lambda: lib.b2f_constvel_criterion(P(flow), P(bflow), B, 2, h, w, 1, P(g2a), P(g2b), P(loss), None, None))
+        calls.append(lambda: lib.b2f_occprior_criterion(P(occ), B, 2, h, w, 1.0, 0, P(g2a), P(loss), None, None))
+        for n, fn, bytes_pp in zip(names, calls, bpp):
+            t = timeit(fn)
+            tot[n] += t
+            if k == 0:
+                top[n] = round(bytes_pp * B * h * w / t / 1e3, 1)
+    cfg3 = tot["OBCC"] + tot["Smoothness(flow,L1)"] + tot["Smoothness(occ,Quadratic)"] + tot["OcclusionPrior"]
+    cfg4 = (tot["OBGCC"] + tot["SecondOrderSmoothness"] + tot["Smoothness(occ,Quadratic)"] + tot["ConstVel"]
+            + tot["OcclusionPrior"])
+    return {"workload": "fused criterion calls (loss + gradients) of one training step, B=8, 320x640 .. 20x40, L2 flushed",
+            "us_sum_over_5_levels": {n: round(v, 1) for n, v in tot.items()},
+            "GBps_alg_at_320x640": top,
+            "config3_hard_step_us": round(cfg3, 1), "config4_soft_step_us": round(cfg4, 1)}
+
+
+# ----------------------------------------------------------------------------------------
 # e2e: module API, host buffers
 # ----------------------------------------------------------------------------------------
 
@@ -530,6 +592,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work (rank 0, N=1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-criterions", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls on one stream instead of the CUDA graph")
     args = ap.parse_args()
@@ -676,6 +739,7 @@ def main():
 
     # ---- per-kernel breakdown (informational) and CPU baseline (rank 0) ----------------
     rows = breakdown(torch, wl) if rank == 0 else None
+    crit = time_criterions(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, desc, sps, n = time_cpu(args.cpu_budget)
@@ -705,6 +769,7 @@ def main():
                                  "branch of a level; the image warps of the five output levels) run concurrently on up "
                                  "to four streams inside a stage, stages in forward-then-backward order"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "criterions": crit,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
