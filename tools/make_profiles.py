@@ -40,14 +40,14 @@ print("step sum %.1f us" % tot)
 
 # ---- full-set summaries -------------------------------------------------------------------
 traffic = {}
-for part in ("cv", "warp"):
+for part in ("cv", "warp", "crit"):
     raw = os.path.join(G, "prof_%s_%s_raw.csv" % (tag, part))
     if not os.path.exists(raw):
         continue
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), raw], capture_output=True, text=True).stdout
-    name = {"cv": "costvol", "warp": "warp"}[part]
+    name = {"cv": "costvol", "warp": "warp", "crit": "criterions"}[part]
     with open(os.path.join(P, "%s_ncu_%s_summary_%s.txt" % (rnd, name, tag)), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on, python tools/prof_target.py %s 1 (BASELINE config 2 sizes)\n" % ("cv3" if part == "cv" else "warp"))
+        f.write("# ncu --set full --clock-control none --import-source on, python tools/prof_target.py %s 1 (BASELINE config sizes)\n" % {"cv": "cv3", "warp": "warp", "crit": "-> tools/prof_crit.py"}[part])
         f.write(out)
     r = list(csv.reader(open(raw)))
     h, u, d = r[0], r[1], r[2:]
