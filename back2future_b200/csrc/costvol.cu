@@ -444,41 +444,54 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
 // buffered).  Per slab a thread reads its 9 x 8 gradOut values once and, per channel, 16 X values
 // for 72 FFMAs.  Every output element is written exactly once: no atomics, no zero-fill.
 namespace cvb {
-constexpr int TH = 8, TW = 32;
+constexpr int TH = 8;             // tile rows
 constexpr int CC = 32;            // channels per CTA
 constexpr int CG = 8;             // channels per warp
-constexpr int NCW = CC / CG;      // compute warps
-constexpr int THREADS = (NCW + 1) * 32;
-constexpr int XW = TW + 12, XR = TH + 8;       // X box: 44 x 16 (pitch 11*16 B)
-constexpr int GW0 = TW + 4;                    // gradRef:   gradOut box 36 wide at (x0, y0)        (pitch 9*16 B)
-constexpr int GW1 = TW + 12;                   // gradFrame: aligned superset 44 wide at (x0-4, y0+s*qy) (pitch 11*16 B)
-constexpr int XG_ELEMS = CG * XR * XW;         // one warp's X group
-constexpr int X_ELEMS = NCW * XG_ELEMS;
-constexpr int GBOX_ELEMS = TH * GW1;           // slab geometry is sized for the wider role
-constexpr int SLAB_ELEMS = 9 * GBOX_ELEMS;
+constexpr int NCG = CC / CG;      // channel groups
+constexpr int XR = TH + 8;        // X box rows
 __host__ __device__ constexpr int fdiv4(int v) { return (v >= 0) ? v / 4 : -((3 - v) / 4); }
-// NSLAB = 2: double-buffered slab ring, two CTAs per SM (large levels).  NSLAB = 9: every slab has its own
-// buffer and all nine are requested at once, one CTA per SM: a small level is a chain of memory round trips,
-// and this turns nine of them into one.
-template <int NSLAB>
-constexpr int smem_bytes() { return (X_ELEMS + NSLAB * SLAB_ELEMS) * 4 + (NCW + 2 * NSLAB) * 8 + 128; }
-static_assert(smem_bytes<2>() * 2 <= 228 * 1024 - 2048 && smem_bytes<9>() <= 227 * 1024, "shared memory budget");
-static_assert((XW / 4) % 2 == 1 && (GW0 / 4) % 2 == 1 && (GW1 / 4) % 2 == 1, "row pitch must be odd*16B");
-static_assert((XG_ELEMS * 4) % 128 == 0 && (GBOX_ELEMS * 4) % 128 == 0, "TMA dst alignment");
+
+// TW = tile width, NSLAB = gradOut slab ring depth:
+//   <32, 2>: two CTAs per SM (115.6 KB each: exactly the limit), four compute warps -- narrow levels
+//   <32, 9>: one CTA per SM, all nine slabs requested at once -- small levels (a chain of round trips)
+//   <64, 3>: one CTA per SM, eight compute warps (two 32-column halves x four channel groups), 3-deep ring.
+//            The TMA unit delivers one box ROW per ~8 cycles per SM whatever its length
+//            (tools/ubench/tma_feed.cu), so 64-column tiles halve the feed time per pixel -- but the kernel
+//            as a whole measured slower than <32, 2> (see the dispatch), so it is an experiment, not the default
+template <int TW_, int NSLAB_>
+struct Cfg {
+  static constexpr int TW = TW_, NSLAB = NSLAB_;
+  static constexpr int NH = TW / 32;              // 32-column halves
+  static constexpr int NCW = NCG * NH;            // compute warps
+  static constexpr int THREADS = (NCW + 1) * 32;
+  static constexpr int XW = TW + 12;              // X box width (odd multiple of 16 B)
+  static constexpr int GW0 = TW + 4;              // gradRef:   gradOut box at (x0, y0)
+  static constexpr int GW1 = TW + 12;             // gradFrame: aligned superset at (x0-4, y0+s*qy)
+  static constexpr int XG_ELEMS = CG * XR * XW;   // one channel group of X
+  static constexpr int X_ELEMS = NCG * XG_ELEMS;
+  static constexpr int GBOX_ELEMS = TH * GW1;     // slab geometry is sized for the wider role
+  static constexpr int SLAB_ELEMS = 9 * GBOX_ELEMS;
+  static constexpr int NBAR = NCG + 2 * NSLAB;
+  static constexpr int SMEM_BYTES = (X_ELEMS + NSLAB * SLAB_ELEMS) * 4 + NBAR * 8 + 128;
+  static constexpr int CTAS_PER_SM = (TW == 32 && NSLAB == 2) ? 2 : 1;
+  static_assert((XW / 4) % 2 == 1 && (GW0 / 4) % 2 == 1 && (GW1 / 4) % 2 == 1, "row pitch must be odd*16B");
+  static_assert((XG_ELEMS * 4) % 128 == 0 && (GBOX_ELEMS * 4) % 128 == 0, "TMA dst alignment");
+  static_assert(SMEM_BYTES * CTAS_PER_SM <= 228 * 1024 - 1024 * CTAS_PER_SM && SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
 
 // Copy this thread's 9 x 8 gradOut values of the current slab into registers.  SHIFT == 0 (gradRef): the
 // slab holds go[q] at the tile itself.  SHIFT == +-1 (gradFrame): the slab holds the 16-byte aligned
-// superset [x0-4, x0+40) of the rows shifted by s*qy; the x shift s*qx is a compile-time constant per ix,
+// superset [x0-4, x0+TW+8) of the rows shifted by s*qy; the x shift s*qx is a compile-time constant per ix,
 // so the 8 wanted floats are 2-3 aligned LDS.128 plus a static register selection (a TMA box cannot start
-// at an x that is not a multiple of 16 bytes).
-template <int SHIFT>
-__device__ __forceinline__ void slab_load_g(float (&g)[9][8], const float* __restrict__ slab, int r, int st) {
-  constexpr int GWS = SHIFT == 0 ? GW0 : GW1;
+// at an x that is not a multiple of 16 bytes).  `col` = first column of the thread inside the tile.
+template <class cfg, int SHIFT>
+__device__ __forceinline__ void slab_load_g(float (&g)[9][8], const float* __restrict__ slab, int r, int col) {
+  constexpr int GWS = SHIFT == 0 ? cfg::GW0 : cfg::GW1;
 #pragma unroll
   for (int ix = 0; ix < 9; ++ix) {
     const int base = SHIFT == 0 ? 0 : 4 + SHIFT * (ix - 4);   // offset of the window inside the box row
     const int o = base - 4 * fdiv4(base);
-    const float* p = slab + ix * (TH * GWS) + r * GWS + 8 * st + 4 * fdiv4(base);
+    const float* p = slab + ix * (TH * GWS) + r * GWS + col + 4 * fdiv4(base);
     float v[12];
 #pragma unroll
     for (int q = 0; q < (o == 0 ? 2 : 3); ++q) {
@@ -490,14 +503,14 @@ __device__ __forceinline__ void slab_load_g(float (&g)[9][8], const float* __res
   }
 }
 
-template <int T>
+template <class cfg, int T>
 __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float (&g)[9][8], const float* __restrict__ xs) {
 #pragma unroll
   for (int c = 0; c < CG; ++c) {
     float xv[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(xs + c * (XR * XW) + 4 * q);
+      const float4 v = *reinterpret_cast<const float4*>(xs + c * (XR * cfg::XW) + 4 * q);
       xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
     }
 #pragma unroll
@@ -508,19 +521,22 @@ __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float (&g)[9
   }
 }
 
-template <int SGN, int NSLAB>
-__global__ void __launch_bounds__(THREADS, NSLAB == 2 ? 2 : 1)
+template <int SGN, int TW, int NSLAB>
+__global__ void __launch_bounds__((Cfg<TW, NSLAB>::THREADS), (Cfg<TW, NSLAB>::CTAS_PER_SM))
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
                 const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_go1,
                 const __grid_constant__ CUtensorMap tm_gref, const __grid_constant__ CUtensorMap tm_gfrm,
                 int nroles, int role0, int nchunk, int C, int H, int W, float kdiv, int dbg) {
+  using cfg = Cfg<TW, NSLAB>;
+  constexpr int NCW = cfg::NCW, XW = cfg::XW, GW0 = cfg::GW0, GW1 = cfg::GW1;
+  constexpr int XG_ELEMS = cfg::XG_ELEMS, SLAB_ELEMS = cfg::SLAB_ELEMS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // pointer + integer offset keeps the shared address space (LDS, not generic LD)
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* xsm = reinterpret_cast<float*>(smem);
-  float* gsm = xsm + X_ELEMS;
-  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (X_ELEMS + NSLAB * SLAB_ELEMS) * 4);
-  uint64_t* gfull = xfull + NCW;
+  float* gsm = xsm + cfg::X_ELEMS;
+  uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + (cfg::X_ELEMS + NSLAB * SLAB_ELEMS) * 4);   // [channel group]
+  uint64_t* gfull = xfull + NCG;
   uint64_t* gempty = gfull + NSLAB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -533,7 +549,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   const int T = (role == 0) ? -SGN : SGN;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NCW; ++i) mbar_init(&xfull[i], 1);
+    for (int i = 0; i < NCG; ++i) mbar_init(&xfull[i], 1);
     for (int i = 0; i < NSLAB; ++i) {
       mbar_init(&gfull[i], 1);
       mbar_init(&gempty[i], NCW);
@@ -563,12 +579,12 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
       };
       load_slab(0);
       if (role == 0) {
-        for (int w = 0; w < NCW; ++w) {
+        for (int w = 0; w < NCG; ++w) {
           mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
           tma_load_4d(xsm + w * XG_ELEMS, &tm_frame, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
         }
       } else {
-        for (int w = 0; w < NCW; ++w) {
+        for (int w = 0; w < NCG; ++w) {
           mbar_arrive_expect_tx(&xfull[w], XG_ELEMS * 4);
           tma_load_4d(xsm + w * XG_ELEMS, &tm_ref, x0 - 4, y0 - 4, c0 + w * CG, b, &xfull[w]);
         }
@@ -581,40 +597,46 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     return;
   }
 
-  // ---- consumers ----
+  // ---- consumers: warp = (channel group, 32-column half) ----
+  const int cg = warp % NCG, half = warp / NCG;
   const int r = lane & 7, st = lane >> 3;
+  const int col = 32 * half + 8 * st;      // first column of this thread inside the tile
   float acc[CG][8];
 #pragma unroll
   for (int c = 0; c < CG; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
 
-  mbar_wait(&xfull[warp], 0);
-  const float* xbase = xsm + warp * XG_ELEMS + 8 * st;
+  mbar_wait(&xfull[cg], 0);
+  const float* xbase = xsm + cg * XG_ELEMS + col;
+#pragma unroll 1
   for (int iy = 0; iy < 9; ++iy) {
     const int s = iy % NSLAB;
     mbar_wait(&gfull[s], (iy / NSLAB) & 1);
     const float* xs = xbase + (r + 4 + T * (iy - 4)) * XW;
     float g[9][8];
-    if (role == 0) slab_load_g<0>(g, gsm + s * SLAB_ELEMS, r, st);
-    else           slab_load_g<SGN>(g, gsm + s * SLAB_ELEMS, r, st);
+    if (role == 0) slab_load_g<cfg, 0>(g, gsm + s * SLAB_ELEMS, r, col);
+    else           slab_load_g<cfg, SGN>(g, gsm + s * SLAB_ELEMS, r, col);
     // the slab is dead as soon as every lane holds its values: release it BEFORE the FFMAs so the
     // producer refills it a whole window row earlier
     __syncwarp();
     if (lane == 0) mbar_arrive(&gempty[s]);
     if (dbg & 1) continue;   // measurement aid: feed only
-    if (T > 0) slab_fma<1>(acc, g, xs);
-    else       slab_fma<-1>(acc, g, xs);
+    if (T > 0) slab_fma<cfg, 1>(acc, g, xs);
+    else       slab_fma<cfg, -1>(acc, g, xs);
   }
 
   // ---- epilogue ----
-  // The warp's X group is dead: its 8 channels x 8 rows x 32 columns of results are staged there with the TMA
-  // 128-byte swizzle (16-byte chunk c of the 128-byte row at address A sits at chunk c ^ ((A >> 7) & 7), so the
-  // eight rows of a quarter-warp hit eight different bank groups) and leave as ONE bulk tensor store; channels
-  // >= C and pixels outside the image are clipped by the TMA.  (Direct STG.128 from this accumulator layout
-  // touches 8 lines per instruction: 33 cycles each, 16 us of the 117 us kernel at level 3.)
+  // The X group is dead once every warp that reads it is done (with 64-column tiles the two halves of a channel
+  // group share it: a 64-thread named barrier).  A warp's 8 channels x 8 rows x 32 columns of results are staged
+  // in its part of the group with the TMA 128-byte swizzle (16-byte chunk c of the 128-byte row at address A
+  // sits at chunk c ^ ((A >> 7) & 7), so the eight rows of a quarter-warp hit eight different bank groups) and
+  // leave as ONE bulk tensor store; channels >= C and pixels outside the image are clipped by the TMA.  (Direct
+  // STG.128 from this accumulator layout touches 8 lines per instruction: 33 cycles each, 16 us of the 117 us
+  // kernel at level 3.)
+  if (cfg::NH > 1) named_bar_sync(1 + cg, 32 * cfg::NH);
   const float kinv = 1.f / kdiv;
-  const uint32_t wbase = smem_u32(xsm) + (uint32_t)(warp * XG_ELEMS) * 4u;
+  const uint32_t wbase = smem_u32(xsm) + (uint32_t)(cg * XG_ELEMS) * 4u + (uint32_t)half * (CG * TH * 128);
 #pragma unroll
   for (int c = 0; c < CG; ++c) {
     const uint32_t rowaddr = wbase + (uint32_t)((c * TH + r) * 128);
@@ -628,8 +650,8 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0 && !(dbg & 2)) {
-    if (role == 0) tma_store_4d_addr(wbase, &tm_gref, x0, y0, c0 + warp * CG, b);
-    else           tma_store_4d_addr(wbase, &tm_gfrm, x0, y0, c0 + warp * CG, b);
+    if (role == 0) tma_store_4d_addr(wbase, &tm_gref, x0 + 32 * half, y0, c0 + cg * CG, b);
+    else           tma_store_4d_addr(wbase, &tm_gfrm, x0 + 32 * half, y0, c0 + cg * CG, b);
     tma_store_commit();
     tma_store_wait_read();   // shared memory must outlive the store's read
   }
@@ -796,23 +818,38 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
                 get_encode_fn() != nullptr;
   if (tma_ok) {
     const int nchunk = (C + cvb::CC - 1) / cvb::CC;
-    const int64_t ctas = (int64_t)B * ((H + cvb::TH - 1) / cvb::TH) * ((W + cvb::TW - 1) / cvb::TW) * nchunk * nroles;
-    if ((ctas < 48 && path < 2) || (int64_t)B * nchunk * nroles > 65535) tma_ok = false;
+    const int nty = (H + cvb::TH - 1) / cvb::TH;
+    const int64_t per_col = (int64_t)B * nty * nchunk * nroles;
+    const int64_t ctas32 = per_col * ((W + 31) / 32), ctas64 = per_col * ((W + 63) / 64);
+    if ((ctas32 < 48 && path < 2) || ctas32 > 0x3fffffff || per_col / nty > 65535) tma_ok = false;
     if (tma_ok) {
+      // variant: 13 / 14 / 15 force <32, 9> / <32, 2> / <64, 3>; automatic: small launches take the nine-slab
+      // form, everything else <32, 2>.  The wide form is measured SLOWER (level 3: 119 vs 109 us, level 4: 70
+      // vs 62 us) although it halves the TMA rows per pixel: with one CTA per SM the eight warps wait on the
+      // same slab at the same time; it stays selectable for experiments (path 15) and is covered by the tests.
+      int variant;   // 0: <32,2>, 1: <32,9>, 2: <64,3>
+      const int64_t sms = num_sms();
+      if (path == 13) variant = 1;
+      else if (path == 14) variant = 0;
+      else if (path == 15) variant = 2;
+      else if (ctas32 <= sms * 3) variant = 1;
+      else variant = 0;
+      (void)ctas64;
+      const int TWv = variant == 2 ? 64 : 32;
       const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
       const uint64_t str[3] = {(uint64_t)W, (uint64_t)hw, (uint64_t)hw * C};
-      const uint32_t box_x[4] = {(uint32_t)cvb::XW, (uint32_t)cvb::XR, (uint32_t)cvb::CG, 1};
+      const uint32_t box_x[4] = {(uint32_t)(TWv + 12), (uint32_t)cvb::XR, (uint32_t)cvb::CG, 1};
       const uint64_t gdims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
       const uint64_t gstr[3] = {(uint64_t)W, (uint64_t)hw, (uint64_t)gbs};
-      const uint32_t box_g0[4] = {(uint32_t)cvb::GW0, (uint32_t)cvb::TH, 1, 1};
-      const uint32_t box_g1[4] = {(uint32_t)cvb::GW1, (uint32_t)cvb::TH, 1, 1};
+      const uint32_t box_g0[4] = {(uint32_t)(TWv + 4), (uint32_t)cvb::TH, 1, 1};
+      const uint32_t box_g1[4] = {(uint32_t)(TWv + 12), (uint32_t)cvb::TH, 1, 1};
       CUtensorMap tfrm, tref, tgo, tgo1;
       if ((rc = make_tmap4(&tfrm, frames[1], dims, str, box_x))) return rc;
       if ((rc = make_tmap4(&tref, frames[0], dims, str, box_x))) return rc;
       if ((rc = make_tmap4(&tgo, gradOut, gdims, gstr, box_g0))) return rc;
       if ((rc = make_tmap4(&tgo1, gradOut, gdims, gstr, box_g1))) return rc;
       // results: 32 x 8 x 8-channel boxes, 128-byte swizzled staging (a missing role reuses the other map)
-      const uint32_t box_o[4] = {(uint32_t)cvb::TW, (uint32_t)cvb::TH, (uint32_t)cvb::CG, 1};
+      const uint32_t box_o[4] = {32, (uint32_t)cvb::TH, (uint32_t)cvb::CG, 1};
       CUtensorMap tgr, tgf;
       float* any = gradFrames[0] ? gradFrames[0] : gradFrames[1];
       if ((rc = make_tmap4(&tgr, gradFrames[0] ? gradFrames[0] : any, dims, str, box_o, true))) return rc;
@@ -821,26 +858,32 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
       int dev = 0;
       B2F_CUDA_TRY(cudaGetDevice(&dev));
       if (attr_dev != dev) {
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<2>()));
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<2>()));
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<9>()));
-        B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::smem_bytes<9>()));
+#define B2F_BWD_ATTR(TWX, NS)                                                                                      \
+  B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<1, TWX, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    cvb::Cfg<TWX, NS>::SMEM_BYTES));                                               \
+  B2F_CUDA_TRY(cudaFuncSetAttribute(cvb::costvol_bwd_tma<-1, TWX, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    cvb::Cfg<TWX, NS>::SMEM_BYTES))
+        B2F_BWD_ATTR(32, 2);
+        B2F_BWD_ATTR(32, 9);
+        B2F_BWD_ATTR(64, 3);
+#undef B2F_BWD_ATTR
         attr_dev = dev;
       }
-      // up to ~3 CTAs per SM in total: one CTA per SM with all nine slabs in flight (path 13 / 14 force either)
-      const bool deep = path == 13 || (path != 14 && ctas <= (int64_t)num_sms() * 3);
       const int role0 = gradFrames[0] ? 0 : 1;
       const int bdbg = (path >= 8 && path <= 10) ? path - 7 : 0;   // 8: no arithmetic, 9: no stores, 10: neither
-      dim3 grid((W + cvb::TW - 1) / cvb::TW, (H + cvb::TH - 1) / cvb::TH, B * nchunk * nroles);
-#define B2F_BWD_LAUNCH(SG, NS)                                                                        \
-  cvb::costvol_bwd_tma<SG, NS><<<grid, cvb::THREADS, cvb::smem_bytes<NS>(), st>>>(                     \
+      dim3 grid((W + TWv - 1) / TWv, nty, B * nchunk * nroles);
+#define B2F_BWD_LAUNCH(SG, TWX, NS)                                                                        \
+  cvb::costvol_bwd_tma<SG, TWX, NS><<<grid, cvb::Cfg<TWX, NS>::THREADS, cvb::Cfg<TWX, NS>::SMEM_BYTES, st>>>( \
       tfrm, tref, tgo, tgo1, tgr, tgf, nroles, role0, nchunk, C, H, W, kdiv, bdbg)
-      if (deep) {
-        if (sgn > 0) B2F_BWD_LAUNCH(1, 9);
-        else B2F_BWD_LAUNCH(-1, 9);
+      if (variant == 1) {
+        if (sgn > 0) B2F_BWD_LAUNCH(1, 32, 9);
+        else B2F_BWD_LAUNCH(-1, 32, 9);
+      } else if (variant == 2) {
+        if (sgn > 0) B2F_BWD_LAUNCH(1, 64, 3);
+        else B2F_BWD_LAUNCH(-1, 64, 3);
       } else {
-        if (sgn > 0) B2F_BWD_LAUNCH(1, 2);
-        else B2F_BWD_LAUNCH(-1, 2);
+        if (sgn > 0) B2F_BWD_LAUNCH(1, 32, 2);
+        else B2F_BWD_LAUNCH(-1, 32, 2);
       }
 #undef B2F_BWD_LAUNCH
       B2F_CHECK_LAUNCH("costvol_bwd_tma");

@@ -66,7 +66,8 @@ B2F_API int b2f_release_scratch(void);             /* frees this thread's scratc
  * grid-size heuristics, with 32- (2, 3) or 16-column (4) forward tiles; 5 = 16-column tiles with
  * the channel range split over at least two work items per tile (the small-level path);
  * 6 / 7 = force / forbid the persistent software-pipelined forward (FFMA2 + TMA-store epilogue).
- * 13 / 14 = backward with nine slab buffers and one CTA per SM / with the double-buffered ring.
+ * 13 / 14 / 15 = backward with nine slab buffers and one CTA per SM / with the double-buffered ring
+ * and two CTAs per SM / with 64-column tiles and a 3-deep ring.
  * 8, 9, 10 are measurement aids that produce WRONG results: the tiled kernels without their
  * arithmetic (8), without their stores (9), or with neither (10) -- they time the TMA feed.       */
 B2F_API int b2f_debug_costvol_path(int mode);

@@ -148,7 +148,8 @@ def test_costvol_forward_generic(env, win, F, B, Cn, h, w, fwd):
 
 @pytest.mark.parametrize("B,Cn,h,w", [(2, 32, 16, 64), (1, 40, 13, 36), (2, 8, 7, 16), (1, 70, 9, 100), (1, 3, 5, 4)])
 @pytest.mark.parametrize("fwd", [True, False])
-@pytest.mark.parametrize("mode", [13, 14])   # 13: nine slab buffers, one CTA per SM; 14: double-buffered ring
+@pytest.mark.parametrize("mode", [13, 14, 15])   # 13: nine slab buffers, one CTA per SM; 14: double-buffered ring;
+                                                  # 15: 64-column tiles, eight compute warps, 3-deep ring
 def test_costvol_backward_tiled(env, mode, B, Cn, h, w, fwd):
     r = rng(4)
     frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(2)]
