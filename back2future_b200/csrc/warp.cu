@@ -141,7 +141,7 @@ constexpr int PIX_THREADS = 128; // one thread per pixel
 // Each 8-lane group handles two pixels of the row (x and x + 32): both grid values are fetched first,
 // then all eight tap loads are in flight together -- the kernel is latency-bound, not byte-bound.
 constexpr int VEC_PPT = 2;
-__global__ void __launch_bounds__(VEC_THREADS)
+__global__ void __launch_bounds__(VEC_THREADS, 4)
 warp_fwd_vec4(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
               int H, int W, int C, int Hg, int Wg) {
   const int xa = blockIdx.x * (VEC_THREADS / LPP) * VEC_PPT + (threadIdx.x >> 3);
