@@ -463,6 +463,41 @@ def test_smoothness_criterion(env, order, pen, B, h, w, alias, size_avg):
     assert o.rel_err(g, oc.backward(x, tgt)) < TOL
 
 
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("Cin,Ct,B,h,w", [(3, 3, 2, 9, 150), (1, 3, 1, 12, 17), (4, 2, 2, 6, 11)])
+def test_smoothness_generic_channel_counts(env, order, Cin, Ct, B, h, w):
+    """Channel counts other than the model's (2, 3) take the run-time-loop kernels; (2, 3) at sizes that span
+    several column strips / row blocks is covered by test_smoothness_criterion and the training-size test."""
+    r = rng(21)
+    x = r.standard_normal((B, Cin, h, w)).astype(np.float32)
+    tgt = (r.uniform(-2.1, 2.6, (B, Ct, h, w)) * 0.05).astype(np.float32)
+    # first-order with Cin != Ct and alias = 1 is the Q9 aliased variant; the oracle implements it for any Cin, Ct
+    for alias in ((1, 0) if order == 1 else (0,)):
+        loss, g = _run_smooth(env, order, 1, 0, alias, x, tgt)
+        oc = o.SmoothnessOracle(order, o.make_penalty(1), size_average=False, alias=bool(alias))
+        ref = oc.forward(x, tgt)
+        assert abs(loss - ref) < TOL * abs(ref) + 1e-12
+        assert o.rel_err(g, oc.backward(x, tgt)) < TOL
+
+
+@pytest.mark.parametrize("gt", [0, 1])
+@pytest.mark.parametrize("Cn", [1, 5])
+def test_ob_criterion_generic_channel_counts(env, gt, Cn):
+    """C != 3 takes the channel-by-channel kernel path (the model always has C = 3)."""
+    r = rng(22)
+    B, h, w = 2, 11, 150
+    flow, bflow, occ, w1, w2, tgt = _ob_inputs(r, B, Cn, h, w, 0.4)
+    kw = dict(gradient_terms=gt, penalty=1, penalty_eps=0.05, penalty_out=1.0, alpha=0.5, beta=0.8, gamma=1.2,
+              pwc_flow_scaling=10.0, past_flow=1, grad_check=0, size_average=0)
+    loss, g_occ, g1, g2 = _run_ob(env, kw, flow, bflow, occ, w1, w2, tgt)
+    oc = o.OBCriterionOracle(bool(gt), o.make_penalty(1), past_flow=True, pwc_flow_scaling=10.0, size_average=False,
+                             alpha=0.5, beta=0.8, gamma=1.2)
+    ref_loss = oc.forward(flow, bflow, occ, [w1, w2], tgt)
+    ro, rw = oc.backward(flow, bflow, occ, [w1, w2], tgt)
+    assert abs(loss - ref_loss) < TOL * abs(ref_loss)
+    assert o.rel_err(g_occ, ro) < TOL and o.rel_err(g1, rw[0]) < TOL and o.rel_err(g2, rw[1]) < TOL
+
+
 def test_smoothness_alias_differs_from_intended_and_same_channel_case(env):
     r = rng(13)
     x = r.standard_normal((2, 2, 8, 10)).astype(np.float32)
