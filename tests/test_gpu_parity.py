@@ -593,3 +593,75 @@ def test_nn_costvol_into_joined_buffer_and_clear_state(env):
         f_mod.forward([torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4)])   # CPU tensors: no fallback
     with pytest.raises(AssertionError):
         f_mod.forward([env.t(ref), env.t(fut[:, :8])])                        # "input sizes mismatch"
+
+
+# ---------------------------------------------------------------------------------------
+# committed golden fixture (tests/golden/hotpath_golden.npz: crops of the reference's sample frames,
+# expected values from the float64 oracle -- see tests/golden/make_golden.py for what that pins)
+# ---------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def golden():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_golden_costvol(env, golden):
+    G = golden
+    for name, frm, sl, fwd in (("cv_fwd", "feat_fut", slice(0, 81), True), ("cv_bwd", "feat_past", slice(81, 162), False)):
+        frames = [G["feat_ref"], G[frm]]
+        assert o.rel_err(_costvol_fwd(env, frames, 9, fwd, wide=True), G[name + "_out"]) < TOL
+        gr, gf = _costvol_bwd(env, frames, G["cv_gradout_joined"], sl, 9, fwd)
+        assert o.rel_err(gr, G[name + "_gradref"]) < TOL and o.rel_err(gf, G[name + "_gradframe"]) < TOL
+
+
+def test_golden_warp(env, golden):
+    G = golden
+    img = np.ascontiguousarray(G["frame_fut"].transpose(0, 2, 3, 1))
+    out, gi, gg = _warp(env, img, G["grid_fut"], G["warp_gradout3"])
+    assert o.rel_err(out, G["warp_img_fut"]) < TOL
+    assert o.rel_err(gi, G["warp_img_fut_gradimg"]) < TOL and o.rel_err(gg, G["warp_img_fut_gradgrid"]) < TOL
+    out, _, _ = _warp(env, np.ascontiguousarray(G["frame_past"].transpose(0, 2, 3, 1)), G["grid_past"], G["warp_gradout3"])
+    assert o.rel_err(out, G["warp_img_past"]) < TOL
+    ft = np.ascontiguousarray(G["feat_fut_full"].transpose(0, 2, 3, 1))
+    out, gi, gg = _warp(env, ft, G["grid_fut"], G["warp_gradout8"])
+    assert o.rel_err(out, G["warp_feat_fut"]) < TOL
+    assert o.rel_err(gi, G["warp_feat_fut_gradimg"]) < TOL and o.rel_err(gg, G["warp_feat_fut_gradgrid"]) < TOL
+
+
+def test_golden_criterions(env, golden):
+    torch = env.torch_
+    G = golden
+    flow, bflow, occ, ref = G["flow"], G["bflow"], G["occ"], G["frame_ref"]
+    wp, wf = G["crit_warp_past"], G["crit_warp_fut"]
+    for name, gt, pf, alpha in (("obcc", 0, 0, 1.0), ("obgcc", 1, 1, 0.0)):
+        kw = dict(gradient_terms=gt, penalty=1, penalty_eps=0.05, penalty_out=1.0, alpha=alpha, beta=1.0, gamma=1.0,
+                  pwc_flow_scaling=20.0, past_flow=pf, grad_check=0, size_average=0)
+        loss, g_occ, g1, g2 = _run_ob(env, kw, flow, bflow, occ, wp, wf, ref)
+        assert abs(loss - G[name + "_loss"]) < TOL * abs(G[name + "_loss"])
+        assert o.rel_err(g_occ, G[name + "_gradocc"]) < TOL
+        assert o.rel_err(g1, G[name + "_gradwarp_past"]) < TOL and o.rel_err(g2, G[name + "_gradwarp_fut"]) < TOL
+        # hard masks: out-of-image pixels carry exactly zero warped-frame gradient, in-image ones (with a non-zero
+        # expected gradient) a non-zero one
+        m_f = G["mask_fut"]
+        m_p = G["mask_past_bflow"] if pf else o.out_of_image_mask(flow, -1, 20.0)
+        assert np.all(g2[np.broadcast_to(~m_f[:, None], g2.shape)] == 0)
+        assert np.all(g1[np.broadcast_to(~m_p[:, None], g1.shape)] == 0)
+        assert np.array_equal(np.any(g2 != 0, axis=1), np.any(G[name + "_gradwarp_fut"] != 0, axis=1))
+    for name, order, inp, pen, alias in (("smooth1_flow", 1, flow, 1, 1), ("smooth2_flow", 2, flow, 1, 1),
+                                         ("smooth1_occ", 1, occ, 0, 1), ("smooth1_flow_intended", 1, flow, 1, 0)):
+        loss, g = _run_smooth(env, order, pen, 0, alias, inp, ref)
+        assert abs(loss - G[name + "_loss"]) < TOL * abs(G[name + "_loss"])
+        assert o.rel_err(g, G[name + "_grad"]) < TOL
+    tf, tb, to = env.t(flow), env.t(bflow), env.t(occ)
+    gf, gb, g = torch.empty_like(tf), torch.empty_like(tb), torch.empty_like(to)
+    host = C.c_double(0)
+    env.check(env.lib.b2f_constvel_criterion(env.p(tf), env.p(tb), 2, 2, 20, 40, 1, env.p(gf), env.p(gb), None,
+                                             C.byref(host), env.stream()))
+    assert abs(host.value - G["constvel_loss"]) < TOL * abs(G["constvel_loss"])
+    assert o.rel_err(gf.cpu().numpy(), G["constvel_gradf"]) < TOL and o.rel_err(gb.cpu().numpy(), G["constvel_gradb"]) < TOL
+    env.check(env.lib.b2f_occprior_criterion(env.p(to), 2, 2, 20, 40, 1.0, 0, env.p(g), None, C.byref(host), env.stream()))
+    assert abs(host.value - G["occprior_loss"]) < TOL * abs(G["occprior_loss"])
+    assert o.rel_err(g.cpu().numpy(), G["occprior_grad"]) < TOL
