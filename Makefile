@@ -9,6 +9,9 @@ SRCS      := $(CSRC)/api.cu $(CSRC)/costvol.cu $(CSRC)/warp.cu $(CSRC)/criterion
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := back2future_b200/libb2f_cuda.so
 ORACLE    := oracle/c/libb2f_cpu.so
+# the reference's own sampler (test-only parity pin), compiled from where it lies; only when the reference is mounted
+REFROOT   ?= /root/reference
+REFLIB    := oracle/_ref/libstn_ref.so
 
 all: $(LIB) $(ORACLE)
 
@@ -22,7 +25,16 @@ $(LIB): $(OBJS)
 $(ORACLE): oracle/c/b2f_cpu.c
 	$(HOSTCC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -fvisibility=hidden -o $@ $< -lm
 
+# Reference sampler: unmodified extras/stnbhwd/{utils.c,BilinearSamplerBHWD.cu} against the stand-in Torch7
+# headers in oracle/ref_shim (the reference's own CMake build wants luarocks + TH/THC/luaT and -arch=sm_30).
+$(REFLIB): oracle/ref_shim/stn_ref.cu $(wildcard oracle/ref_shim/*.h)
+	@mkdir -p oracle/_ref
+	$(NVCC) -O2 -std=c++17 $(ARCH) -Xcompiler -fPIC,-fvisibility=hidden -diag-suppress 177 -shared \
+	    -I oracle/ref_shim -I $(REFROOT)/extras/stnbhwd -o $@ $<
+
+ref: $(REFLIB)
+
 clean:
 	rm -rf $(OBJDIR) $(LIB) $(ORACLE)
 
-.PHONY: all clean
+.PHONY: all clean ref

@@ -5,10 +5,13 @@ path BASELINE.json's north_star names.  Only ``tests/``, ``__graft_entry__.smoke
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product
 (``back2future_b200``) never does and fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference (Lua/Torch7 + a luarocks C/CUDA package) cannot be executed
-in the build container (no LuaJIT, no Torch7, no network) and its own tests hold no golden
-vector, known-answer value or fixture for this path.  What pins
-this oracle instead:
+PARITY: the sampler (warp_forward / warp_backward, rows a4/a5) is PINNED to the reference itself --
+the reference's own CUDA sampler, compiled unmodified into oracle/_ref/libstn_ref.so, produced
+tests/golden/ref_sampler_golden.npz on a B200 and this module reproduces it to 1e-6
+(tests/test_golden.py, tests/test_ref_sampler.py).  Everything else here (cost volume, criterions:
+Lua over Torch7 tensor methods) is PARITY UNPINNED: the reference cannot be executed in the build
+container (no LuaJIT, no Torch7, no network) and its own tests hold no golden vector, known-answer
+value or fixture for those rows.  What pins those parts instead:
   * two independent restatements per module where that is possible (a literal transcription
     of the Lua loops next to a closed form) cross-checked in tests/test_oracle.py;
   * finite-difference gradient checks in the spirit of the reference's commented-out

@@ -126,3 +126,61 @@ def test_c_restatement_reproduces_golden(G, cpu_lib):
     gi, gg = np.zeros_like(img), np.empty_like(grid)
     assert cpu_lib.b2fcpu_warp_backward(_fp(img), _fp(grid), _fp(go), _fp(gi), _fp(gg), B, H, W, Cn, H, W) == 0
     assert o.rel_err(gi, G["warp_img_fut_gradimg"]) < 1e-5 and o.rel_err(gg, G["warp_img_fut_gradgrid"]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------
+# ref_sampler_golden.npz: outputs of the REFERENCE'S OWN CUDA sampler (oracle/_ref/libstn_ref.so =
+# extras/stnbhwd/BilinearSamplerBHWD.cu compiled unmodified, run on a B200 by
+# tests/golden/make_ref_sampler_golden.py).  These pin the sampler oracles to the reference itself.
+# ---------------------------------------------------------------------------------------
+
+REF_PATH = os.path.join(ROOT, "tests", "golden", "ref_sampler_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def RG():
+    with np.load(REF_PATH) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _ref_cases(RG):
+    return sorted({k.split("__")[0] for k in RG})
+
+
+def test_reference_sampler_fixture_covers_the_delicate_cases(RG):
+    names = _ref_cases(RG)
+    assert names == ["far_out", "feat32", "feat96", "img3_sigma4", "img3_sub", "one_pixel", "smallgrid_int"]
+    for n in names:
+        img, grid, out = RG[n + "__img"], RG[n + "__grid"], RG[n + "__out"]
+        assert out.shape == grid.shape[:3] + img.shape[3:] and out.dtype == np.float32
+        assert np.isfinite(out).all() and np.isfinite(RG[n + "__gradimg"]).all() and np.isfinite(RG[n + "__gradgrid"]).all()
+    g = RG["far_out__grid"]
+    x = np.arange(g.shape[2], dtype=np.float32)[None, None, :] + g[..., 0]
+    assert (x < 0).any() and (x > g.shape[2] - 1).any()          # the clamp is exercised on both sides
+    assert (RG["smallgrid_int__grid"] == np.round(RG["smallgrid_int__grid"])).mean() > 0.9   # exact-integer coordinates
+
+
+def test_numpy_sampler_oracle_matches_the_reference_kernel(RG):
+    for n in _ref_cases(RG):
+        img, grid, go = RG[n + "__img"], RG[n + "__grid"], RG[n + "__gradout"]
+        assert o.rel_err(o.warp_forward(img, grid), RG[n + "__out"]) < 1e-6, n
+        gi, gg = o.warp_backward(img, grid, go)
+        assert o.rel_err(gg, RG[n + "__gradgrid"]) < 2e-6, n
+        assert o.rel_err(gi, RG[n + "__gradimg"]) < 1e-5, n            # float atomics in the reference
+        _, gg_only = o.warp_backward(img, grid, go, only_grid=True)
+        assert np.array_equal(gg_only, gg), n
+    n = "img3_sigma4"                                                  # the independent scalar restatement too
+    assert o.rel_err(o.warp_forward_loops(RG[n + "__img"], RG[n + "__grid"]), RG[n + "__out"]) < 1e-6
+
+
+def test_c_sampler_oracle_matches_the_reference_kernel(RG, cpu_lib):
+    for n in _ref_cases(RG):
+        img, grid, go = (np.ascontiguousarray(RG[n + k]) for k in ("__img", "__grid", "__gradout"))
+        B, H, W, Cn = img.shape
+        _, Hg, Wg, _ = grid.shape
+        out = np.empty((B, Hg, Wg, Cn), np.float32)
+        assert cpu_lib.b2fcpu_warp_forward(_fp(img), _fp(grid), _fp(out), B, H, W, Cn, Hg, Wg) == 0
+        assert o.rel_err(out, RG[n + "__out"]) < 1e-6, n
+        gi, gg = np.zeros_like(img), np.empty_like(grid)
+        assert cpu_lib.b2fcpu_warp_backward(_fp(img), _fp(grid), _fp(go), _fp(gi), _fp(gg), B, H, W, Cn, Hg, Wg) == 0
+        assert o.rel_err(gg, RG[n + "__gradgrid"]) < 2e-5 and o.rel_err(gi, RG[n + "__gradimg"]) < 1e-5, n
