@@ -849,6 +849,78 @@ occprior_kernel(const float* __restrict__ occ, float* __restrict__ grad, int B, 
   finish_loss(loss, lo);
 }
 
+// Model shapes (two flow / occlusion channels, hw % 4 == 0, 16-byte aligned planes): four pixels per thread,
+// every plane read and written with 128-bit accesses and all loads of the four pixels issued before the first
+// use.  The scalar kernels above keep 4 bytes per load in flight per thread, far too little for the ~6 MB the
+// HBM system needs in flight (1.7 TB/s measured); this form is what a streaming kernel has to look like here.
+__device__ __forceinline__ float4 ldg_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+__global__ void __launch_bounds__(kThreads)
+constvel_c2_kernel(const float* __restrict__ f, const float* __restrict__ bb, float* __restrict__ gf,
+                   float* __restrict__ gb, int64_t hw, float gnorm, LossOut lo) {
+  const int b = blockIdx.y;
+  const float* f0 = f + (int64_t)b * 2 * hw;
+  const float* b0 = bb + (int64_t)b * 2 * hw;
+  float loss = 0.f;
+  const int64_t nq = hw >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nq; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t o = q << 2;
+    const float4 fu = ldg_stream4(f0 + o), fv = ldg_stream4(f0 + hw + o);
+    const float4 bu = ldg_stream4(b0 + o), bv = ldg_stream4(b0 + hw + o);
+    const float du[4] = {fu.x - bu.x, fu.y - bu.y, fu.z - bu.z, fu.w - bu.w};
+    const float dv[4] = {fv.x - bv.x, fv.y - bv.y, fv.z - bv.z, fv.w - bv.w};
+    float gu[4], gv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s = 0.f;            // same accumulation order as the channel loop of the generic kernel
+      s += du[i] * du[i];
+      s += dv[i] * dv[i];
+      const float nrm = sqrtf(s);
+      loss += nrm;
+      const float den = nrm + 1e-12f;
+      gu[i] = (du[i] / den) * gnorm;
+      gv[i] = (dv[i] / den) * gnorm;
+    }
+    if (gf) {
+      stg_stream4(gf + (int64_t)b * 2 * hw + o, make_float4(gu[0], gu[1], gu[2], gu[3]));
+      stg_stream4(gf + (int64_t)b * 2 * hw + hw + o, make_float4(gv[0], gv[1], gv[2], gv[3]));
+    }
+    if (gb) {   // (b - f) / den = -((f - b) / den) exactly
+      stg_stream4(gb + (int64_t)b * 2 * hw + o, make_float4(-gu[0], -gu[1], -gu[2], -gu[3]));
+      stg_stream4(gb + (int64_t)b * 2 * hw + hw + o, make_float4(-gv[0], -gv[1], -gv[2], -gv[3]));
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+__global__ void __launch_bounds__(kThreads)
+occprior_c2_kernel(const float* __restrict__ occ, float* __restrict__ grad, int64_t hw, float penalty, float norm,
+                   LossOut lo) {
+  const int b = blockIdx.y;
+  const float* o0 = occ + (int64_t)b * 2 * hw;
+  float loss = 0.f;
+  const int64_t nq = hw >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < nq; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t o = q << 2;
+    const float4 a = ldg_stream4(o0 + o), c = ldg_stream4(o0 + hw + o);
+    loss += (1.f - a.x * c.x) * penalty;
+    loss += (1.f - a.y * c.y) * penalty;
+    loss += (1.f - a.z * c.z) * penalty;
+    loss += (1.f - a.w * c.w) * penalty;
+    if (grad) {
+      float* g0 = grad + (int64_t)b * 2 * hw + o;
+      stg_stream4(g0, make_float4((1.f - c.x) * penalty * norm, (1.f - c.y) * penalty * norm,
+                                  (1.f - c.z) * penalty * norm, (1.f - c.w) * penalty * norm));
+      stg_stream4(g0 + hw, make_float4((1.f - a.x) * penalty * norm, (1.f - a.y) * penalty * norm,
+                                       (1.f - a.z) * penalty * norm, (1.f - a.w) * penalty * norm));
+    }
+  }
+  finish_loss(loss, lo);
+}
+
+bool planes16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // Number of row (or tile) slots in the grid when `cols` blocks exist per slot and there are `n` rows: about one
 // wave of resident blocks (16 x 128 threads per SM), at most 16 rows per block.
 int rows_per_grid(int64_t cols, int n) {
@@ -1025,14 +1097,16 @@ extern "C" int b2f_constvel_criterion(const float* f, const float* b, int B, int
   const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
   int blocks;
   dim3 grid;
-  int rc = grid_flat(B, hw, &grid, &blocks);
+  const bool vec = C == 2 && (hw & 3) == 0 && planes16(f) && planes16(b) && planes16(grad_f) && planes16(grad_b);
+  int rc = grid_flat(B, vec ? hw / 4 : hw, &grid, &blocks);
   if (rc) return rc;
   // forward: 1/nElement (ConstVelCriterion.lua:33, 41-43); backward: 1/npixels (:58, 69-72)  (Q11)
   const double scale = size_average ? 1.0 / ((double)npix * C) : 1.0;
   const float gnorm = size_average ? (float)(1.0 / (double)npix) : 1.f;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
-  constvel_kernel<<<grid, kThreads, 0, st>>>(f, b, grad_f, grad_b, B, C, hw, gnorm, ls.lo);
+  if (vec) constvel_c2_kernel<<<grid, kThreads, 0, st>>>(f, b, grad_f, grad_b, hw, gnorm, ls.lo);
+  else constvel_kernel<<<grid, kThreads, 0, st>>>(f, b, grad_f, grad_b, B, C, hw, gnorm, ls.lo);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);
@@ -1050,12 +1124,14 @@ extern "C" int b2f_occprior_criterion(const float* occ, int B, int C, int h, int
   const int64_t hw = (int64_t)h * w, npix = (int64_t)B * hw;
   int blocks;
   dim3 grid;
-  int rc = grid_flat(B, hw, &grid, &blocks);
+  const bool vec = C == 2 && (hw & 3) == 0 && planes16(occ) && planes16(grad);
+  int rc = grid_flat(B, vec ? hw / 4 : hw, &grid, &blocks);
   if (rc) return rc;
   const double scale = size_average ? 1.0 / (double)npix : 1.0;
   LossScratch ls;
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
-  occprior_kernel<<<grid, kThreads, 0, st>>>(occ, grad, B, C, hw, penalty, (float)scale, ls.lo);
+  if (vec) occprior_c2_kernel<<<grid, kThreads, 0, st>>>(occ, grad, hw, penalty, (float)scale, ls.lo);
+  else occprior_kernel<<<grid, kThreads, 0, st>>>(occ, grad, B, C, hw, penalty, (float)scale, ls.lo);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   rc = ls.end(loss_host);

@@ -406,6 +406,139 @@ warp_bwd_c3(const float* __restrict__ img, const float* __restrict__ grid, const
   reinterpret_cast<float2*>(ggrid)[row + xo] = r;
 }
 
+// ---- C == 3, lean forms (the model's image warps) ----------------------------------------------------------
+// The kernels above spend ~320 issue slots per pixel (4-way alignment branches, 64-bit index arithmetic, extent
+// checks, an unrolled copy loop): ncu shows them issue-bound at 0.6 IPC per scheduler with the memory system a
+// quarter busy, and a smooth flow field runs no faster than an i.i.d. one.  These forms do the same arithmetic
+// with 32-bit offsets and no divergent code: the six contiguous floats of a tap row are fetched as two (three
+// when the run starts at float 3 of a 16-byte chunk) aligned 128-bit loads and moved into place by a two-stage
+// predicated barrel shift; the scatter is the mirror image -- the six products are shifted into 16-byte chunks
+// padded with zeros and leave as two red.global.add.v4.f32 (plus one scalar when the run spills into a third
+// chunk): 4.5 reduction operations per pixel instead of 5-6, and adding +0 to a neighbour is exact.
+// Preconditions (checked by the dispatcher): 16-byte aligned tensors, B*H*W*3 a multiple of 4 (every chunk that
+// holds a valid float is then inside the tensor) and below 2^31, Wg a multiple of 4.
+struct Chunks9 {
+  float4 c0, c1;
+  float c2;
+};
+__device__ __forceinline__ Chunks9 load_chunks(const float* __restrict__ img, unsigned a, unsigned total) {
+  const unsigned base = a & ~3u;
+  const float4* p = reinterpret_cast<const float4*>(img + base);
+  Chunks9 r;
+  r.c0 = __ldg(p);
+  r.c1 = (base + 8u <= total) ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  r.c2 = ((a & 3u) == 3u && base + 12u <= total) ? __ldg(img + base + 8) : 0.f;
+  return r;
+}
+// v[i] = chunk floats [o + i], o = a & 3
+__device__ __forceinline__ void shift_out(const Chunks9& r, unsigned o, float (&v)[6]) {
+  const float c[9] = {r.c0.x, r.c0.y, r.c0.z, r.c0.w, r.c1.x, r.c1.y, r.c1.z, r.c1.w, r.c2};
+  const bool p2 = (o & 2u) != 0, p1 = (o & 1u) != 0;
+  float t[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = p2 ? c[i + 2] : c[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = p1 ? t[i + 1] : t[i];
+}
+// scatter-add v[0..6) at float offset a: the inverse shift, then aligned vector reductions
+__device__ __forceinline__ void red_chunks(float* __restrict__ gimg, unsigned a, unsigned total, const float (&v)[6]) {
+  const unsigned o = a & 3u, base = a & ~3u;
+  const bool p2 = (o & 2u) != 0, p1 = (o & 1u) != 0;
+  float u[7];
+  u[0] = p1 ? 0.f : v[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) u[i] = p1 ? v[i - 1] : v[i];
+  u[6] = p1 ? v[5] : 0.f;
+  float s[9];
+  s[0] = p2 ? 0.f : u[0];
+  s[1] = p2 ? 0.f : u[1];
+#pragma unroll
+  for (int i = 2; i < 7; ++i) s[i] = p2 ? u[i - 2] : u[i];
+  s[7] = p2 ? u[5] : 0.f;
+  s[8] = p2 ? u[6] : 0.f;
+  float* p = gimg + base;
+  red_add_v4(p, s[0], s[1], s[2], s[3]);
+  if (base + 8u <= total) red_add_v4(p + 4, s[4], s[5], s[6], s[7]);
+  if (o == 3u && base + 12u <= total) red_add(p + 8, s[8]);
+}
+
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_fwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
+                 int H, int W, int Hg, int Wg, unsigned total) {
+  __shared__ __align__(16) float s_out[PIX_THREADS * 3];
+  const int x0 = blockIdx.x * PIX_THREADS;
+  const int xo = x0 + threadIdx.x;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const unsigned row = ((unsigned)b * Hg + yo) * Wg;
+  if (xo < Wg) {
+    const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + row + xo);
+    const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+    const unsigned a = (((unsigned)b * H + g.yi) * W + g.xi) * 3u;
+    const unsigned ab = g.bin ? a + (unsigned)W * 3u : a;
+    const Chunks9 rt = load_chunks(img, a, total);
+    const Chunks9 rb = load_chunks(img, ab, total);
+    const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+    const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+    float top[6], bot[6];
+    shift_out(rt, a & 3u, top);
+    shift_out(rb, ab & 3u, bot);
+    const bool both = g.rin && g.bin;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      s_out[threadIdx.x * 3 + c] = w_tl * top[c] + w_tr * (g.rin ? top[3 + c] : 0.f) +
+                                   w_bl * (g.bin ? bot[c] : 0.f) + w_br * (both ? bot[3 + c] : 0.f);
+  }
+  __syncthreads();
+  // 128 x 3 floats leave as 96 x 16 bytes (Wg % 4 == 0: the row segment starts and ends on a 16-byte boundary)
+  const int nq = (min(PIX_THREADS, Wg - x0) * 3) >> 2;
+  if ((int)threadIdx.x < nq)
+    __stcs(reinterpret_cast<float4*>(out + (size_t)(row + x0) * 3) + threadIdx.x,
+           reinterpret_cast<const float4*>(s_out)[threadIdx.x]);
+}
+
+template <bool ONLY_GRID>
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_bwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
+                 float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W, int Hg, int Wg, unsigned total) {
+  const int xo = blockIdx.x * PIX_THREADS + threadIdx.x;
+  if (xo >= Wg) return;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const unsigned pix = ((unsigned)b * Hg + yo) * Wg + xo;
+  const float2 gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+  const float* gp = gout + (size_t)pix * 3;
+  const float v0 = __ldcs(gp), v1 = __ldcs(gp + 1), v2 = __ldcs(gp + 2);
+  const Geo g = geometry(gxy.x, gxy.y, xo, yo, H, W);
+  const unsigned a = (((unsigned)b * H + g.yi) * W + g.xi) * 3u;
+  const unsigned ab = g.bin ? a + (unsigned)W * 3u : a;
+  const Chunks9 rt = load_chunks(img, a, total);
+  const Chunks9 rb = load_chunks(img, ab, total);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  float top[6], bot[6];
+  shift_out(rt, a & 3u, top);
+  shift_out(rb, ab & 3u, bot);
+  const float d_tl = top[0] * v0 + top[1] * v1 + top[2] * v2;
+  const float d_tr = g.rin ? top[3] * v0 + top[4] * v1 + top[5] * v2 : 0.f;
+  const float d_bl = g.bin ? bot[0] * v0 + bot[1] * v1 + bot[2] * v2 : 0.f;
+  const float d_br = (g.rin && g.bin) ? bot[3] * v0 + bot[4] * v1 + bot[5] * v2 : 0.f;
+  float2 r;
+  r.x = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
+  r.y = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
+  reinterpret_cast<float2*>(ggrid)[pix] = r;
+  if (!ONLY_GRID) {
+    // a tap outside the image receives nothing (BilinearSamplerBHWD.cu:236-262): its products are replaced by
+    // zeros, which the padded reductions add harmlessly to the floats that happen to follow
+    const float tr0 = g.rin ? w_tr * v0 : 0.f, tr1 = g.rin ? w_tr * v1 : 0.f, tr2 = g.rin ? w_tr * v2 : 0.f;
+    const float vt[6] = {w_tl * v0, w_tl * v1, w_tl * v2, tr0, tr1, tr2};
+    red_chunks(gimg, a, total, vt);
+    if (g.bin) {
+      const float br0 = g.rin ? w_br * v0 : 0.f, br1 = g.rin ? w_br * v1 : 0.f, br2 = g.rin ? w_br * v2 : 0.f;
+      const float vb[6] = {w_bl * v0, w_bl * v1, w_bl * v2, br0, br1, br2};
+      red_chunks(gimg, ab, total, vb);
+    }
+  }
+}
+
 // ---- backward, any C: one thread per pixel --------------------------------------------
 template <bool ONLY_GRID>
 __global__ void __launch_bounds__(PIX_THREADS)
@@ -459,6 +592,13 @@ int vec_rows_grid(int Wg, int Hg, int B) {
   return (int)gy;
 }
 
+// preconditions of the lean C = 3 kernels (see there); B2F_WARP_C3_LEGACY=1 forces the older kernels (experiments)
+bool c3_lean_ok(int B, int H, int W, int Hg, int Wg) {
+  static const bool legacy = [] { const char* e = getenv("B2F_WARP_C3_LEGACY"); return e && e[0] == '1'; }();
+  const size_t total = (size_t)B * H * W * 3, gpix = (size_t)B * Hg * Wg;
+  return !legacy && (total & 3u) == 0 && total < (1ull << 31) && gpix * 3 < (1ull << 31) && (Wg & 3) == 0;
+}
+
 int check_args(const float* img, const float* grid, int B, int H, int W, int C, int Hg, int Wg) {
   if (!img || !grid) return fail(B2F_EINVAL, "warp: NULL img/grid");
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || Hg <= 0 || Wg <= 0)
@@ -488,8 +628,13 @@ extern "C" int b2f_warp_bhwd_forward(const float* img, const float* grid, float*
     B2F_CHECK_LAUNCH("warp_fwd_vec4");
   } else if (C == 3) {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
-    warp_fwd_c3<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg, img + (size_t)B * H * W * 3);
-    B2F_CHECK_LAUNCH("warp_fwd_c3");
+    if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && aligned16(out)) {
+      warp_fwd_c3_lean<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg, (unsigned)((size_t)B * H * W * 3));
+      B2F_CHECK_LAUNCH("warp_fwd_c3_lean");
+    } else {
+      warp_fwd_c3<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg, img + (size_t)B * H * W * 3);
+      B2F_CHECK_LAUNCH("warp_fwd_c3");
+    }
   } else {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
     warp_fwd_scalar<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, C, Hg, Wg);
@@ -517,9 +662,15 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
   } else if (C == 3) {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
     const size_t elems = (size_t)B * H * W * 3;
-    if (only) warp_bwd_c3<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
-    else warp_bwd_c3<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
-    B2F_CHECK_LAUNCH("warp_bwd_c3");
+    if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && (only || aligned16(gradImg))) {
+      if (only) warp_bwd_c3_lean<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, (unsigned)elems);
+      else warp_bwd_c3_lean<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, (unsigned)elems);
+      B2F_CHECK_LAUNCH("warp_bwd_c3_lean");
+    } else {
+      if (only) warp_bwd_c3<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
+      else warp_bwd_c3<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, elems);
+      B2F_CHECK_LAUNCH("warp_bwd_c3");
+    }
   } else {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
     if (only) warp_bwd_scalar<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);

@@ -163,16 +163,20 @@ class Workload:
                 self.keep += [fptr, gptr]
                 self._mk.append(("f", "costvol_fwd L%d %s" % (l, "fut" if fwd else "past"), "costvol_fwd_L%d" % l,
                                  lambda s, a=(fptr, 2, B, Cn, h, w, 9, fwd, P(out), joined.stride(0)):
-                                 (lambda: lib.b2f_costvol_forward(*a, s)), fb, fl, None))
+                                 (lambda: lib.b2f_costvol_forward(*a, s)), fb, fl, None, ("cv", l, d)))
                 self._mk.append(("b", "costvol_bwd L%d %s" % (l, "fut" if fwd else "past"), "costvol_bwd_L%d" % l,
                                  lambda s, a=(fptr, 2, B, Cn, h, w, 9, fwd, P(go), gjoined.stride(0), gptr):
-                                 (lambda: lib.b2f_costvol_backward(*a, s)), bb, 2 * fl, None))
+                                 (lambda: lib.b2f_costvol_backward(*a, s)), bb, 2 * fl, None, ("cv", l, d)))
 
         # ---- warps ---------------------------------------------------------------------
-        warp_cfgs = [("feat L%d" % l, LEVEL_C[l], level_hw(l)) for l in (6, 5, 4, 3)]
-        warp_cfgs += [("img %dx%d" % (H_FULL >> k, W_FULL >> k), 3, (H_FULL >> k, W_FULL >> k)) for k in (4, 3, 2, 1, 0)]
-        for name, Cn, (h, w) in warp_cfgs:
-            for fr in ("past", "fut"):
+        # feature warp "L l" produces the warped features the level-l cost volume consumes (pwc.lua:402-408); image
+        # warp k belongs to pyramid level l = k + 3: it warps the image at the resolution of level l - 2 with the
+        # skip-upsampled flow of level l (pwc.lua:441-446)
+        warp_cfgs = [("feat L%d" % l, LEVEL_C[l], level_hw(l), ("fw", l)) for l in (6, 5, 4, 3)]
+        warp_cfgs += [("img %dx%d" % (H_FULL >> k, W_FULL >> k), 3, (H_FULL >> k, W_FULL >> k), ("iw", k + 3))
+                      for k in (4, 3, 2, 1, 0)]
+        for name, Cn, (h, w), wtag in warp_cfgs:
+            for d, fr in ((1, "past"), (0, "fut")):
                 img, grid = randn(B, h, w, Cn), randn(B, h, w, 2, scale=4.0)
                 out, go = empty(B, h, w, Cn), randn(B, h, w, Cn)
                 gimg, ggrid = empty(B, h, w, Cn), empty(B, h, w, 2)
@@ -185,23 +189,38 @@ class Workload:
                 kind = "warp_%s" % name.replace(" ", "_")
                 self._mk.append(("f", tag + " fwd", kind + "_fwd",
                                  lambda s, a=(P(img), P(grid), P(out), B, h, w, Cn, h, w):
-                                 (lambda: lib.b2f_warp_bhwd_forward(*a, s)), fb, 0, None))
+                                 (lambda: lib.b2f_warp_bhwd_forward(*a, s)), fb, 0, None, wtag + (d,)))
                 self._mk.append(("b", tag + " bwd", kind + "_bwd",
                                  lambda s, a=(P(img), P(grid), P(go), P(gimg), P(ggrid), B, h, w, Cn, h, w):
                                  (lambda: lib.b2f_warp_bhwd_backward(*a, s)), bb, 0,
-                                 (P(gimg), gimg.numel() * 4)))
+                                 (P(gimg), gimg.numel() * 4), wtag + (d,)))
+
+    @staticmethod
+    def network_order():
+        """(direction, tag) of every call of one step in the order the network's dataflow imposes
+        (models/pwc.lua:237-456): coarse to fine, per level the two cost volumes, then the level's image warps
+        (leaves of the loss) and the feature warps that feed the next finer level; backward is the mirror image."""
+        fwd = []
+        for l in (7, 6, 5, 4, 3):
+            fwd += [("cv", l, 0), ("cv", l, 1), ("iw", l, 0), ("iw", l, 1)]
+            if l > 3:
+                fwd += [("fw", l - 1, 0), ("fw", l - 1, 1)]
+        return [("f", t) for t in fwd] + [("b", t) for t in fwd[::-1]]
 
     def bind(self, stream_handle):
         s = C.c_void_p(stream_handle)
         lib = self.lib
         self.fwd_ops, self.bwd_ops = [], []
-        for which, name, kind, mk, nbytes, flops, zero in self._mk:
+        by_tag = {}
+        for which, name, kind, mk, nbytes, flops, zero, tag in self._mk:
             z = None
             if zero is not None:
                 z = (lambda a=zero: lib.b2f_zero_async(a[0], a[1], s))
             op = Op(name, kind, mk(s), nbytes, flops, z)
             (self.fwd_ops if which == "f" else self.bwd_ops).append(op)
-        self.ops = self.fwd_ops + self.bwd_ops[::-1]
+            by_tag[(which, tag)] = op
+        self.ops = [by_tag[k] for k in self.network_order()]
+        assert len(self.ops) == len(self._mk)
 
     def step(self, marks=None):
         """One pass: forward coarse-to-fine, then backward in reverse.  `marks` maps an op kind to a
@@ -228,67 +247,85 @@ class Workload:
 
     # -- CUDA graph of one step -------------------------------------------------------------
     def capture(self, streams):
-        """Capture one step as a CUDA graph over `streams` (the first one is the capture stream).
+        """Capture one step as a CUDA graph whose edges are the network's own data dependencies
+        (models/pwc.lua:237-456), over six streams (the first one is the capture stream):
 
-        Stages keep the forward-then-backward order of `step`; calls that are independent in the network run
-        concurrently inside a stage and are joined before the next one:
-          * the past and the future branch of a level (two CostVolMulti / sampler instances feeding one decoder);
-          * the image warps of the five output levels: each only needs its own level's flow (forward) or its
-            own level's loss gradient (backward) -- they are the leaves of the loss, one stage each way.
-        Replaying the graph also removes the per-call launch gaps that dominate the small pyramid levels."""
+          forward, per level l = 7..3:   [CV_l future || CV_l past] -> join (the level's decoder)
+                                          -> image warps of level l (side streams; leaves of the loss: nothing in the
+                                             forward waits for them) and, for l > 3, [feature warp future || past]
+                                             -> join -> CV_{l-1};
+          backward, l = 3..7:            image-warp backward of level l (needs only the loss gradient, so all five
+                                          levels start when the backward starts; level 3 on the main streams) must be
+                                          done before [CV_l backward future || past] -> [feature-warp L l backward].
+
+        So the L1/L2-bound C = 3 image warps of a level run under the shared-memory/FMA-bound cost volumes of the next
+        level, as a graph executor of the real network would schedule them.  The gradImg zero-fills (b2f_zero_async)
+        are issued at the start of the step on their own stream and joined before the first scatter."""
         torch, lib = self.torch, self.lib
-        groups = {}
-        order = []
-        for which, name, kind, mk, nbytes, flops, zero in self._mk:
-            key = (which, "warp_img" if kind.startswith("warp_img") else kind)
-            if key not in groups:
-                groups[key] = []
-                order.append(key)
-            groups[key].append((name, mk, zero))
-        fwd = [k for k in order if k[0] == "f"]
-        bwd = [k for k in order if k[0] == "b"][::-1]
-        main = streams[0]
-        handles = [C.c_void_p(st.cuda_stream) for st in streams]
-        stages = []
-        for key in fwd + bwd:
-            row = []
-            members = groups[key] if key[0] == "f" else groups[key][::-1]
-            for i, (name, mk, zero) in enumerate(members):
-                si = i % len(streams)
-                sh = handles[si]
-                z = _Zero(lib, zero) if zero is not None else None
-                row.append((si, z, mk(sh), name))
-            stages.append(row)
-        self.graph_stages = [[name for _, _, _, name in row] for row in stages]
+        assert len(streams) >= 6
+        M, S, I1, I2, Z = streams[0], streams[1], streams[2], streams[3], streams[5]
+        H = {st: C.c_void_p(st.cuda_stream) for st in streams}
+        ops = {}
+        for which, name, kind, mk, nbytes, flops, zero, tag in self._mk:
+            ops[(which, tag)] = (name, mk, zero)
+        sched = []
+
+        def call(which, tag, st):
+            name, mk, _ = ops[(which, tag)]
+            rc = mk(H[st])()
+            if rc:
+                raise RuntimeError("%s failed during capture: %d: %s" % (name, rc, lib.b2f_last_error().decode()))
+            sched.append((name, streams.index(st)))
+
+        def pair(which, kind, l):
+            S.wait_stream(M)
+            call(which, (kind, l, 0), M)
+            call(which, (kind, l, 1), S)
+            M.wait_stream(S)
+
         graph = torch.cuda.CUDAGraph()
-        zs = streams[-1]
-        with torch.cuda.graph(graph, stream=main):
-            # the zero-fill of every gradImg buffer (the scatter targets of the sampler backward; b2f_zero_async is
-            # a separate ABI call) is issued up front on its own stream: the HBM-write-bound memsets run under the
-            # forward kernels instead of in front of each backward kernel
-            zs.wait_stream(main)
-            zh = handles[len(streams) - 1]
-            for row in stages:
-                for si, z, call, name in row:
-                    if z is not None and z.zero_on(zh):
-                        raise RuntimeError("b2f_zero_async failed during capture")
-            zeroed = False
-            for row in stages:
-                used = sorted({si for si, _, _, _ in row if si != 0})
-                if not zeroed and any(z is not None for _, z, _, _ in row):
-                    main.wait_stream(zs)     # first stage that scatters: all buffers are clean
-                    zeroed = True
-                for si in used:
-                    streams[si].wait_stream(main)
-                for si, z, call, name in row:
-                    rc = call()
-                    if rc:
-                        raise RuntimeError("%s failed during capture: %d: %s" % (name, rc, lib.b2f_last_error().decode()))
-                for si in used:
-                    main.wait_stream(streams[si])
-            if not zeroed:
-                main.wait_stream(zs)
+        with torch.cuda.graph(graph, stream=M):
+            Z.wait_stream(M)
+            for which, name, kind, mk, nbytes, flops, zero, tag in self._mk:
+                if zero is not None and lib.b2f_zero_async(zero[0], zero[1], H[Z]):
+                    raise RuntimeError("b2f_zero_async failed during capture")
+            # ---- forward
+            for l in (7, 6, 5, 4, 3):
+                pair("f", "cv", l)
+                I1.wait_stream(M)
+                I2.wait_stream(M)
+                call("f", ("iw", l, 0), I1)
+                call("f", ("iw", l, 1), I2)
+                if l > 3:
+                    pair("f", "fw", l - 1)
+            M.wait_stream(I1)
+            M.wait_stream(I2)
+            M.wait_stream(Z)          # every scatter target is clean before the first backward kernel
+            # ---- backward
+            I1.wait_stream(M)
+            I2.wait_stream(M)
+            pair("b", "iw", 3)
+            done = {}
+            for l in (4, 5, 6, 7):
+                call("b", ("iw", l, 0), I1)
+                call("b", ("iw", l, 1), I2)
+                e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+                e1.record(I1)
+                e2.record(I2)
+                done[l] = (e1, e2)
+            for l in (3, 4, 5, 6, 7):
+                if l > 3:
+                    M.wait_event(done[l][0])
+                    M.wait_event(done[l][1])
+                pair("b", "cv", l)
+                if l < 7:
+                    pair("b", "fw", l)
+            M.wait_stream(I1)
+            M.wait_stream(I2)
+        self.graph_schedule = sched
+        assert len(sched) == len(self._mk)
         return graph
+
 
 def breakdown(torch, wl, iters=10):
     """Per-kernel device times (separate pass, events around every call; not part of `value`)."""
@@ -667,7 +704,7 @@ def main():
     marks = {k: [] for k in dominant}
     graph = None
     if not args.eager:
-        gstreams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        gstreams = [torch.cuda.Stream(device=dev) for _ in range(6)]
         graph = wl.capture(gstreams)
         for _ in range(3):
             graph.replay()
@@ -789,10 +826,11 @@ def main():
                              "buffer is reused" % (wl.total_bytes() / 1e9),
                        "alg_bytes_per_step": wl.total_bytes(),
                        "launch": "eager, one stream" if args.eager else
-                                 "one CUDA-graph replay per step; calls that are independent in the network (future / past "
-                                 "branch of a level; the image warps of the five output levels) run concurrently on up "
-                                 "to four streams inside a stage, stages in forward-then-backward order; the gradImg zero-fills "
-                                 "(b2f_zero_async) are issued at the start of the step on their own stream"},
+                                 "one CUDA-graph replay per step; the graph's edges are the network's data dependencies "
+                                 "(pwc.lua:237-456): per level [CV future || CV past] -> [feature warp future || past] -> next "
+                                 "level, the level's image warps (leaves of the loss) on side streams under the next level's "
+                                 "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
+                                 "start of the step on their own stream"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "criterions": crit,
         }

@@ -288,6 +288,8 @@ def _warp(env, img, grid, go, only_grid=False):
 @pytest.mark.parametrize("B,H,W,Cn,sigma", [
     (2, 14, 32, 128, 4.0), (2, 28, 64, 96, 4.0), (1, 17, 23, 32, 0.5), (2, 9, 11, 3, 4.0), (1, 33, 65, 3, 0.5),
     (1, 6, 7, 5, 2.0), (1, 5, 6, 1, 2.0), (1, 4, 5, 4, 30.0), (3, 1, 1, 8, 1.0), (1, 16, 16, 192, 3.0),
+    # C = 3 with W % 4 == 0: the lean image-warp kernels (barrel-shifted 128-bit loads / padded vector reductions)
+    (2, 12, 16, 3, 4.0), (1, 8, 4, 3, 6.0), (3, 5, 20, 3, 0.5), (1, 24, 64, 3, 30.0), (2, 33, 132, 3, 2.0), (1, 1, 4, 3, 1.0),
 ])
 def test_warp_forward_backward(env, B, H, W, Cn, sigma):
     r = rng(7)
@@ -316,6 +318,25 @@ def test_warp_grid_smaller_than_image_and_integer_coordinates(env):
     rgi, rgg = o.warp_backward(img, grid, go)
     assert o.rel_err(out, o.warp_forward(img, grid)) < TOL
     assert o.rel_err(gi, rgi) < TOL and o.rel_err(gg, rgg) < TOL
+
+
+def test_warp_c3_lean_grid_smaller_and_integer_coordinates(env):
+    """The lean C = 3 path with Hg,Wg != H,W, exact-integer and on-the-border coordinates, and the tensor's very
+    last pixel as a tap (its right / bottom neighbours lie past the end of the buffer and must not be touched)."""
+    r = rng(18)
+    img = r.standard_normal((2, 9, 12, 3)).astype(np.float32)
+    grid = np.round(r.standard_normal((2, 5, 8, 2)) * 3).astype(np.float32)
+    grid[0, 0, 0] = (11.0, 8.0)
+    grid[1, 4, 7] = (4.0, 4.0)        # (x, y) = (11, 8): the last pixel of the last batch item
+    grid[1, 4, 6] = (4.5, 3.5)
+    grid[0, 1, 1] = (-1e-8, 1e-8)
+    go = r.standard_normal((2, 5, 8, 3)).astype(np.float32)
+    out, gi, gg = _warp(env, img, grid, go)
+    rgi, rgg = o.warp_backward(img, grid, go)
+    assert o.rel_err(out, o.warp_forward(img, grid)) < TOL
+    assert o.rel_err(gi, rgi) < TOL and o.rel_err(gg, rgg) < TOL
+    _, gi2, gg2 = _warp(env, img, grid, go, only_grid=True)
+    assert gi2 is None and np.array_equal(gg2, gg)
 
 
 def test_warp_identity_kat(env):

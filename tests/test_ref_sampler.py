@@ -55,6 +55,7 @@ def _product(cuda_lib, img, grid, go, only_grid=False):
     (2, 9, 11, 3, 9, 11, 4.0), (1, 33, 65, 3, 33, 65, 0.5), (1, 6, 7, 5, 6, 7, 2.0), (1, 5, 6, 1, 5, 6, 2.0),
     (1, 4, 5, 4, 4, 5, 30.0), (3, 1, 1, 8, 1, 1, 1.0), (1, 16, 16, 192, 16, 16, 3.0), (2, 9, 12, 8, 5, 7, 3.0),
     (1, 56, 128, 64, 56, 128, 4.0), (2, 112, 256, 3, 112, 256, 4.0),
+    (2, 12, 16, 3, 12, 16, 4.0), (1, 24, 64, 3, 24, 64, 30.0), (2, 9, 12, 3, 5, 8, 3.0), (1, 1, 4, 3, 1, 4, 1.0),
 ])
 def test_reference_kernel_vs_oracle_vs_product(ref, cuda_lib, B, H, W, Cn, Hg, Wg, sigma):
     r = np.random.default_rng(11)
