@@ -596,6 +596,148 @@ smooth1_kernel(SmArgs a, LossOut lo, int rows) {
   finish_loss(loss, lo);
 }
 
+// Lean, software-pipelined form of smooth1_kernel for tensors whose flat indices fit 32 bits.  ncu put the kernel
+// above at 0.46 IPC per scheduler with the memory system 7 % busy: ~600 issue slots per pixel (64-bit index
+// arithmetic for every load, a lane-0-only path that the whole first warp steps through, per-thread recomputation
+// of row-uniform quantities) and one dependent round trip per row.  Here
+//   * thread 0 of a block is a halo column (x0 - 1): it only produces Gx for its right neighbour, so every thread
+//     runs the same code (127 output columns per block);
+//   * all offsets are 32-bit, row-uniform parts of the Q9 index arithmetic are hoisted out of the channel loops;
+//   * the 16 loads of row y + 1 (input neighbours + the raw target pairs of both edge weights) are issued before
+//     row y is evaluated, so two rows of loads are in flight per thread.
+// Same operands and operation order per value as smooth1_kernel.
+struct S1Raw {
+  float vr[2], vd[2];           // input right / down neighbours
+  float xa[3], xb[3];           // x-weight target pairs: |xb - xa| summed
+  float ya[3], yb[3];           // y-weight target pairs
+};
+
+template <bool ALIAS>
+__device__ __forceinline__ void s1_fetch(const SmArgs& a, const float* __restrict__ in0, unsigned b, int y, int x,
+                                         bool inimg, S1Raw& r) {
+  const unsigned w = a.w, h = a.h, hw = (unsigned)a.h * a.w;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r.xa[i] = r.xb[i] = r.ya[i] = r.yb[i] = 0.f;
+  r.vr[0] = r.vr[1] = r.vd[0] = r.vd[1] = 0.f;
+  if (!inimg) return;
+  const unsigned off = (unsigned)y * w + x;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    if ((unsigned)x < w - 1) r.vr[ch] = __ldg(in0 + ch * hw + off + 1);
+    if ((unsigned)y < h - 1) r.vd[ch] = __ldg(in0 + ch * hw + off + w);
+  }
+  if (ALIAS) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const unsigned t = (b * 2 + j) * h + y;          // row counter of the (B,Cin,h,w) view
+      const unsigned k = t * w + x;                      // flat index into the contiguous difference arrays
+      if ((int64_t)k < a.n_dx) {
+        const unsigned rowi = fast_div(k, w - 1, a.mul_w1, a.shr_w1);
+        const float* p = a.tgt + rowi * w + (k - rowi * (w - 1));
+        r.xa[j] = __ldg(p);
+        r.xb[j] = __ldg(p + 1);
+      }
+      if ((int64_t)k < a.n_dy) {
+        const unsigned t2 = fast_div(t, h - 1, a.mul_h1, a.shr_h1);
+        const float* p = a.tgt + t2 * hw + (t - t2 * (h - 1)) * w + x;
+        r.ya[j] = __ldg(p);
+        r.yb[j] = __ldg(p + w);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* p = a.tgt + (b * 3 + c) * hw + off;
+      const float v = __ldg(p);
+      r.xa[c] = r.ya[c] = v;
+      r.xb[c] = ((unsigned)x < w - 1) ? __ldg(p + 1) : v;     // |v - v| = 0: the term is absent
+      r.yb[c] = ((unsigned)y < h - 1) ? __ldg(p + w) : v;
+    }
+  }
+}
+template <bool ALIAS>
+__device__ __forceinline__ float s1_weight(const float (&lo)[3], const float (&hi)[3], float cs) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s += fabsf(hi[i] - lo[i]);     // the third alias term is |0 - 0|
+  return __expf(-cs * (s / (ALIAS ? 2.f : 3.f)));
+}
+
+constexpr int kS1Out = kThreads - 1;
+template <int PEN, bool ALIAS>
+__global__ void __launch_bounds__(kThreads)
+smooth1_lean_kernel(SmArgs a, LossOut lo, int rows) {
+  constexpr int CIN = 2;
+  __shared__ float s_gx[2][CIN][kThreads];
+  const int w = a.w, h = a.h;
+  const unsigned hw = (unsigned)h * w;
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x * kS1Out + tid - 1;
+  const unsigned b = blockIdx.z;
+  const int y0 = blockIdx.y * rows, y1 = min(h, y0 + rows);
+  const bool inimg = x >= 0 && x < w;
+  const bool outp = inimg && tid >= 1;
+  const bool need_g = a.grad != nullptr;
+  const float* in0 = a.in + (size_t)b * CIN * hw;
+  float loss = 0.f;
+  float gy_up[CIN] = {0.f, 0.f}, v_cur[CIN] = {0.f, 0.f};
+  S1Raw cur;
+  s1_fetch<ALIAS>(a, in0, b, y0, x, inimg, cur);
+  if (inimg) {
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) v_cur[ch] = __ldg(in0 + ch * hw + (unsigned)y0 * w + x);
+    if (need_g && y0 > 0) {   // Gy of the row above the strip, once per strip
+      S1Raw up;
+      s1_fetch<ALIAS>(a, in0, b, y0 - 1, x, true, up);
+      const float wyu = s1_weight<ALIAS>(up.ya, up.yb, a.cs);
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch)
+        gy_up[ch] = pen_der<PEN>(v_cur[ch] - __ldg(in0 + ch * hw + (unsigned)(y0 - 1) * w + x), a.eps2) * wyu;
+    }
+  }
+  for (int y = y0; y < y1; ++y) {
+    S1Raw nxt;
+    s1_fetch<ALIAS>(a, in0, b, y + 1, x, inimg && y + 1 < y1, nxt);   // in flight while row y is evaluated
+    float Gx[CIN] = {0.f, 0.f}, Gy[CIN] = {0.f, 0.f};
+    if (inimg) {
+      const float wx0 = s1_weight<ALIAS>(cur.xa, cur.xb, a.cs), wy0 = s1_weight<ALIAS>(cur.ya, cur.yb, a.cs);
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        const float v = v_cur[ch];
+        const float gx = (x < w - 1) ? cur.vr[ch] - v : 0.f;
+        const float gy = (y < h - 1) ? cur.vd[ch] - v : 0.f;
+        if (outp) loss += pen_apply<PEN>(gx, a.eps2) * wx0 + pen_apply<PEN>(gy, a.eps2) * wy0;
+        Gx[ch] = pen_der<PEN>(gx, a.eps2) * wx0;
+        Gy[ch] = pen_der<PEN>(gy, a.eps2) * wy0;
+      }
+    }
+    if (need_g) {   // uniform for the block
+      const int buf = y & 1;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) s_gx[buf][ch][tid] = Gx[ch];
+      __syncthreads();
+      if (outp) {
+#pragma unroll
+        for (int ch = 0; ch < CIN; ++ch) {
+          // -Gx + shift(Gx) - Gy + shift(Gy), in the reference's order (SmoothnessCriterion.lua:95-103)
+          float g = -Gx[ch];
+          if (x > 0) g += s_gx[buf][ch][tid - 1];
+          g -= Gy[ch];
+          if (y > 0) g += gy_up[ch];
+          a.grad[(size_t)b * CIN * hw + ch * hw + (unsigned)y * w + x] = g * a.norm;
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) {
+      gy_up[ch] = Gy[ch];
+      v_cur[ch] = cur.vd[ch];   // the down neighbour is the next row's centre value
+    }
+    cur = nxt;
+  }
+  finish_loss(loss, lo);
+}
+
 // order-2 weights (SecondOrderSmoothnessCriterion.lua:49-61) ------------------------------
 template <int CIN, int CT>
 __device__ __forceinline__ float w2_y(const SmArgs& a, int b, int y, int x) {
@@ -791,6 +933,155 @@ smooth2_kernel(SmArgs a, LossOut lo, int rows) {
   finish_loss(loss, lo);
 }
 
+// Lean, software-pipelined form of smooth2_kernel (32-bit offsets; see smooth1_lean_kernel).  Row r needs the target
+// at rows r-1, r, r+1 and at x-1, x+1, and the input at x-1, x+1 and rows r-1, r, r+1.  Centre columns slide
+// through three-row register windows (one new target row and one new input row per iteration); everything
+// iteration r + 1 needs from memory is requested before iteration r is evaluated.
+struct S2Raw {
+  float tc2[3];          // target, centre column, row r + 1
+  float tl[3], tr[3];    // target, row r, x - 1 / x + 1
+  float xl[2], xr[2];    // input, row r, x - 1 / x + 1
+  float in2[2];          // input, centre column, row r + 1
+};
+__device__ __forceinline__ void s2_fetch(const SmArgs& a, const float* __restrict__ in0, const float* __restrict__ t0,
+                                         int r, int x, bool on, bool own, S2Raw& q) {
+  const int w = a.w, h = a.h;
+  const unsigned hw = (unsigned)h * w;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) q.tc2[c] = q.tl[c] = q.tr[c] = 0.f;
+  q.xl[0] = q.xl[1] = q.xr[0] = q.xr[1] = q.in2[0] = q.in2[1] = 0.f;
+  if (!on) return;
+  const bool row_ok = r >= 0 && r < h;
+  const unsigned off = (unsigned)(row_ok ? r : 0) * w + x;
+  if (r + 1 >= 0 && r + 1 < h) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) q.tc2[c] = __ldg(t0 + c * hw + (unsigned)(r + 1) * w + x);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) q.in2[ch] = __ldg(in0 + ch * hw + (unsigned)(r + 1) * w + x);
+  }
+  if (row_ok && own) {
+    if (x >= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q.tl[c] = __ldg(t0 + c * hw + off - 1);
+    }
+    if (x >= 1 && x <= w - 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) q.tr[c] = __ldg(t0 + c * hw + off + 1);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        q.xl[ch] = __ldg(in0 + ch * hw + off - 1);
+        q.xr[ch] = __ldg(in0 + ch * hw + off + 1);
+      }
+    }
+  }
+}
+
+template <int PEN>
+__global__ void __launch_bounds__(kThreads)
+smooth2_lean_kernel(SmArgs a, LossOut lo, int rows) {
+  constexpr int CIN = 2, CT = 3;
+  __shared__ float s_gx[2][CIN][kThreads];
+  const int w = a.w, h = a.h;
+  const unsigned hw = (unsigned)h * w;
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x * kS2Out + tid - 1;
+  const unsigned b = blockIdx.z;
+  const int y0 = blockIdx.y * rows, y1 = min(h, y0 + rows);
+  const bool inimg = x >= 0 && x < w;
+  const bool outp = inimg && tid >= 1 && tid <= kS2Out;
+  const bool need_g = a.grad != nullptr;
+  const float* in0 = a.in + (size_t)b * CIN * hw;
+  const float* t0 = a.tgt + (size_t)b * CT * hw;
+  float loss = 0.f;
+  const int rbeg = need_g ? y0 - 1 : y0, rend = need_g ? y1 : y1 - 1;
+  // windows over rows r-1, r (r+1 arrives with the prefetched data) and over Gy(r-2), Gy(r-1)
+  float im1[CIN], i0[CIN], tm1[CT], tc[CT], gy2[CIN], gy1[CIN], xterm[CIN], gyc[CIN];
+#pragma unroll
+  for (int ch = 0; ch < CIN; ++ch) {
+    im1[ch] = i0[ch] = gy2[ch] = gy1[ch] = xterm[ch] = gyc[ch] = 0.f;
+    if (inimg) {
+      if (rbeg - 1 >= 0) im1[ch] = __ldg(in0 + ch * hw + (unsigned)(rbeg - 1) * w + x);
+      if (rbeg >= 0) i0[ch] = __ldg(in0 + ch * hw + (unsigned)rbeg * w + x);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    tm1[c] = tc[c] = 0.f;
+    if (inimg) {
+      if (rbeg - 1 >= 0) tm1[c] = __ldg(t0 + c * hw + (unsigned)(rbeg - 1) * w + x);
+      if (rbeg >= 0) tc[c] = __ldg(t0 + c * hw + (unsigned)rbeg * w + x);
+    }
+  }
+  S2Raw cur;
+  s2_fetch(a, in0, t0, rbeg, x, inimg, rbeg >= y0 && rbeg < y1, cur);
+  for (int r = rbeg; r <= rend; ++r) {
+    const bool own = r >= y0 && r < y1;   // a row of this block (loss, x terms); else only Gy is needed
+    S2Raw nxt;
+    s2_fetch(a, in0, t0, r + 1, x, inimg && r + 1 <= rend, r + 1 >= y0 && r + 1 < y1, nxt);
+    float Gx[CIN] = {0.f, 0.f};
+    if (inimg && r >= 0 && r < h) {
+      // edge weights (SecondOrderSmoothnessCriterion.lua:49-61), same accumulation order as w2_y / w2_x
+      float sy1 = 0.f, sy2 = 0.f, sx1 = 0.f, sx2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        if (r >= 1) sy1 += fabsf(tc[c] - tm1[c]);
+        if (r >= 1 && r <= h - 2) sy2 += fabsf(tc[c] - cur.tc2[c]);
+        if (x >= 1) sx1 += fabsf(tc[c] - cur.tl[c]);
+        if (x >= 1 && x <= w - 2) sx2 += fabsf(tc[c] - cur.tr[c]);
+      }
+      const float wy = __expf(-a.cs * (sy1 / (float)CT + sy2 / (float)CT));
+      const float wx = own ? __expf(-a.cs * (sx1 / (float)CT + sx2 / (float)CT)) : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) {
+        const float gy = (r >= 1 && r <= h - 2) ? (2.f * i0[ch] - im1[ch]) - cur.in2[ch] : 0.f;
+        gyc[ch] = (r >= 1 && r <= h - 2) ? pen_der<PEN>(gy, a.eps2) * wy : 0.f;
+        if (own) {
+          float gx = 0.f;
+          if (x >= 1 && x <= w - 2) {
+            gx = (2.f * i0[ch] - cur.xl[ch]) - cur.xr[ch];
+            Gx[ch] = pen_der<PEN>(gx, a.eps2) * wx;
+          }
+          if (outp) loss += pen_apply<PEN>(gx, a.eps2) * wx + pen_apply<PEN>(gy, a.eps2) * wy;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) gyc[ch] = 0.f;
+    }
+    if (need_g) {   // uniform for the block
+      const int buf = r & 1;
+#pragma unroll
+      for (int ch = 0; ch < CIN; ++ch) s_gx[buf][ch][tid] = Gx[ch];
+      __syncthreads();
+      if (outp) {
+#pragma unroll
+        for (int ch = 0; ch < CIN; ++ch) {
+          // row r-1 is complete: 2 Gy(r-1) - Gy(r) - Gy(r-2) + its x terms
+          if (r - 1 >= y0) {
+            const float g = ((2.f * gy1[ch] - gyc[ch]) - gy2[ch]) + xterm[ch];
+            a.grad[(size_t)b * CIN * hw + ch * hw + (unsigned)(r - 1) * w + x] = g * a.norm;
+          }
+          if (own) xterm[ch] = (2.f * Gx[ch] - s_gx[buf][ch][tid + 1]) - s_gx[buf][ch][tid - 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) {
+      gy2[ch] = gy1[ch];
+      gy1[ch] = gyc[ch];
+      im1[ch] = i0[ch];
+      i0[ch] = cur.in2[ch];
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      tm1[c] = tc[c];
+      tc[c] = cur.tc2[c];
+    }
+    cur = nxt;
+  }
+  finish_loss(loss, lo);
+}
+
 // =======================================================================================
 // ConstVelCriterion / OcclusionPriorCriterion
 // =======================================================================================
@@ -953,6 +1244,12 @@ int grid_flat(int B, int64_t hw, dim3* g, int* blocks) {
   return B2F_OK;
 }
 
+// B2F_SMOOTH_LEGACY=1 selects the older fast kernels (experiments / A-B timing)
+bool smooth_legacy() {
+  static const bool v = [] { const char* e = getenv("B2F_SMOOTH_LEGACY"); return e && e[0] == '1'; }();
+  return v;
+}
+
 bool valid_penalty(int p) { return p == B2F_PENALTY_QUADRATIC || p == B2F_PENALTY_L1 || p == B2F_PENALTY_LORENTZIAN; }
 
 template <bool GT>
@@ -1058,7 +1355,16 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
   if ((rc = ls.begin(blocks, scale, loss_dev, st))) return rc;
   const int pen = prm->penalty;
   const bool fixed = Cin == 2 && Ct == 3;   // the model's shapes: flow / occlusion map vs RGB target
-  if (prm->order == 1 && fixed) {
+  if (prm->order == 1 && fixed && a.small && !smooth_legacy()) {
+    const int rows = (h + (int)grid.y - 1) / (int)grid.y;   // consecutive rows per block (measured flat from 4 to 14)
+    const dim3 g1((w + kS1Out - 1) / kS1Out, (h + rows - 1) / rows, grid.z);
+#define B2F_S1(P) do { if (a.alias) smooth1_lean_kernel<P, true><<<g1, kThreads, 0, st>>>(a, ls.lo, rows); \
+                       else smooth1_lean_kernel<P, false><<<g1, kThreads, 0, st>>>(a, ls.lo, rows); } while (0)
+    if (pen == B2F_PENALTY_QUADRATIC) B2F_S1(B2F_PENALTY_QUADRATIC);
+    else if (pen == B2F_PENALTY_L1) B2F_S1(B2F_PENALTY_L1);
+    else B2F_S1(B2F_PENALTY_LORENTZIAN);
+#undef B2F_S1
+  } else if (prm->order == 1 && fixed) {
     const int rows = (h + (int)grid.y - 1) / (int)grid.y;   // consecutive rows per block
     const dim3 g1(grid.x, (h + rows - 1) / rows, grid.z);
     if (pen == B2F_PENALTY_QUADRATIC) smooth1_kernel<B2F_PENALTY_QUADRATIC><<<g1, kThreads, 0, st>>>(a, ls.lo, rows);
@@ -1069,7 +1375,13 @@ extern "C" int b2f_smoothness_criterion(const b2f_smooth_params* prm, const floa
     else if (pen == B2F_PENALTY_L1) smooth1_generic_kernel<B2F_PENALTY_L1, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
     else smooth1_generic_kernel<B2F_PENALTY_LORENTZIAN, 0, 0><<<grid, kThreads, 0, st>>>(a, ls.lo);
   } else {
-    if (fixed) {
+    if (fixed && a.small && !smooth_legacy()) {
+      const int rows = std::max(4, (h + (int)grid.y - 1) / (int)grid.y);   // consecutive rows per block (2 extra per strip)
+      const dim3 g2((w + kS2Out - 1) / kS2Out, (h + rows - 1) / rows, grid.z);
+      if (pen == B2F_PENALTY_QUADRATIC) smooth2_lean_kernel<B2F_PENALTY_QUADRATIC><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+      else if (pen == B2F_PENALTY_L1) smooth2_lean_kernel<B2F_PENALTY_L1><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+      else smooth2_lean_kernel<B2F_PENALTY_LORENTZIAN><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
+    } else if (fixed) {
       const int rows = std::max(4, (h + (int)grid.y - 1) / (int)grid.y);   // consecutive rows per block (2 extra per strip)
       const dim3 g2((w + kS2Out - 1) / kS2Out, (h + rows - 1) / rows, grid.z);
       if (pen == B2F_PENALTY_QUADRATIC) smooth2_kernel<B2F_PENALTY_QUADRATIC><<<g2, kThreads, 0, st>>>(a, ls.lo, rows);
