@@ -71,6 +71,76 @@ int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream) {
   return B2F_OK;
 }
 
+// ---- .flo files: host-side wire format of flow fields (flowExtensions.lua:254-287) ----
+namespace {
+constexpr float kFloTag = 202021.25f;
+struct File {
+  FILE* f;
+  explicit File(const char* path, const char* mode) : f(path ? fopen(path, mode) : nullptr) {}
+  ~File() { if (f) fclose(f); }
+};
+int flo_header(FILE* f, const char* path, int* w, int* h) {
+  float tag = 0.f;
+  int32_t dims[2] = {0, 0};
+  if (fread(&tag, 4, 1, f) != 1 || fread(dims, 4, 2, f) != 2) return b2f::fail(B2F_EINVAL, "flo: %s: truncated header", path);
+  if (tag != kFloTag) return b2f::fail(B2F_EINVAL, "flo: unable to read %s perhaps bigendian error", path);
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[0] > 99999 || dims[1] > 99999)
+    return b2f::fail(B2F_EINVAL, "flo: %s: bad size %d x %d", path, dims[0], dims[1]);
+  *w = dims[0];
+  *h = dims[1];
+  return B2F_OK;
+}
+}  // namespace
+
+int b2f_flo_write(const char* path, const float* flow_chw, int h, int w) {
+  if (!path || !flow_chw || h <= 0 || w <= 0) return b2f::fail(B2F_EINVAL, "flo_write: bad argument");
+  File fh(path, "wb");
+  if (!fh.f) return b2f::fail(B2F_EINVAL, "flo_write: cannot open %s", path);
+  const int32_t dims[2] = {w, h};
+  if (fwrite(&kFloTag, 4, 1, fh.f) != 1 || fwrite(dims, 4, 2, fh.f) != 2) return b2f::fail(B2F_EINVAL, "flo_write: %s: write failed", path);
+  const size_t hw = (size_t)h * w;
+  float row[2 * 1024];
+  for (size_t i = 0; i < hw;) {   // (2,h,w) -> interleaved (u,v), F:permute(2,3,1) in the reference
+    const size_t n = hw - i < 1024 ? hw - i : 1024;
+    for (size_t j = 0; j < n; ++j) {
+      row[2 * j] = flow_chw[i + j];
+      row[2 * j + 1] = flow_chw[hw + i + j];
+    }
+    if (fwrite(row, 8, n, fh.f) != n) return b2f::fail(B2F_EINVAL, "flo_write: %s: write failed", path);
+    i += n;
+  }
+  return B2F_OK;
+}
+
+int b2f_flo_read_header(const char* path, int* w, int* h) {
+  if (!path || !w || !h) return b2f::fail(B2F_EINVAL, "flo_read_header: bad argument");
+  File fh(path, "rb");
+  if (!fh.f) return b2f::fail(B2F_EINVAL, "flo: cannot open %s", path);
+  return flo_header(fh.f, path, w, h);
+}
+
+int b2f_flo_read(const char* path, float* flow_chw, int h, int w) {
+  if (!path || !flow_chw) return b2f::fail(B2F_EINVAL, "flo_read: bad argument");
+  File fh(path, "rb");
+  if (!fh.f) return b2f::fail(B2F_EINVAL, "flo: cannot open %s", path);
+  int fw = 0, fhh = 0;
+  int rc = flo_header(fh.f, path, &fw, &fhh);
+  if (rc) return rc;
+  if (fw != w || fhh != h) return b2f::fail(B2F_EINVAL, "flo_read: %s is %d x %d, buffer is %d x %d", path, fw, fhh, w, h);
+  const size_t hw = (size_t)h * w;
+  float row[2 * 1024];
+  for (size_t i = 0; i < hw;) {
+    const size_t n = hw - i < 1024 ? hw - i : 1024;
+    if (fread(row, 8, n, fh.f) != n) return b2f::fail(B2F_EINVAL, "flo_read: %s: truncated data", path);
+    for (size_t j = 0; j < n; ++j) {
+      flow_chw[i + j] = row[2 * j];
+      flow_chw[hw + i + j] = row[2 * j + 1];
+    }
+    i += n;
+  }
+  return B2F_OK;
+}
+
 int64_t b2f_launch_count(int reset) {
   int64_t v = b2f::g_launches;
   if (reset) b2f::g_launches = 0;

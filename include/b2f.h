@@ -173,6 +173,19 @@ B2F_API int b2f_occprior_criterion(const float* occ, int B, int C, int h, int w,
                            int size_average, float* grad,
                            double* loss_dev, double* loss_host, b2f_stream_t stream);
 
+/* ---- Middlebury .flo files -- HOST buffers, no device work ----------------
+ * File layout (flowExtensions.lua:254-287): float32 tag 202021.25 ("PIEH"), int32 width, int32
+ * height, then height*width interleaved (u, v) float32 pairs, all little-endian.  The reference
+ * keeps flow as a (2, h, w) tensor and permutes on the way in and out (loadFLO :268-269, writeFLO
+ * :275); these entries take / return that planar (2, h, w) layout.                              */
+/* flowExtensions.lua:274-286 writeFLO(filename, F).                                              */
+B2F_API int b2f_flo_write(const char* path, const float* flow_chw, int h, int w);
+/* Reads the header only (tag check, loadFLO :256-264): *w, *h.                                   */
+B2F_API int b2f_flo_read_header(const char* path, int* w, int* h);
+/* flowExtensions.lua:254-271 loadFLO(filename) into a caller-owned (2, h, w) buffer whose h, w
+ * must equal the header's.                                                                       */
+B2F_API int b2f_flo_read(const char* path, float* flow_chw, int h, int w);
+
 #ifdef __cplusplus
 }
 #endif
