@@ -46,6 +46,10 @@ SIGNATURES = {
     "b2f_debug_costvol_path": (C.c_int, [C.c_int]),
     "b2f_zero_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2f_launch_count": (C.c_int64, [C.c_int]),
+    "b2f_warp_bdhw_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    "b2f_warp_bdhw_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b2f_flo_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "b2f_flo_read_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2f_flo_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),

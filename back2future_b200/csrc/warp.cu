@@ -579,6 +579,154 @@ warp_bwd_scalar(const float* __restrict__ img, const float* __restrict__ grid, c
   reinterpret_cast<float2*>(ggrid)[pix] = r;
 }
 
+// ---- warpingUnit fused: BDHW in, BDHW out -------------------------------------------
+// models/pwc.lua:68-73 wraps the sampler in four nn.Transpose copies (image and flow to BHWD, result back) behind a
+// nn.MulConstant on the flow (:402-408, :441-446): three extra passes over every warped tensor.  These kernels
+// read the network's planar tensors directly: out[b,c,y,x] = bilinear(img[b,c], x + s*flow[b,0,y,x],
+// y + s*flow[b,1,y,x]).  One thread per pixel; the geometry is evaluated once per pixel (the BHWD kernels evaluate it
+// in every channel lane) and the channel loop gathers four taps per plane -- neighbouring lanes read neighbouring
+// addresses when the flow is smooth, which is what the decoder's bilinearly up-sampled flow is.  s*flow is rounded
+// to fp32 before the pixel coordinate is added, as MulConstant followed by getTopLeft does.
+// CQ > 1 (small pyramid levels, too few pixels to fill the machine with one thread per pixel): the block is
+// (128 / CQ pixels) x (CQ channel ranges); C % (CQ * UNROLL) == 0.
+template <int UNROLL, int CQ>
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_bdhw_fwd(const float* __restrict__ img, const float* __restrict__ flow, float scale, float* __restrict__ out,
+              int C, int H, int W) {
+  constexpr int PX = PIX_THREADS / CQ;
+  const int x = blockIdx.x * PX + (threadIdx.x % PX);
+  const int cq = threadIdx.x / PX;
+  if (x >= W) return;
+  const int y = blockIdx.y;
+  const unsigned b = blockIdx.z, hw = (unsigned)H * W, pix = (unsigned)y * W + x;
+  const float* fl = flow + (size_t)b * 2 * hw + pix;
+  const Geo g = geometry(__fmul_rn(__ldg(fl), scale), __fmul_rn(__ldg(fl + hw), scale), x, y, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const unsigned o_tl = (unsigned)g.yi * W + g.xi;
+  const unsigned d_r = g.rin ? 1u : 0u, d_b = g.bin ? (unsigned)W : 0u;   // absent taps re-read TL and are zeroed
+  const bool both = g.rin && g.bin;
+  const float* ip = img + (size_t)b * C * hw + o_tl;
+  float* op = out + (size_t)b * C * hw + pix;
+  int c = CQ > 1 ? cq * (C / CQ) : 0;
+  const int C_end = CQ > 1 ? c + C / CQ : C;
+  for (; c + UNROLL <= C_end; c += UNROLL) {
+    float tl[UNROLL], tr[UNROLL], bl[UNROLL], br[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float* p = ip + (size_t)(c + u) * hw;
+      tl[u] = __ldg(p);
+      tr[u] = __ldg(p + d_r);
+      bl[u] = __ldg(p + d_b);
+      br[u] = __ldg(p + d_b + d_r);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      __stcs(op + (size_t)(c + u) * hw, w_tl * tl[u] + w_tr * (g.rin ? tr[u] : 0.f) + w_bl * (g.bin ? bl[u] : 0.f) +
+                                            w_br * (both ? br[u] : 0.f));
+  }
+  for (; c < C_end; ++c) {
+    const float* p = ip + (size_t)c * hw;
+    const float tl = __ldg(p), tr = __ldg(p + d_r), bl = __ldg(p + d_b), br = __ldg(p + d_b + d_r);
+    __stcs(op + (size_t)c * hw, w_tl * tl + w_tr * (g.rin ? tr : 0.f) + w_bl * (g.bin ? bl : 0.f) + w_br * (both ? br : 0.f));
+  }
+}
+
+// gradImg (planar, pre-zeroed by the caller, NULL = flow gradient only) is scattered with scalar reductions --
+// with a smooth flow the 32 lanes of a warp hit one or two lines per tap; the four dot products of the flow
+// gradient accumulate over the channel loop in the pixel's own thread (no cross-lane reduction), and the result is
+// multiplied by s (MulConstant's backward) and stored planar.
+template <int UNROLL, bool ONLY_GRID, int CQ>
+__global__ void __launch_bounds__(PIX_THREADS)
+warp_bdhw_bwd(const float* __restrict__ img, const float* __restrict__ flow, float scale,
+              const float* __restrict__ gout, float* __restrict__ gimg, float* __restrict__ gflow, int C, int H, int W) {
+  constexpr int PX = PIX_THREADS / CQ;
+  __shared__ float s_dot[CQ > 1 ? CQ : 1][4][PX];
+  const int lx = threadIdx.x % PX, cq = threadIdx.x / PX;
+  const int x = blockIdx.x * PX + lx;
+  const bool live = x < W;
+  if (CQ == 1 && !live) return;
+  if (CQ > 1 && !live) {   // keeps the barrier below uniform
+    __syncthreads();
+    return;
+  }
+  const int y = blockIdx.y;
+  const unsigned b = blockIdx.z, hw = (unsigned)H * W, pix = (unsigned)y * W + x;
+  const float* fl = flow + (size_t)b * 2 * hw + pix;
+  const Geo g = geometry(__fmul_rn(__ldg(fl), scale), __fmul_rn(__ldg(fl + hw), scale), x, y, H, W);
+  const float w_tl = g.wx * g.wy, w_tr = (1.f - g.wx) * g.wy;
+  const float w_bl = g.wx * (1.f - g.wy), w_br = (1.f - g.wx) * (1.f - g.wy);
+  const unsigned o_tl = (unsigned)g.yi * W + g.xi;
+  const unsigned d_r = g.rin ? 1u : 0u, d_b = g.bin ? (unsigned)W : 0u;
+  const bool both = g.rin && g.bin;
+  const float* ip = img + (size_t)b * C * hw + o_tl;
+  const float* gp = gout + (size_t)b * C * hw + pix;
+  float* gi = ONLY_GRID ? nullptr : gimg + (size_t)b * C * hw + o_tl;
+  float d_tl = 0.f, d_tr = 0.f, d_bl = 0.f, d_br = 0.f;
+  int c = CQ > 1 ? cq * (C / CQ) : 0;
+  const int C_end = CQ > 1 ? c + C / CQ : C;
+  for (; c + UNROLL <= C_end; c += UNROLL) {
+    float v[UNROLL], tl[UNROLL], tr[UNROLL], bl[UNROLL], br[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float* p = ip + (size_t)(c + u) * hw;
+      v[u] = __ldcs(gp + (size_t)(c + u) * hw);
+      tl[u] = __ldg(p);
+      tr[u] = __ldg(p + d_r);
+      bl[u] = __ldg(p + d_b);
+      br[u] = __ldg(p + d_b + d_r);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      d_tl += tl[u] * v[u];
+      d_tr += tr[u] * v[u];
+      d_bl += bl[u] * v[u];
+      d_br += br[u] * v[u];
+      if (!ONLY_GRID) {
+        float* q = gi + (size_t)(c + u) * hw;
+        red_add(q, w_tl * v[u]);
+        if (g.rin) red_add(q + 1, w_tr * v[u]);
+        if (g.bin) red_add(q + W, w_bl * v[u]);
+        if (both) red_add(q + W + 1, w_br * v[u]);
+      }
+    }
+  }
+  for (; c < C_end; ++c) {
+    const float* p = ip + (size_t)c * hw;
+    const float v = __ldcs(gp + (size_t)c * hw);
+    d_tl += __ldg(p) * v;
+    d_tr += __ldg(p + d_r) * v;
+    d_bl += __ldg(p + d_b) * v;
+    d_br += __ldg(p + d_b + d_r) * v;
+    if (!ONLY_GRID) {
+      float* q = gi + (size_t)c * hw;
+      red_add(q, w_tl * v);
+      if (g.rin) red_add(q + 1, w_tr * v);
+      if (g.bin) red_add(q + W, w_bl * v);
+      if (both) red_add(q + W + 1, w_br * v);
+    }
+  }
+  if (CQ > 1) {   // fixed-order sum of the channel ranges' partial dot products
+    s_dot[cq][0][lx] = d_tl; s_dot[cq][1][lx] = d_tr; s_dot[cq][2][lx] = d_bl; s_dot[cq][3][lx] = d_br;
+    __syncthreads();
+    if (cq != 0) return;
+    d_tl = d_tr = d_bl = d_br = 0.f;
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      d_tl += s_dot[q][0][lx]; d_tr += s_dot[q][1][lx]; d_bl += s_dot[q][2][lx]; d_br += s_dot[q][3][lx];
+    }
+  }
+  // a tap outside the image contributes nothing to the dot products (BilinearSamplerBHWD.cu:236-262)
+  if (!g.rin) d_tr = 0.f;
+  if (!g.bin) d_bl = 0.f;
+  if (!both) d_br = 0.f;
+  const float gx = -g.wy * d_tl + g.wy * d_tr - (1.f - g.wy) * d_bl + (1.f - g.wy) * d_br;
+  const float gy = -g.wx * d_tl + g.wx * d_bl - (1.f - g.wx) * d_tr + (1.f - g.wx) * d_br;
+  float* gf = gflow + (size_t)b * 2 * hw + pix;
+  gf[0] = gx * scale;
+  gf[hw] = gy * scale;
+}
+
 // gridDim.y of the vector backward kernel: a block walks every gridDim.y-th row (the forward measured
 // slower with the row loop: its extra registers cost a resident block).  Enough blocks for ~2-3 waves of
 // resident CTAs (2-3 per SM), at most 8 rows per block so the tail stays short.
@@ -591,6 +739,9 @@ int vec_rows_grid(int Wg, int Hg, int B) {
   if (gy > Hg) gy = Hg;
   return (int)gy;
 }
+
+// small levels of the fused warpingUnit: four channel ranges per pixel when one thread per pixel cannot fill the SMs
+bool bdhw_split(int B, int C, int H, int W) { return C % 16 == 0 && (int64_t)B * H * W < (int64_t)num_sms() * 1024; }
 
 // preconditions of the lean C = 3 kernels (see there); B2F_WARP_C3_LEGACY=1 forces the older kernels (experiments)
 bool c3_lean_ok(int B, int H, int W, int Hg, int Wg) {
@@ -677,5 +828,51 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
     else warp_bwd_scalar<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, C, Hg, Wg);
     B2F_CHECK_LAUNCH("warp_bwd_scalar");
   }
+  return B2F_OK;
+}
+
+// warpingUnit(I, F) of models/pwc.lua:68-73 with the nn.MulConstant that feeds it (:402-408, :441-446) folded in.
+extern "C" int b2f_warp_bdhw_forward(const float* img, const float* flow, float flow_scale, float* out, int B,
+                                     int C, int H, int W, b2f_stream_t stream) {
+  if (!img || !flow || !out) return fail(B2F_EINVAL, "warp_bdhw_forward: NULL pointer");
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "warp_bdhw: bad size B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (B > 65535 || H > 65535) return fail(B2F_EINVAL, "warp_bdhw: B and H must be <= 65535 (grid y/z limits)");
+  if ((size_t)H * W >= (1ull << 31)) return fail(B2F_EINVAL, "warp_bdhw: H*W must be below 2^31");
+  if (!aligned4(img) || !aligned4(flow) || !aligned4(out)) return fail(B2F_EALIGN, "warp_bdhw_forward: misaligned");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bdhw_split(B, C, H, W)) {
+    dim3 grid_dim((W + 31) / 32, H, B);
+    warp_bdhw_fwd<4, 4><<<grid_dim, PIX_THREADS, 0, st>>>(img, flow, flow_scale, out, C, H, W);
+  } else {
+    dim3 grid_dim((W + PIX_THREADS - 1) / PIX_THREADS, H, B);
+    if (C % 4 == 0) warp_bdhw_fwd<4, 1><<<grid_dim, PIX_THREADS, 0, st>>>(img, flow, flow_scale, out, C, H, W);
+    else warp_bdhw_fwd<3, 1><<<grid_dim, PIX_THREADS, 0, st>>>(img, flow, flow_scale, out, C, H, W);
+  }
+  B2F_CHECK_LAUNCH("warp_bdhw_fwd");
+  return B2F_OK;
+}
+
+extern "C" int b2f_warp_bdhw_backward(const float* img, const float* flow, float flow_scale, const float* gradOut,
+                                      float* gradImg, float* gradFlow, int B, int C, int H, int W,
+                                      b2f_stream_t stream) {
+  if (!img || !flow || !gradOut || !gradFlow) return fail(B2F_EINVAL, "warp_bdhw_backward: NULL pointer");
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "warp_bdhw: bad size B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (B > 65535 || H > 65535) return fail(B2F_EINVAL, "warp_bdhw: B and H must be <= 65535 (grid y/z limits)");
+  if ((size_t)H * W >= (1ull << 31)) return fail(B2F_EINVAL, "warp_bdhw: H*W must be below 2^31");
+  if (!aligned4(img) || !aligned4(flow) || !aligned4(gradOut) || !aligned4(gradFlow) || (gradImg && !aligned4(gradImg)))
+    return fail(B2F_EALIGN, "warp_bdhw_backward: misaligned");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool only = gradImg == nullptr;
+  const bool split = bdhw_split(B, C, H, W);
+  dim3 grid_dim(split ? (W + 31) / 32 : (W + PIX_THREADS - 1) / PIX_THREADS, H, B);
+#define B2F_BDHW_BWD(U, Q) do { if (only) warp_bdhw_bwd<U, true, Q><<<grid_dim, PIX_THREADS, 0, st>>>(img, flow, flow_scale, gradOut, gradImg, gradFlow, C, H, W); \
+                                else warp_bdhw_bwd<U, false, Q><<<grid_dim, PIX_THREADS, 0, st>>>(img, flow, flow_scale, gradOut, gradImg, gradFlow, C, H, W); } while (0)
+  if (split) B2F_BDHW_BWD(4, 4);
+  else if (C % 4 == 0) B2F_BDHW_BWD(4, 1);
+  else B2F_BDHW_BWD(3, 1);
+#undef B2F_BDHW_BWD
+  B2F_CHECK_LAUNCH("warp_bdhw_bwd");
   return B2F_OK;
 }

@@ -290,6 +290,54 @@ class BilinearSamplerBHWD(Module):
         return self.gradInput
 
 
+class WarpingUnit(Module):
+    """`warpingUnit(I, F)` of models/pwc.lua:68-73 as ONE module, with the `nn.MulConstant(flow_scale)` that feeds
+    it (:402-408 feature warps, :441-446 image warps) folded in: input = {I (B,C,H,W), F (B,2,H,W)}, both in the
+    network's own BDHW layout; output (B,C,H,W).  Replaces Transpose x2 -> BilinearSamplerBHWD -> Transpose and the
+    scaling pass; results equal that chain's."""
+
+    def __init__(self, flow_scale=1.0):
+        super().__init__()
+        self.flow_scale = float(flow_scale)
+        self.gradInput = []
+
+    @staticmethod
+    def check(input, gradOutput=None):
+        I, F = input
+        assert I.dim() == 4 and F.dim() == 4
+        assert I.size(0) == F.size(0) and F.size(1) == 2
+        assert I.size(2) == F.size(2) and I.size(3) == F.size(3)
+        if gradOutput is not None:
+            assert tuple(gradOutput.shape) == tuple(I.shape)
+
+    def updateOutput(self, input):
+        lib = _lib.load()
+        I, F = _dev(input[0], "I"), _dev(input[1], "F")
+        self.check((I, F))
+        I = I if I.is_contiguous() else I.contiguous()
+        F = F if F.is_contiguous() else F.contiguous()
+        B, Cn, H, W = I.shape
+        if self.output.shape != I.shape or self.output.device != I.device:
+            self.output = torch.empty_like(I)
+        _lib.check(lib.b2f_warp_bdhw_forward(_p(I), _p(F), self.flow_scale, _p(self.output), B, Cn, H, W, _stream()))
+        return self.output
+
+    def updateGradInput(self, input, gradOutput, only_grid=False):
+        lib = _lib.load()
+        I, F, go = _dev(input[0], "I"), _dev(input[1], "F"), _dev(gradOutput, "gradOutput")
+        self.check((I, F), go)
+        I = I if I.is_contiguous() else I.contiguous()
+        F = F if F.is_contiguous() else F.contiguous()
+        go = go if go.is_contiguous() else go.contiguous()
+        B, Cn, H, W = I.shape
+        gI = torch.zeros_like(I)
+        gF = torch.empty_like(F)
+        _lib.check(lib.b2f_warp_bdhw_backward(_p(I), _p(F), self.flow_scale, _p(go), None if only_grid else _p(gI),
+                                              _p(gF), B, Cn, H, W, _stream()))
+        self.gradInput = [gI, gF]
+        return self.gradInput
+
+
 # ---------------------------------------------------------------------------------------
 # nn.Criterion protocol
 # ---------------------------------------------------------------------------------------

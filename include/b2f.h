@@ -173,6 +173,20 @@ B2F_API int b2f_occprior_criterion(const float* occ, int B, int C, int h, int w,
                            int size_average, float* grad,
                            double* loss_dev, double* loss_host, b2f_stream_t stream);
 
+/* ---- warpingUnit fused ------------------------------------------------
+ * models/pwc.lua:68-73 `warpingUnit(I, F)` = Transpose(I), Transpose(F) -> nn.BilinearSamplerBHWD ->
+ * Transpose back, fed by `nn.MulConstant(s)` on the flow (:402-408 feature warps, :441-446 image
+ * warps).  These entries take the network's planar tensors directly -- img (B,C,H,W), flow (B,2,H,W)
+ * with channel 0 = x, 1 = y in network units, flow_scale = the MulConstant factor -- and produce what
+ * that chain produces: out (B,C,H,W); backward: gradImg (B,C,H,W) ACCUMULATED into a caller-zeroed
+ * buffer (NULL = flow gradient only), gradFlow (B,2,H,W) = s * gradGrid.  Four layout passes and one
+ * scaling pass of the reference disappear; results equal the chain's within fp32 rounding.       */
+B2F_API int b2f_warp_bdhw_forward(const float* img, const float* flow, float flow_scale, float* out,
+                                  int B, int C, int H, int W, b2f_stream_t stream);
+B2F_API int b2f_warp_bdhw_backward(const float* img, const float* flow, float flow_scale,
+                                   const float* gradOut, float* gradImg, float* gradFlow,
+                                   int B, int C, int H, int W, b2f_stream_t stream);
+
 /* ---- Middlebury .flo files -- HOST buffers, no device work ----------------
  * File layout (flowExtensions.lua:254-287): float32 tag 202021.25 ("PIEH"), int32 width, int32
  * height, then height*width interleaved (u, v) float32 pairs, all little-endian.  The reference

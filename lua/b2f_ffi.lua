@@ -26,6 +26,10 @@ int b2f_warp_bhwd_forward(const float* img, const float* grid, float* out, int B
                           int Hg, int Wg, b2f_stream_t stream);
 int b2f_warp_bhwd_backward(const float* img, const float* grid, const float* gradOut, float* gradImg,
                            float* gradGrid, int B, int H, int W, int C, int Hg, int Wg, b2f_stream_t stream);
+int b2f_warp_bdhw_forward(const float* img, const float* flow, float flow_scale, float* out, int B, int C,
+                          int H, int W, b2f_stream_t stream);
+int b2f_warp_bdhw_backward(const float* img, const float* flow, float flow_scale, const float* gradOut,
+                           float* gradImg, float* gradFlow, int B, int C, int H, int W, b2f_stream_t stream);
 int b2f_ob_criterion(const b2f_ob_params* prm, const float* flow, const float* bflow, const float* occ,
                      const float* warp_past, const float* warp_future, const float* target,
                      int B, int C, int h, int w, float* grad_occ, float* grad_warp_past,

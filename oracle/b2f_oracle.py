@@ -322,6 +322,30 @@ def warp_backward(img, grid, grad_out, only_grid=False, dtype=np.float64):
     return grad_img, grad_grid
 
 
+def warping_unit_forward(img_bdhw, flow_bdhw, scale, dtype=np.float64):
+    """models/pwc.lua:68-73 `warpingUnit(I, F)` behind the `nn.MulConstant(scale)` of :402-408 / :441-446:
+    Transpose({2,3},{3,4}) of image and flow (BDHW -> BHWD), BilinearSamplerBHWD, Transpose({3,4},{2,3}) back.
+    img (B,C,H,W), flow (B,2,H,W) in network units; returns (B,C,H,W).  The product flow*scale is rounded to
+    fp32 (MulConstant runs in fp32) before the sampler sees it."""
+    img = np.asarray(img_bdhw, F32)
+    grid = (np.asarray(flow_bdhw, F32) * F32(scale)).astype(F32)
+    out = warp_forward(np.ascontiguousarray(img.transpose(0, 2, 3, 1)),
+                       np.ascontiguousarray(grid.transpose(0, 2, 3, 1)), dtype=dtype)
+    return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
+
+
+def warping_unit_backward(img_bdhw, flow_bdhw, scale, grad_out_bdhw, only_grid=False, dtype=np.float64):
+    """Backward of the same chain: (gradImg (B,C,H,W) or None, gradFlow (B,2,H,W)); MulConstant's backward
+    multiplies the sampler's flow gradient by `scale` (nn.MulConstant.updateGradInput)."""
+    img = np.asarray(img_bdhw, F32)
+    grid = (np.asarray(flow_bdhw, F32) * F32(scale)).astype(F32)
+    go = np.ascontiguousarray(np.asarray(grad_out_bdhw).transpose(0, 2, 3, 1))
+    gi, gg = warp_backward(np.ascontiguousarray(img.transpose(0, 2, 3, 1)),
+                           np.ascontiguousarray(grid.transpose(0, 2, 3, 1)), go, only_grid=only_grid, dtype=dtype)
+    gflow = np.ascontiguousarray(gg.transpose(0, 3, 1, 2)) * dtype(F32(scale))
+    return (None if gi is None else np.ascontiguousarray(gi.transpose(0, 3, 1, 2))), gflow
+
+
 def warp_forward_loops(img, grid):
     """Scalar per-pixel transcription of the kernel (float64 arithmetic, fp32 geometry).
     Slow: small cases only.  Independent of the vectorised version above."""

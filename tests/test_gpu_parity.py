@@ -380,6 +380,70 @@ def test_warp_full_size_image_adjoint(env):
 
 
 # ---------------------------------------------------------------------------------------
+# fused warpingUnit (BDHW in / BDHW out, flow scaling folded in) -- SURVEY 8f row N2
+# ---------------------------------------------------------------------------------------
+
+def _smooth_flow(r, B, H, W, amp):
+    ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    f = np.stack([np.sin(xs / 7.0 + ys / 5.0) + 0.4, np.cos(xs / 6.0 - ys / 9.0)], 0)[None] * amp
+    return (f + 0.05 * r.standard_normal((B, 2, H, W))).astype(np.float32)
+
+
+@pytest.mark.parametrize("B,Cn,H,W,scale,kind", [
+    (2, 32, 14, 32, 2.5, "smooth"), (1, 64, 9, 20, -1.25, "smooth"), (2, 3, 20, 37, 5.0, "smooth"), (1, 3, 33, 130, -10.0, "iid"),
+    (1, 5, 6, 7, 20.0, "iid"), (1, 1, 5, 6, 1.0, "iid"), (3, 8, 1, 1, 1.0, "iid"), (1, 96, 7, 16, 0.625, "smooth"), (1, 4, 4, 5, 300.0, "iid"),
+])
+def test_warping_unit_fused_matches_the_reference_chain(env, B, Cn, H, W, scale, kind):
+    """b2f_warp_bdhw_* == Transpose -> MulConstant -> BilinearSamplerBHWD -> Transpose (pwc.lua:68-73, 402-446),
+    against the oracle's composition and against our own BHWD kernels run through that chain."""
+    torch = env.torch_
+    r = rng(21)
+    img = r.standard_normal((B, Cn, H, W)).astype(np.float32)
+    flow = _smooth_flow(r, B, H, W, 0.8) if kind == "smooth" else (r.standard_normal((B, 2, H, W)) * 0.3).astype(np.float32)
+    go = r.standard_normal((B, Cn, H, W)).astype(np.float32)
+    ti, tf, tg = env.t(img), env.t(flow), env.t(go)
+    out = torch.full_like(ti, float("nan"))
+    gi = torch.zeros_like(ti)
+    gf = torch.full_like(tf, float("nan"))
+    L = env.lib
+    env.check(L.b2f_warp_bdhw_forward(env.p(ti), env.p(tf), scale, env.p(out), B, Cn, H, W, env.stream()))
+    env.check(L.b2f_warp_bdhw_backward(env.p(ti), env.p(tf), scale, env.p(tg), env.p(gi), env.p(gf), B, Cn, H, W, env.stream()))
+    gf_only = torch.full_like(tf, float("nan"))
+    env.check(L.b2f_warp_bdhw_backward(env.p(ti), env.p(tf), scale, env.p(tg), None, env.p(gf_only), B, Cn, H, W, env.stream()))
+    torch.cuda.synchronize()
+    assert o.rel_err(out.cpu().numpy(), o.warping_unit_forward(img, flow, scale)) < TOL
+    rgi, rgf = o.warping_unit_backward(img, flow, scale, go)
+    assert o.rel_err(gi.cpu().numpy(), rgi) < TOL and o.rel_err(gf.cpu().numpy(), rgf) < TOL
+    assert torch.equal(gf_only, gf)
+    # the same chain through the BHWD entry points (what the unmodified pwc.lua would run on this library)
+    img_t = ti.permute(0, 2, 3, 1).contiguous()
+    grid_t = (tf * scale).permute(0, 2, 3, 1).contiguous()
+    out_t, gi_t, gg_t = _warp(env, img_t.cpu().numpy(), grid_t.cpu().numpy(), tg.permute(0, 2, 3, 1).contiguous().cpu().numpy())
+    assert o.rel_err(out.cpu().numpy(), out_t.transpose(0, 3, 1, 2)) < 1e-6
+    assert o.rel_err(gi.cpu().numpy(), gi_t.transpose(0, 3, 1, 2)) < 1e-5
+    assert o.rel_err(gf.cpu().numpy(), gg_t.transpose(0, 3, 1, 2) * np.float32(scale)) < 1e-5
+
+
+def test_warping_unit_module_and_argument_errors(env):
+    from back2future_b200 import nn as bnn
+    torch = env.torch_
+    r = rng(22)
+    img = r.standard_normal((2, 16, 12, 24)).astype(np.float32)
+    flow = _smooth_flow(r, 2, 12, 24, 0.5)
+    go = r.standard_normal(img.shape).astype(np.float32)
+    m = bnn.WarpingUnit(20.0 / 8)
+    out = m.forward([env.t(img), env.t(flow)])
+    assert o.rel_err(out.cpu().numpy(), o.warping_unit_forward(img, flow, 2.5)) < TOL
+    gI, gF = m.backward([env.t(img), env.t(flow)], env.t(go))
+    rgi, rgf = o.warping_unit_backward(img, flow, 2.5, go)
+    assert o.rel_err(gI.cpu().numpy(), rgi) < TOL and o.rel_err(gF.cpu().numpy(), rgf) < TOL
+    with pytest.raises(AssertionError):
+        m.forward([env.t(img), env.t(flow[:, :, :5])])
+    assert env.lib.b2f_warp_bdhw_forward(None, None, 1.0, None, 1, 1, 1, 1, env.stream()) != 0
+    assert env.lib.b2f_warp_bdhw_forward(env.p(out), env.p(out), 1.0, env.p(out), 1, 0, 4, 4, env.stream()) != 0
+
+
+# ---------------------------------------------------------------------------------------
 # criterions
 # ---------------------------------------------------------------------------------------
 

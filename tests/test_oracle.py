@@ -424,3 +424,34 @@ def test_l1_penalty_ignores_alpha():
     x = np.linspace(-1, 1, 7)
     assert np.array_equal(o.L1Penalty(0.38).apply(x), o.L1Penalty().apply(x))
     assert np.isclose(o.L1Penalty().apply(np.zeros(1))[0], 1e-3)
+
+
+# ---------------------------------------------------------------------------------------
+# warpingUnit composition (models/pwc.lua:68-73 + MulConstant)
+# ---------------------------------------------------------------------------------------
+
+def test_warping_unit_composition_identity_adjoint_and_flow_gradient():
+    r = np.random.default_rng(31)
+    img = r.standard_normal((2, 5, 6, 7)).astype(np.float32)
+    flow = (r.standard_normal((2, 2, 6, 7)) * 0.3).astype(np.float32)
+    go = r.standard_normal(img.shape)
+    # zero flow is the identity whatever the scale; channel 0 of the flow moves along x
+    assert np.array_equal(o.warping_unit_forward(img, flow * 0, 3.0), img.astype(np.float64))
+    shift = np.zeros_like(flow)
+    shift[:, 0] = 0.5
+    out = o.warping_unit_forward(img, shift, 4.0)                       # +2 px in x
+    assert np.array_equal(out[..., :5], img[..., 2:].astype(np.float64))
+    # gradImg is the adjoint of the (linear in img) forward
+    gi, gf = o.warping_unit_backward(img, flow, 4.0, go)
+    probe = r.standard_normal(img.shape).astype(np.float32)
+    assert abs((o.warping_unit_forward(probe, flow, 4.0) * go).sum() - (probe * gi).sum()) < 1e-9
+    # gradFlow carries MulConstant's factor: finite differences in network units
+    for idx in ((0, 0, 2, 3), (1, 1, 4, 1)):
+        eps = 1e-3
+        f2, f1 = flow.copy(), flow.copy()
+        f2[idx] += eps
+        f1[idx] -= eps
+        fd = ((o.warping_unit_forward(img, f2, 4.0) - o.warping_unit_forward(img, f1, 4.0)) * go).sum() / (2 * eps)
+        assert abs(fd - gf[idx]) < 1e-3 * max(1.0, abs(fd))
+    gi2, gf2 = o.warping_unit_backward(img, flow, 4.0, go, only_grid=True)
+    assert gi2 is None and np.array_equal(gf2, gf)

@@ -9,7 +9,7 @@ P = os.path.join(ROOT, "profiles")
 rnd = "r01"
 
 def short(n):
-    n = n.replace("void ", "").replace("b2f::<unnamed>::", "")
+    n = n.replace("void ", "").replace("b2f::<unnamed>::", "").replace("unnamed>::", "")
     return n.split("(")[0]
 
 # ---- launch list of the bench command ------------------------------------------------------
@@ -19,12 +19,12 @@ ki, vi, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index(
 def us(r):
     v = float(r[vi].replace(",", ""))
     return v / 1000 if r[ui].startswith("n") else v
-ours = [(short(r[ki]), r[gi], us(r)) for r in data if "b2f::" in r[ki]]
+ours = [(short(r[ki]), r[gi], us(r)) for r in data if "b2f::" in r[ki] or "unnamed>::" in r[ki]]
 # one step = the last 56 kernels of ours (10 cv fwd, 18 warp fwd, 18 warp bwd, 10 cv bwd)
 step = ours[-56:]
 tot = sum(t for _, _, t in step)
 with open(os.path.join(P, "%s_ncu_launch_list_bench.txt" % rnd), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 700 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:costvol|warp_|... -c 900 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-criterions\n")
     f.write("# last captured step (56 launches; cold-cache, serialised times).  sum = %.1f us\n" % tot)
     f.write("%-52s %-16s %9s %7s\n" % ("kernel", "grid", "us", "share"))
     for n, g, t in step:
