@@ -626,6 +626,23 @@ def test_constvel_and_occprior(env, size_avg):
         assert o.rel_err(g.cpu().numpy(), o.occprior_backward(occ, bool(size_avg))) < TOL
 
 
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("w", [126, 127, 128, 129, 253, 255, 381])
+@pytest.mark.parametrize("alias", [1, 0])
+def test_smoothness_tile_boundaries(env, order, w, alias):
+    """Widths around the x-tile sizes of the lean kernels (127 / 126 output columns per block: thread 0, and for the
+    second order thread 127, are halo columns) and several row strips per image: loss and every gradient element,
+    including the columns next to a tile seam and the rows next to a strip seam, against the float64 oracle."""
+    r = rng(40 + w)
+    B, h = 2, 45
+    x = (r.standard_normal((B, 2, h, w)) * 0.3).astype(np.float32)
+    tgt = r.uniform(-2.1, 2.6, (B, 3, h, w)).astype(np.float32)
+    loss, g = _run_smooth(env, order, 1, 0, alias, x, tgt)
+    oc = o.SmoothnessOracle(order, o.make_penalty(1), size_average=False, alias=bool(alias))
+    assert abs(loss - oc.forward(x, tgt)) < TOL * abs(loss)
+    assert o.rel_err(g, oc.backward(x, tgt)) < TOL
+
+
 def test_criterions_training_sizes(env):
     """BASELINE config 3 / 4 finest level (B=8, 320x640): losses against the float64 oracle."""
     r = rng(15)
