@@ -132,6 +132,7 @@ class Workload:
         def empty(*shape):
             return torch.empty(shape, device=dev, dtype=torch.float32)
 
+        self.grids = []         # the flow fields of the warps (refilled by set_flow for the flow-variant timings)
         self.keep = []          # every tensor the ops reference
         self.inputs = []        # (name, tensor) copied H2D per e2e step
         self.outputs = []       # (name, tensor) copied D2H per e2e step
@@ -178,6 +179,7 @@ class Workload:
         for name, Cn, (h, w), wtag in warp_cfgs:
             for d, fr in ((1, "past"), (0, "fut")):
                 img, grid = randn(B, h, w, Cn), randn(B, h, w, 2, scale=4.0)
+                self.grids.append(grid)
                 out, go = empty(B, h, w, Cn), randn(B, h, w, Cn)
                 gimg, ggrid = empty(B, h, w, Cn), empty(B, h, w, 2)
                 self.keep += [img, grid, out, go, gimg, ggrid]
@@ -244,6 +246,24 @@ class Workload:
 
     def total_bytes(self):
         return sum(op.bytes for op in self.ops)
+
+    def set_flow(self, kind, seed=3):
+        """Refill every warp's flow field in place: "iid4" / "iid0.5" = i.i.d. N(0, sigma px) (sigma = 4 is
+        the headline workload, 0.5 its second run), "smooth" = a low-frequency field of +-6 px (scaled with the
+        level's width) plus 0.05 px noise -- what the decoder's bilinearly up-sampled flow looks like."""
+        torch = self.torch
+        g = torch.Generator(device=self.dev).manual_seed(seed)
+        for grid in self.grids:
+            B, h, w, _ = grid.shape
+            if kind.startswith("iid"):
+                grid.copy_(torch.randn(grid.shape, device=self.dev, generator=g) * float(kind[3:]))
+            else:
+                ys, xs = torch.meshgrid(torch.arange(h, device=self.dev, dtype=torch.float32),
+                                        torch.arange(w, device=self.dev, dtype=torch.float32), indexing="ij")
+                k = w / 1024.0
+                f = torch.stack([6 * k * torch.sin(xs / (90 * k) + ys / (70 * k)) + 3 * k,
+                                 5 * k * torch.cos(xs / (60 * k) - ys / (110 * k))], -1)
+                grid.copy_(f[None] + 0.05 * torch.randn(grid.shape, device=self.dev, generator=g))
 
     # -- CUDA graph of one step -------------------------------------------------------------
     def capture(self, streams):
@@ -800,6 +820,23 @@ def main():
 
     # ---- per-kernel breakdown (informational) and CPU baseline (rank 0) ----------------
     rows = breakdown(torch, wl) if rank == 0 else None
+    # the same step with other flow statistics (graph replays; outside the timed region, N = 1 only)
+    flow_var = None
+    if graph is not None and rank == 0 and world == 1 and not args.no_criterions:
+        flow_var = {"iid_sigma4_ms": round(ms / K, 4)}
+        for kind, key in (("iid0.5", "iid_sigma0.5_ms"), ("smooth", "smooth_ms")):
+            wl.set_flow(kind)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fa.record()
+            for _ in range(30):
+                graph.replay()
+            fb.record()
+            torch.cuda.synchronize()
+            flow_var[key] = round(fa.elapsed_time(fb) / 30, 4)
+        wl.set_flow("iid4", seed=2)
     crit = time_criterions(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -832,7 +869,7 @@ def main():
                                  "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
                                  "start of the step on their own stream"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "criterions": crit,
+            "criterions": crit, "flow_variants": flow_var,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
