@@ -20,7 +20,9 @@ def timeit(fn, n=12):
     return ts[len(ts) // 2]
 g = torch.Generator(device="cuda").manual_seed(2)
 print(os.path.basename(os.environ.get("B2F_LIB_PATH", "default")))
-for (B, H, W, Cn) in ((8, 448, 1024, 3), (8, 224, 512, 3), (8, 112, 256, 32)):
+import os as _os
+SHAPES = ((8, 112, 256, 32), (8, 56, 128, 64), (8, 28, 64, 96), (8, 14, 32, 128)) if _os.environ.get('TW_FEAT') else ((8, 448, 1024, 3), (8, 224, 512, 3), (8, 112, 256, 32))
+for (B, H, W, Cn) in SHAPES:
     img = torch.randn(B, H, W, Cn, device=dev, generator=g)
     go = torch.randn(B, H, W, Cn, device=dev, generator=g)
     out, gi = torch.empty_like(img), torch.zeros_like(img)
