@@ -818,6 +818,56 @@ def main():
                "api": "back2future_b200.nn.CostVolMulti / BilinearSamplerBHWD updateOutput+updateGradInput"}
         del ee
 
+    # ---- training path only: the gradient all-reduce next to / under the hot-path step, N > 1 ----
+    # The microbenchmark itself has no collective (triplets are sharded); a training step adds exactly one
+    # sum-all-reduce of the flattened fp32 gradient (7.19 M floats for Ours-Hard) on a side stream.  Reported: its
+    # time alone, and the step time when it runs under the next step's kernels (outside the timed region).
+    allreduce = None
+    if world > 1:
+        from back2future_b200.dist import GradientAllReduce, NPARAMS_HARD
+        flat = torch.randn(NPARAMS_HARD, device=dev)
+        ar = GradientAllReduce(flat)
+
+        def timed(fn, n):
+            barrier()
+            torch.cuda.synchronize()
+            ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ta.record()
+            for _ in range(n):
+                fn()
+            tb.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([ta.elapsed_time(tb) / n], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        def alone():
+            ar.start()
+            ar.wait()
+
+        def overlapped():
+            ar.wait()             # the previous step's reduction must be done before its buffer is reused
+            if graph is not None:
+                graph.replay()
+            else:
+                wl.step()
+            ar.start()            # "backward has produced the gradient": reduce under the next step
+
+        for _ in range(3):
+            alone()
+        t_alone = timed(alone, 20)
+        for _ in range(3):
+            overlapped()
+        t_over = timed(overlapped, 30)
+        ar.wait()
+        torch.cuda.synchronize()
+        nbytes = flat.numel() * 4
+        allreduce = {"floats": flat.numel(), "bytes": nbytes, "alone_ms": round(t_alone, 4),
+                     "busbw_GBps": round(2 * (world - 1) / world * nbytes / (t_alone * 1e-3) / 1e9, 1),
+                     "step_ms": round(ms / K, 4), "step_with_allreduce_ms": round(t_over, 4),
+                     "backend": dist.get_backend()}
+        del flat, ar
+
     # ---- per-kernel breakdown (informational) and CPU baseline (rank 0) ----------------
     rows = breakdown(torch, wl) if rank == 0 else None
     # the same step with other flow statistics (graph replays; outside the timed region, N = 1 only)
@@ -869,7 +919,7 @@ def main():
                                  "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
                                  "start of the step on their own stream"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "criterions": crit, "flow_variants": flow_var,
+            "criterions": crit, "flow_variants": flow_var, "allreduce": allreduce,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
