@@ -503,22 +503,51 @@ __device__ __forceinline__ void slab_load_g(float (&g)[9][8], const float* __res
   }
 }
 
+template <class cfg>
+__device__ __forceinline__ void load_xv(float (&xv)[16], const float* __restrict__ xs, int c) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + c * (XR * cfg::XW) + 4 * q);
+    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+  }
+}
+#ifndef B2F_CVB_DB
+#define B2F_CVB_DB 1
+#endif
+// The X operands of channel c + 1 are requested before the 72 FMAs of channel c (B2F_CVB_DB, default on): with two
+// compute warps per scheduler an LDS round trip in front of every channel's FMAs is not always covered.
 template <class cfg, int T>
 __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float (&g)[9][8], const float* __restrict__ xs) {
+#if B2F_CVB_DB
+  float xa[16], xb[16];
+  load_xv<cfg>(xa, xs, 0);
+#pragma unroll
+  for (int c = 0; c < CG; c += 2) {
+    load_xv<cfg>(xb, xs, c + 1);
+#pragma unroll
+    for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[c][j] = fmaf(g[ix][j], xa[j + (T > 0 ? ix : 8 - ix)], acc[c][j]);
+    if (c + 2 < CG) load_xv<cfg>(xa, xs, c + 2);
+#pragma unroll
+    for (int ix = 0; ix < 9; ++ix)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[c + 1][j] = fmaf(g[ix][j], xb[j + (T > 0 ? ix : 8 - ix)], acc[c + 1][j]);
+  }
+#else
 #pragma unroll
   for (int c = 0; c < CG; ++c) {
     float xv[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(xs + c * (XR * cfg::XW) + 4 * q);
-      xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
-    }
+    load_xv<cfg>(xv, xs, c);
 #pragma unroll
     for (int ix = 0; ix < 9; ++ix)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         acc[c][j] = fmaf(g[ix][j], xv[j + (T > 0 ? ix : 8 - ix)], acc[c][j]);
   }
+#endif
 }
 
 template <int SGN, int TW, int NSLAB>
