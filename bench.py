@@ -404,7 +404,19 @@ def time_criterions(torch, lib, dev, B=BATCH, iters=9):
     bpp = (84, 84, 28, 28, 28, 32, 16)
     tot = dict.fromkeys(names, 0.0)
     top = {}
-    for k in range(5):
+    keep = []
+    by_level = []      # the calls (and, through their closures, the tensors) of every level, for the back-to-back timing
+
+    def make_level(k, shs=None):
+        # shs: stream handles; call i of the level goes to shs[(k + i) % len(shs)] and every call has its own loss slot
+        lv = torch.zeros(8, dtype=torch.float64, device=dev)
+        keep.append(lv)
+        slot = [0]
+
+        def nxt():
+            i = slot[0]
+            slot[0] += 1
+            return C.c_void_p(lv.data_ptr() + 8 * i), (shs[(k + i) % len(shs)] if shs else None)
         h, w = 320 >> k, 640 >> k
         flow, bflow = torch.randn(B, 2, h, w, device=dev) * 0.2, torch.randn(B, 2, h, w, device=dev) * 0.2
         occ = torch.softmax(torch.randn(B, 2, h, w, device=dev), 1).contiguous()
@@ -413,14 +425,26 @@ def time_criterions(torch, lib, dev, B=BATCH, iters=9):
         calls = []
         for gt in (0, 1):
             prm = _lib.ObParams(gt, 1, 0.05, 1.0, 0.0 if gt else 1.0, 1.0, 1.0, 20.0 / 2 ** k, gt, 0, 0)
-            calls.append(lambda prm=prm: lib.b2f_ob_criterion(C.byref(prm), P(flow), P(bflow), P(occ), P(w1), P(w2), P(tgt),
-                                                              B, 3, h, w, P(g2a), P(g3a), P(g3b), P(loss), None, None))
+            lp, st_ = nxt()
+            calls.append(lambda prm=prm, lp=lp, st_=st_: lib.b2f_ob_criterion(
+                C.byref(prm), P(flow), P(bflow), P(occ), P(w1), P(w2), P(tgt), B, 3, h, w, P(g2a), P(g3a), P(g3b), lp, None, st_))
         for order, pen, src in ((1, 1, flow), (1, 0, occ), (2, 1, flow)):
             prm = _lib.SmoothParams(order, pen, 0.05, 20.0, 0, 1)
-            calls.append(lambda prm=prm, src=src: lib.b2f_smoothness_criterion(C.byref(prm), P(src), P(tgt), B, 2, 3, h, w,
-                                                                               P(g2a), P(loss), None, None))
-        calls.append(lambda: lib.b2f_constvel_criterion(P(flow), P(bflow), B, 2, h, w, 1, P(g2a), P(g2b), P(loss), None, None))
-        calls.append(lambda: lib.b2f_occprior_criterion(P(occ), B, 2, h, w, 1.0, 0, P(g2a), P(loss), None, None))
+            lp, st_ = nxt()
+            gsm = torch.empty_like(flow)      # own gradient buffer: the calls of a level may run concurrently
+            calls.append(lambda prm=prm, src=src, lp=lp, st_=st_, gsm=gsm: lib.b2f_smoothness_criterion(
+                C.byref(prm), P(src), P(tgt), B, 2, 3, h, w, P(gsm), lp, None, st_))
+        lp, st_ = nxt()
+        gcv = torch.empty_like(flow)
+        calls.append(lambda lp=lp, st_=st_: lib.b2f_constvel_criterion(P(flow), P(bflow), B, 2, h, w, 1, P(gcv), P(g2b), lp, None, st_))
+        lp, st_ = nxt()
+        gop = torch.empty_like(flow)
+        calls.append(lambda lp=lp, st_=st_: lib.b2f_occprior_criterion(P(occ), B, 2, h, w, 1.0, 0, P(gop), lp, None, st_))
+        return h, w, calls
+
+    for k in range(5):
+        h, w, calls = make_level(k)
+        by_level.append(dict(zip(names, calls)))
         for n, fn, bytes_pp in zip(names, calls, bpp):
             t = timeit(fn)
             tot[n] += t
@@ -429,10 +453,56 @@ def time_criterions(torch, lib, dev, B=BATCH, iters=9):
     cfg3 = tot["OBCC"] + tot["Smoothness(flow,L1)"] + tot["Smoothness(occ,Quadratic)"] + tot["OcclusionPrior"]
     cfg4 = (tot["OBGCC"] + tot["SecondOrderSmoothness"] + tot["Smoothness(occ,Quadratic)"] + tot["ConstVel"]
             + tot["OcclusionPrior"])
+    # the same calls the way a training step issues them (train.lua:416-475): all levels back to back on one stream,
+    # losses left on the device (loss_dev), L2 flushed once in front -- launch latency and the loss hand-off of one
+    # call overlap the next call's kernel instead of being counted once per call
+    def step_of(keys):
+        def run():
+            for lvl in by_level:
+                for n in keys:
+                    rc = lvl[n]()
+                    if rc:
+                        raise RuntimeError("criterion call failed: %d" % rc)
+            return 0
+        return run
+    hard = ("Smoothness(flow,L1)", "OBCC", "Smoothness(occ,Quadratic)", "OcclusionPrior")
+    soft = ("SecondOrderSmoothness", "ConstVel", "OBGCC", "Smoothness(occ,Quadratic)", "OcclusionPrior")
+    b2b3, b2b4 = timeit(step_of(hard)), timeit(step_of(soft))
+    # ... and captured once as a CUDA graph (every entry only enqueues work on the stream it is given when the
+    # loss stays on the device): the ~20 launches of a step cost one replay
+    gss = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    gs = gss[0]
+    gshs = [C.c_void_p(x.cuda_stream) for x in gss]
+    by_level_eager = by_level
+    by_level = [dict(zip(names, make_level(k, gshs)[2])) for k in range(5)]
+    graphs = {}
+    for key, keys in (("hard", hard), ("soft", soft)):
+        run = step_of(keys)
+        torch.cuda.synchronize()
+        run()                          # first call on every stream: kernel attributes, scratch buffers
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=gs):
+            # the criterion calls of a step are independent of each other (each reads the level's outputs and
+            # writes its own gradient): four streams, joined at the end
+            for x in gss[1:]:
+                x.wait_stream(gs)
+            run()
+            for x in gss[1:]:
+                gs.wait_stream(x)
+        graphs[key] = gr
+    g3 = timeit(lambda: (graphs["hard"].replay(), 0)[1])
+    g4 = timeit(lambda: (graphs["soft"].replay(), 0)[1])
+    by_level = by_level_eager
     return {"workload": "fused criterion calls (loss + gradients) of one training step, B=8, 320x640 .. 20x40, L2 flushed",
             "us_sum_over_5_levels": {n: round(v, 1) for n, v in tot.items()},
             "GBps_alg_at_320x640": top,
-            "config3_hard_step_us": round(cfg3, 1), "config4_soft_step_us": round(cfg4, 1)}
+            "config3_hard_step_us": round(cfg3, 1), "config4_soft_step_us": round(cfg4, 1),
+            "config3_hard_step_back_to_back_us": round(b2b3, 1), "config4_soft_step_back_to_back_us": round(b2b4, 1),
+            "config3_hard_step_graph_us": round(g3, 1), "config4_soft_step_graph_us": round(g4, 1),
+            "note": "step_us = sum of the calls timed one by one (L2 flushed before each); back_to_back = the step's calls "
+                    "issued in train.lua's order on one stream; graph = the same calls captured once over four streams "
+                    "(they are independent of each other) and replayed"}
 
 
 # ----------------------------------------------------------------------------------------
