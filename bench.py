@@ -120,10 +120,14 @@ class _Zero:
 class Workload:
     """Device buffers + the ordered list of C-ABI calls of one step."""
 
-    def __init__(self, torch, lib, dev, B=BATCH, seed=2):
+    def __init__(self, torch, lib, dev, B=BATCH, seed=2, full_hw=None):
         from back2future_b200 import _lib
         self.torch, self.lib, self.dev, self.B = torch, lib, dev, B
         g = torch.Generator(device=dev).manual_seed(seed)
+        HF, WF = full_hw or (H_FULL, W_FULL)      # network input size (a multiple of 64, back2future.lua:57-71)
+
+        def level_hw(l):
+            return HF >> (l - 1), WF >> (l - 1)
 
         def randn(*shape, scale=1.0):
             t = torch.randn(shape, device=dev, generator=g, dtype=torch.float32)
@@ -174,7 +178,7 @@ class Workload:
         # warp k belongs to pyramid level l = k + 3: it warps the image at the resolution of level l - 2 with the
         # skip-upsampled flow of level l (pwc.lua:441-446)
         warp_cfgs = [("feat L%d" % l, LEVEL_C[l], level_hw(l), ("fw", l)) for l in (6, 5, 4, 3)]
-        warp_cfgs += [("img %dx%d" % (H_FULL >> k, W_FULL >> k), 3, (H_FULL >> k, W_FULL >> k), ("iw", k + 3))
+        warp_cfgs += [("img %dx%d" % (HF >> k, WF >> k), 3, (HF >> k, WF >> k), ("iw", k + 3))
                       for k in (4, 3, 2, 1, 0)]
         for name, Cn, (h, w), wtag in warp_cfgs:
             for d, fr in ((1, "past"), (0, "fut")):
@@ -266,7 +270,7 @@ class Workload:
                 grid.copy_(f[None] + 0.05 * torch.randn(grid.shape, device=self.dev, generator=g))
 
     # -- CUDA graph of one step -------------------------------------------------------------
-    def capture(self, streams):
+    def capture(self, streams, forward_only=False):
         """Capture one step as a CUDA graph whose edges are the network's own data dependencies
         (models/pwc.lua:237-456), over six streams (the first one is the capture stream):
 
@@ -307,6 +311,8 @@ class Workload:
         with torch.cuda.graph(graph, stream=M):
             Z.wait_stream(M)
             for which, name, kind, mk, nbytes, flops, zero, tag in self._mk:
+                if forward_only:
+                    break
                 if zero is not None and lib.b2f_zero_async(zero[0], zero[1], H[Z]):
                     raise RuntimeError("b2f_zero_async failed during capture")
             # ---- forward
@@ -321,6 +327,9 @@ class Workload:
             M.wait_stream(I1)
             M.wait_stream(I2)
             M.wait_stream(Z)          # every scatter target is clean before the first backward kernel
+            if forward_only:          # inference (back2future.lua:74 model:forward): the forward half is the step
+                self.graph_schedule = sched
+                return graph
             # ---- backward
             I1.wait_stream(M)
             I2.wait_stream(M)
@@ -371,6 +380,48 @@ def breakdown(torch, wl, iters=10):
                      "GBps": round(op.bytes / ms / 1e6, 1) if ms > 0 else None,
                      "GFLOPs": round(op.flops / ms / 1e6, 1) if op.flops and ms > 0 else None})
     return rows
+
+
+# ----------------------------------------------------------------------------------------
+# inference shapes (BASELINE configs[0], [4]): hot-path-only, forward only, one triplet at a time
+# ----------------------------------------------------------------------------------------
+
+def time_inference(torch, lib, dev, reps=200):
+    """The hot-path calls of ONE inference forward (back2future.lua:74: both cost volumes of levels 7..3, the feature
+    warps, the image warps; no backward) at the sizes `computeFlow` feeds the network for BASELINE configs[0]
+    (1242x375 -> 1216x320) and configs[4] (1024x436 -> 1024x384), B = 1, synthetic features, as one CUDA-graph replay
+    per triplet.  The conv trunk is not part of this library, so this is the hot path's share of a
+    triplet, not whole-network triplets/s."""
+    out = {}
+    for key, hw in (("config0_1216x320", (320, 1216)), ("config4_1024x384", (384, 1024))):
+        wl = Workload(torch, lib, dev, B=1, full_hw=hw)
+        wl.bind(torch.cuda.current_stream().cuda_stream)
+        nf = len(wl.ops) // 2
+        for op in wl.ops[:nf]:           # eager forward once: kernel attributes, tensor maps
+            if op.call():
+                raise RuntimeError("%s failed: %s" % (op.name, lib.b2f_last_error().decode()))
+        torch.cuda.synchronize()
+        graph = wl.capture([torch.cuda.Stream(device=dev) for _ in range(6)], forward_only=True)
+        res = {"launches_per_triplet": nf, "alg_bytes_per_triplet": sum(op.bytes for op in wl.ops[:nf])}
+        for kind in ("smooth", "iid4"):
+            wl.set_flow(kind)
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / reps
+            res["us_per_triplet_%s_flow" % kind] = round(us, 1)
+        res["hot_path_triplets_per_s"] = round(1e6 / res["us_per_triplet_smooth_flow"], 1)
+        out[key] = res
+        del wl, graph
+    out["note"] = ("forward-only hot path of one triplet (B = 1) as one CUDA-graph replay; whole-network inference also "
+                   "needs the conv trunk (row N1, not in this library)")
+    return out
 
 
 # ----------------------------------------------------------------------------------------
@@ -958,6 +1009,7 @@ def main():
             flow_var[key] = round(fa.elapsed_time(fb) / 30, 4)
         wl.set_flow("iid4", seed=2)
     crit = time_criterions(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
+    infer = time_inference(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, desc, sps, n = time_cpu(args.cpu_budget)
@@ -989,7 +1041,7 @@ def main():
                                  "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
                                  "start of the step on their own stream"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "criterions": crit, "flow_variants": flow_var, "allreduce": allreduce,
+            "criterions": crit, "flow_variants": flow_var, "inference_shapes": infer, "allreduce": allreduce,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
