@@ -200,6 +200,30 @@ def test_costvol_auto_dispatch_level_shapes(env):
             assert o.rel_err(grads[0], ref[0]) < TOL and o.rel_err(grads[1], ref[1]) < TOL
 
 
+def test_costvol_and_warps_at_the_reference_sample_size(env):
+    """BASELINE configs[0]: the reference's own inference example (samples/frame_0009-0011.png, 1242x375 resized to
+    1216x320 by back2future.lua:57-71), B = 1.  Levels 6 and 7 are 38 and 19 pixels wide (not a multiple of 4): they take
+    the generic kernels, levels 3-5 the TMA kernels; feature warps at the same shapes."""
+    r = rng(16)
+    for Cn, h, w in [(32, 80, 304), (64, 40, 152), (96, 20, 76), (128, 10, 38), (192, 5, 19)]:
+        frames = [r.standard_normal((1, Cn, h, w)).astype(np.float32) for _ in range(2)]
+        wide = r.standard_normal((1, 162, h, w)).astype(np.float32)
+        for fwd, sl in ((True, slice(0, 81)), (False, slice(81, 162))):
+            out = _costvol_fwd(env, frames, 9, fwd, wide=True)
+            assert o.rel_err(out, o.costvol_forward(frames, 9, fwd)) < TOL
+            grads = _costvol_bwd(env, frames, wide, sl, 9, fwd)
+            ref = o.costvol_backward(frames, wide[:, sl], 9, fwd)
+            assert o.rel_err(grads[0], ref[0]) < TOL and o.rel_err(grads[1], ref[1]) < TOL
+        if Cn <= 128:
+            img = np.ascontiguousarray(frames[0].transpose(0, 2, 3, 1))
+            grid = (r.standard_normal((1, h, w, 2)) * 2).astype(np.float32)
+            go = r.standard_normal(img.shape).astype(np.float32)
+            wout, gi, gg = _warp(env, img, grid, go)
+            rgi, rgg = o.warp_backward(img, grid, go)
+            assert o.rel_err(wout, o.warp_forward(img, grid)) < TOL
+            assert o.rel_err(gi, rgi) < TOL and o.rel_err(gg, rgg) < TOL
+
+
 def test_costvol_delta_kat(env):
     """Derived known-answer test (models/CostVolMulti.lua:225-254 with two frames)."""
     ref = np.zeros((1, 1, 8, 8), np.float32)
