@@ -43,6 +43,24 @@ def warp(Cn, h, w):
     torch.cuda.synchronize()
 
 
+def warp_unit(Cn, h, w, scale):
+    """fused warpingUnit (row N2), smooth flow in network units"""
+    img = torch.randn((B, Cn, h, w), device=dev, generator=g)
+    go = torch.randn((B, Cn, h, w), device=dev, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+    k = w / 1024.0
+    flow = (torch.stack([6 * k * torch.sin(xs / (90 * k) + ys / (70 * k)) + 3 * k, 5 * k * torch.cos(xs / (60 * k) - ys / (110 * k))], 0)[None]
+            + 0.05 * torch.randn((B, 2, h, w), device=dev, generator=g)).contiguous() / scale
+    out, gi, gf = torch.empty_like(img), torch.zeros_like(img), torch.empty_like(flow)
+    for _ in range(reps):
+        _lib.check(lib.b2f_warp_bdhw_forward(P(img), P(flow), scale, P(out), B, Cn, h, w, None))
+        _lib.check(lib.b2f_warp_bdhw_backward(P(img), P(flow), scale, P(go), P(gi), P(gf), B, Cn, h, w, None))
+    torch.cuda.synchronize()
+
+
+if what == "wu":
+    warp_unit(32, 112, 256, 5.0)
+    warp_unit(3, 448, 1024, 20.0)
 if what in ("cv3", "all"):
     cv(32, 112, 256)
 if what in ("cv4", "all"):
