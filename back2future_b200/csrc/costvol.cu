@@ -378,6 +378,37 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     if constexpr (PIPE) {
       // stage the tile as [channel][row][32 columns] with the TMA 128-byte swizzle (16-byte chunk c of row R
       // sits at chunk c ^ (R & 7)): the eight rows of a quarter-warp hit eight different bank groups
+#ifndef B2F_CVF_WARP_STORE
+#define B2F_CVF_WARP_STORE 1
+#endif
+      if (B2F_CVF_WARP_STORE && (dbg & 4)) {
+        // Per-warp epilogue (tm_out is then the 5-D view (x, y, window row iy, window column ix, batch)): warp iy
+        // stages its nine planes ix*9+iy in its own [ix][row][128 B] region and issues its own bulk tensor store, so
+        // no warp waits for another one -- with 9 compute warps on 4 schedulers (3/2/2/2) the two CTA-wide barriers
+        // of the whole-tile store were the hottest spot of the kernel (15 % of the stall samples on the first STS
+        // behind the barrier).  Bulk async groups are per thread: lane 0 waits for ITS previous store only.
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        const uint32_t wbase = obase + (uint32_t)(iy * 9 * TH * 128);
+#pragma unroll
+        for (int ix = 0; ix < 9; ++ix) {
+          const uint32_t rowaddr = wbase + (uint32_t)((ix * TH + r) * 128);
+#pragma unroll
+          for (int q = 0; q < A / 4; ++q) {
+            const int d = SGN > 0 ? 8 - ix : ix;
+            const float4 v = make_float4(acc2.get(4 * q, d) * kinv, acc2.get(4 * q + 1, d) * kinv,
+                                         acc2.get(4 * q + 2, d) * kinv, acc2.get(4 * q + 3, d) * kinv);
+            sts128(rowaddr + 16u * (uint32_t)(((A / 4) * st + q) ^ r), v);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(dbg & 2)) {
+          if (nsplit == 1) tma_store_5d_addr(wbase, &tm_out, tx * cfg::TW, ty * TH, iy, 0, b);
+          else tma_reduce_add_5d_addr(wbase, &tm_out, tx * cfg::TW, ty * TH, iy, 0, b);
+          tma_store_commit();
+        }
+      } else {
       if (warp == 0) {   // the previous tile's TMA store must have finished reading the staging tile
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -400,6 +431,7 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         if (nsplit == 1) tma_store_4d_addr(obase, &tm_out, tx * cfg::TW, ty * TH, 0, b);
         else tma_reduce_add_4d_addr(obase, &tm_out, tx * cfg::TW, ty * TH, 0, b);
         tma_store_commit();
+      }
       }
     } else {
       const int y = ty * TH + r;
@@ -427,7 +459,7 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
       }
     }
   }
-  if (PIPE && warp == 0 && lane == 0) tma_store_wait_read();   // shared memory must outlive the last store
+  if (PIPE && lane == 0) tma_store_wait_read();   // shared memory must outlive the last store (of every warp)
 }
 }  // namespace cvf
 
@@ -730,12 +762,25 @@ int launch_fwd_tma(const float* ref, const float* frm, float* out, int64_t obs, 
   int rc = make_tmap4(&tr, ref, dims, str, box_r);
   if (rc) return rc;
   if ((rc = make_tmap4(&tf, frm, dims, str, box_f))) return rc;
-  CUtensorMap to = tr;   // PIPE only: (W, H, 81, B) view of the output, 128-byte swizzled 32 x 8 x 81 boxes
+  CUtensorMap to = tr;   // PIPE only: view of the output for the staged TMA store
+  bool warp_store = false;
   if (PIPE) {
-    const uint64_t odims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
-    const uint64_t ostr[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)obs};
-    const uint32_t box_o[4] = {(uint32_t)cfg::TW, (uint32_t)cvf::TH, 81, 1};
-    if ((rc = make_tmap4(&to, out, odims, ostr, box_o, true))) return rc;
+    // per-warp stores: (x, y, window row iy, window column ix, batch) view, one 32 x 8 x 1 x 9 box per compute warp
+    // (channel = ix*9 + iy); B2F_CVF_TILE_STORE=1 or a refused 5-D encode falls back to one 32 x 8 x 81 box per tile
+    static const bool tile_store = [] { const char* e = getenv("B2F_CVF_TILE_STORE"); return e && e[0] == '1'; }();
+    if (!tile_store) {
+      const uint64_t hw = (uint64_t)W * H;
+      const uint64_t odims5[5] = {(uint64_t)W, (uint64_t)H, 9, 9, (uint64_t)B};
+      const uint64_t ostr5[4] = {(uint64_t)W, hw, 9 * hw, (uint64_t)obs};
+      const uint32_t box5[5] = {(uint32_t)cfg::TW, (uint32_t)cvf::TH, 1, 9, 1};
+      warp_store = make_tmap5(&to, out, odims5, ostr5, box5, true) == B2F_OK;
+    }
+    if (!warp_store) {
+      const uint64_t odims[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+      const uint64_t ostr[3] = {(uint64_t)W, (uint64_t)W * H, (uint64_t)obs};
+      const uint32_t box_o[4] = {(uint32_t)cfg::TW, (uint32_t)cvf::TH, 81, 1};
+      if ((rc = make_tmap4(&to, out, odims, ostr, box_o, true))) return rc;
+    }
   }
   auto kern = cvf::costvol_fwd_tma<A, SGN, PIPE>;
   static thread_local int attr_dev = -1;
@@ -755,7 +800,7 @@ int launch_fwd_tma(const float* ref, const float* frm, float* out, int64_t obs, 
   if (ntiles > 0x3fffffff) return fail(B2F_EINVAL, "costvol_forward: too many tiles");
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * cfg::CTAS_PER_SM);
   const int path = costvol_path();
-  const int dbg = (path >= 8 && path <= 10) ? path - 7 : 0;   // 8: no arithmetic, 9: no stores, 10: neither
+  const int dbg = ((path >= 8 && path <= 10) ? path - 7 : 0) | (warp_store ? 4 : 0);   // 8: no arithmetic, 9: no stores, 10: neither; bit 2: per-warp stores
   kern<<<grid, cvf::THREADS, cfg::SMEM_BYTES, st>>>(tr, tf, to, out, obs, C, H, W, kdiv, nsplit, cps, ntx, nty,
                                                     (int)ntiles, dbg);
   B2F_CHECK_LAUNCH("costvol_fwd_tma");

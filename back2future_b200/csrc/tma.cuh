@@ -50,7 +50,7 @@ inline int make_tmap4(CUtensorMap* tm, const float* base, const uint64_t dims[4]
 
 // 5-D variant (the gradOut slab: x, y, window row, window column, batch)
 inline int make_tmap5(CUtensorMap* tm, const float* base, const uint64_t dims[5],
-                      const uint64_t strides_elems[4], const uint32_t box[5]) {
+                      const uint64_t strides_elems[4], const uint32_t box[5], bool swizzle128 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2F_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5] = {dims[0], dims[1], dims[2], dims[3], dims[4]};
@@ -58,8 +58,8 @@ inline int make_tmap5(CUtensorMap* tm, const float* base, const uint64_t dims[5]
   cuuint32_t bx[5] = {box[0], box[1], box[2], box[3], box[4]};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2F_EINVAL, "cuTensorMapEncodeTiled (5-D) failed with CUresult %d", (int)r);
   return B2F_OK;
 }
@@ -145,6 +145,18 @@ __device__ __forceinline__ void tma_store_4d_addr(uint32_t smem_src, const CUten
                                                   int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d_addr(uint32_t smem_src, const CUtensorMap* tm, int c0, int c1, int c2,
+                                                  int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_5d_addr(uint32_t smem_src, const CUtensorMap* tm, int c0, int c1,
+                                                       int c2, int c3, int c4) {
+  asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tma_reduce_add_4d_addr(uint32_t smem_src, const CUtensorMap* tm, int c0, int c1,
