@@ -858,8 +858,10 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
       if (2 * t <= sms || path == 5) nsplit = (int)std::min<int64_t>(nchunks, std::max<int64_t>(path == 5 ? 2 : 1, sms / t));
       if ((int64_t)B * nsplit > 65535) nsplit = 1;
     }
-    // software-pipelined single-CTA form once every SM gets at least two tiles (path 6 forces it, 7 forbids)
-    const bool pipe = path == 6 || (path >= 8 && path <= 10) || (path != 7 && tiles_for(A, B, H, W) * nsplit >= 2 * (int64_t)sms);
+    // software-pipelined single-CTA form from 1.5 tiles per SM on (path 6 forces it, 7 forbids); measured with the
+    // per-warp epilogue: level 4 of the benchmark (224 tiles on 148 SMs) 30.7-32.8 us against 32.8-34.8 us for the
+    // two-CTAs-per-SM form, level 5 (64 tiles) 24.5 against 18.4 us
+    const bool pipe = path == 6 || (path >= 8 && path <= 10) || (path != 7 && 2 * tiles_for(A, B, H, W) * nsplit >= 3 * (int64_t)sms);
     if (A == 8)
       return pipe ? launch_fwd_sgn<8, true>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st)
                   : launch_fwd_sgn<8, false>(sgn, frames[0], frames[1], out, obs, B, C, H, W, kdiv, nsplit, st);

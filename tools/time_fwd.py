@@ -5,6 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from back2future_b200 import _lib
 lib = _lib.load()
+if os.environ.get('B2F_PATH'):
+    lib.b2f_debug_costvol_path(int(os.environ['B2F_PATH']))
 dev = torch.device("cuda:0")
 B = 8
 P = lambda t: C.c_void_p(t.data_ptr())
