@@ -583,6 +583,26 @@ __device__ __forceinline__ void slab_fma(float (&acc)[CG][8], const float (&g)[9
 #endif
 }
 
+// Timeline instrumentation (tools/cvb_trace.py; only in builds with -DB2F_CVB_TRACE, tools/build_variants.sh): lane 0
+// of every warp stores clock64 stamps -- 32 slots per warp, 8 warps per CTA -- into the buffer registered with
+// b2f_debug_cvb_trace.  clock64 is per SM: stamps of CTAs with the same %smid (slot 1) share a time base.
+#ifdef B2F_CVB_TRACE
+__device__ unsigned long long* g_cvb_trace;
+#define CVB_STAMP(k)                                                                                         \
+  do {                                                                                                       \
+    if (lane == 0 && g_cvb_trace)                                                                            \
+      g_cvb_trace[((size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + warp) * 32 + (k)] = clock64(); \
+  } while (0)
+#define CVB_STAMP_VAL(k, v)                                                                                  \
+  do {                                                                                                       \
+    if (lane == 0 && g_cvb_trace)                                                                            \
+      g_cvb_trace[((size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + warp) * 32 + (k)] = (v); \
+  } while (0)
+#else
+#define CVB_STAMP(k) do {} while (0)
+#define CVB_STAMP_VAL(k, v) do {} while (0)
+#endif
+
 template <int SGN, int TW, int NSLAB>
 __global__ void __launch_bounds__((Cfg<TW, NSLAB>::THREADS), (Cfg<TW, NSLAB>::CTAS_PER_SM))
 costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_constant__ CUtensorMap tm_ref,
@@ -620,6 +640,18 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
   }
   __syncthreads();
 
+  CVB_STAMP(0);
+#ifdef B2F_CVB_TRACE
+  {
+    unsigned sm_, gt_lo, gt_hi;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+    unsigned long long gt_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
+    (void)gt_lo; (void)gt_hi;
+    CVB_STAMP_VAL(1, (unsigned long long)sm_);
+    CVB_STAMP_VAL(30, gt_);
+  }
+#endif
   if (warp == NCW) {  // ---- TMA producer ----
     // NOTE: tensor maps are addressed as kernel parameters at every use (a runtime-selected descriptor
     // pointer is not a constant-bank address any more and the TMA faults).
@@ -640,6 +672,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
         }
       };
       load_slab(0);
+      CVB_STAMP(2);
       // X halo tile, per channel group as two 8-row boxes with their own barriers, the half that window row 0 reads
       // first for every group: slab 0 touches rows 0..7 (T > 0) or 8..15 (T < 0) only, so a warp starts after a
       // quarter of the box rows it used to wait for (the wait for the whole 16-row box was the hottest instruction
@@ -655,9 +688,11 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
           else           tma_load_4d(dst, &tm_ref, x0 - 4, y0 - 4 + 8 * hf, c0 + w * CG, b, &xfull[2 * w + hf]);
         }
       }
+      CVB_STAMP(20);
       for (int iy = 1; iy < 9; ++iy) {
         if (iy >= NSLAB) mbar_wait(&gempty[iy % NSLAB], ((iy / NSLAB) - 1) & 1);
         load_slab(iy);
+        CVB_STAMP(2 + iy);
       }
     }
     return;
@@ -680,6 +715,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     if (iy == 0) mbar_wait(&xfull[2 * cg + (T > 0 ? 0 : 1)], 0);
     if (iy == 1) mbar_wait(&xfull[2 * cg + (T > 0 ? 1 : 0)], 0);
     mbar_wait(&gfull[s], (iy / NSLAB) & 1);
+    CVB_STAMP(2 + 2 * iy);
     const int xrow = r + 4 + T * (iy - 4);     // 0..15: half = row / 8, layout [half][channel][8 rows][XW]
     const float* xs = xbase + (xrow >> 3) * cfg::XH_ELEMS + (xrow & 7) * XW;
     float g[9][8];
@@ -692,6 +728,7 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     if (dbg & 1) continue;   // measurement aid: feed only
     if (T > 0) slab_fma<cfg, 1>(acc, g, xs);
     else       slab_fma<cfg, -1>(acc, g, xs);
+    CVB_STAMP(3 + 2 * iy);
   }
 
   // ---- epilogue ----
@@ -721,10 +758,13 @@ costvol_bwd_tma(const __grid_constant__ CUtensorMap tm_frame, const __grid_const
     if (role == 0) tma_store_4d_addr(wbase, &tm_gref, x0 + 32 * half, y0, c0 + cg * CG, b);
     else           tma_store_4d_addr(wbase, &tm_gfrm, x0 + 32 * half, y0, c0 + cg * CG, b);
     tma_store_commit();
+    CVB_STAMP(20);
     tma_store_wait_read();   // shared memory must outlive the store's read
   }
+  CVB_STAMP(21);
 }
 }  // namespace cvb
+
 
 // =======================================================================================
 // host dispatch
@@ -985,3 +1025,9 @@ extern "C" int b2f_costvol_backward(const float* const* frames, int F, int B, in
   }
   return B2F_OK;
 }
+
+#ifdef B2F_CVB_TRACE
+extern "C" __attribute__((visibility("default"))) int b2f_debug_cvb_trace(void* buf) {
+  return (int)cudaMemcpyToSymbol(cvb::g_cvb_trace, &buf, sizeof(buf));
+}
+#endif
