@@ -28,7 +28,7 @@ gr, gf = torch.empty_like(ref), torch.empty_like(frm)
 fp = _lib.ptr_array([ref.data_ptr(), frm.data_ptr()])
 gp = _lib.ptr_array([gr.data_ptr(), gf.data_ptr()])
 P = lambda t: C.c_void_p(t.data_ptr())
-lib.b2f_debug_costvol_path(14)
+lib.b2f_debug_costvol_path(int(os.environ.get("B2F_PATH", "14")))
 run = lambda: _lib.check(lib.b2f_costvol_backward(fp, 2, B, Cn, h, w, 9, 1, P(gj), gj.stride(0), gp, None))
 for _ in range(3):
     run()
