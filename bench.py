@@ -667,6 +667,15 @@ class CpuArm:
         self.lib = C.CDLL(path)
         self.lib.b2fcpu_costvol_backward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                      C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 for N > 1, which would time
+        # the reference arm on one core
+        try:
+            usable = len(os.sched_getaffinity(0))
+        except AttributeError:
+            usable = os.cpu_count() or 1
+        self.lib.b2fcpu_set_num_threads.argtypes = [C.c_int]
+        self.lib.b2fcpu_set_num_threads.restype = None
+        self.lib.b2fcpu_set_num_threads(usable)
         self.cores = self.lib.b2fcpu_num_threads()
         self.np = np
         rng = np.random.default_rng(seed)
