@@ -560,6 +560,71 @@ def time_criterions(torch, lib, dev, B=BATCH, iters=9):
 # e2e: module API, host buffers
 # ----------------------------------------------------------------------------------------
 
+def _gpu_local_cpus(torch, dev):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        bus = None
+        pr = torch.cuda.get_device_properties(idx)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        else:
+            buf = C.create_string_buffer(32)
+            for name in ("libcudart.so.12", "libcudart.so"):
+                try:
+                    rt = C.CDLL(name)
+                    if rt.cudaDeviceGetPCIBusId(buf, 32, C.c_int(idx)) == 0:
+                        bus = buf.value.decode().lower()
+                        break
+                except OSError:
+                    continue
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:      # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        return cpus or None
+    except Exception:
+        return None
+
+
+class _NumaLocal:
+    """While pinned host buffers are allocated: run on the CPUs next to the GPU, so that the pages are taken from
+    that NUMA node (first touch) and the H2D / D2H copies of several ranks do not cross the socket interconnect."""
+
+    def __init__(self, torch, dev):
+        self.prev = None
+        self.bound = 0
+        try:
+            cur = os.sched_getaffinity(0)
+            local = _gpu_local_cpus(torch, dev)
+            want = (local & cur) if local else None
+            if want and len(want) < len(cur):
+                self.prev = cur
+                os.sched_setaffinity(0, want)
+                self.bound = len(want)
+        except Exception:
+            self.prev = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+        return False
+
+
 class E2E:
     """The same pass through back2future_b200.nn with pinned HOST inputs and outputs.
 
@@ -586,6 +651,17 @@ class E2E:
         def dev_like(ts):
             return [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in ts]
 
+        with _NumaLocal(torch, dev) as numa:
+            self.numa_cpus = numa.bound
+            self._alloc(bnn, B, pin, pin_out, dev_like)
+        for it in self.items:
+            self.h2d += sum(t.numel() * 4 for t in it[2])
+            self.d2h += sum(t.numel() * 4 for t in it[3])
+        self.ev_cmp = [None] * len(self.items)
+        self.ev_out = [None] * len(self.items)
+
+    def _alloc(self, bnn, B, pin, pin_out, dev_like):
+        torch, dev = self.torch, self.dev
         for l in (7, 6, 5, 4, 3):
             Cn = LEVEL_C[l]
             h, w = level_hw(l)
@@ -599,11 +675,6 @@ class E2E:
                 hin = [pin(B, h, w, Cn), pin(B, h, w, 2, scale=4.0), pin(B, h, w, Cn)]
                 hout = [pin_out(B, h, w, Cn), pin_out(B, h, w, Cn), pin_out(B, h, w, 2)]
                 self.items.append(["warp", bnn.BilinearSamplerBHWD(), hin, hout, dev_like(hin), None])
-        for it in self.items:
-            self.h2d += sum(t.numel() * 4 for t in it[2])
-            self.d2h += sum(t.numel() * 4 for t in it[3])
-        self.ev_cmp = [None] * len(self.items)
-        self.ev_out = [None] * len(self.items)
 
     def step(self):
         """One pass.  Nothing here waits for the host: the three streams are ordered by per-item events only
@@ -945,7 +1016,9 @@ def main():
         e2e = {"value": round(world * BATCH * args.e2e_steps / (ems / 1e3), 2), "unit": UNIT,
                "h2d_bytes_per_step": ee.h2d, "d2h_bytes_per_step": ee.d2h, "steps": args.e2e_steps,
                "ms_per_step": round(ems / args.e2e_steps, 3),
-               "api": "back2future_b200.nn.CostVolMulti / BilinearSamplerBHWD updateOutput+updateGradInput"}
+               "api": "back2future_b200.nn.CostVolMulti / BilinearSamplerBHWD updateOutput+updateGradInput",
+               # CPUs this rank was bound to while it allocated its pinned buffers (GPU-local NUMA node), 0 = not bound
+               "pinned_alloc_numa_cpus": ee.numa_cpus}
         del ee
 
     # ---- training path only: the gradient all-reduce next to / under the hot-path step, N > 1 ----
@@ -1049,7 +1122,14 @@ def main():
                                  "level, the level's image warps (leaves of the loss) on side streams under the next level's "
                                  "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
                                  "start of the step on their own stream"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+            # every hot kernel against the same HBM peak (separate pass with events around each call, one call at a
+            # time: the isolated times behind the stderr table; `roofline` above is the cost-volume kernel BASELINE's
+            # metric names, the C = 3 image-warp backward is as long per launch)
+            "roofline_by_kernel": ([{"kernel": r["kernel"], "ms": r["ms"], "GBps": r["GBps"],
+                                     "frac": round(r["GBps"] / roof["peak"], 4) if (r["GBps"] and roof and roof.get("peak")) else None}
+                                    for r in sorted(rows, key=lambda r: -r["ms"])[:12]] if rows else None),
+            "cpu_baseline": cpu,
             "criterions": crit, "flow_variants": flow_var, "inference_shapes": infer, "allreduce": allreduce,
         }
         print(json.dumps(line), flush=True)
