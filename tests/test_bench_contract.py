@@ -28,7 +28,8 @@ def test_network_order_respects_the_dataflow_of_pwc_lua():
 
 
 def test_reference_arm_prints_one_json_line_without_a_gpu():
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    # OMP_NUM_THREADS=1 is what torchrun exports for N > 1: the arm must still use every core it may run on
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
@@ -37,5 +38,17 @@ def test_reference_arm_prints_one_json_line_without_a_gpu():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "frame_triplets_per_sec_1024x448" and d["unit"] == "triplets/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_gpu_local_cpu_list_parsing_is_defensive():
+    """bench._gpu_local_cpus returns None (no binding) when there is no GPU / no sysfs entry instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import torch
+    assert bench._gpu_local_cpus(torch, torch.device("cuda:0")) is None or isinstance(
+        bench._gpu_local_cpus(torch, torch.device("cuda:0")), set)
+    with bench._NumaLocal(torch, torch.device("cuda:0")) as n:
+        assert n.bound >= 0
+    assert os.sched_getaffinity(0)   # affinity restored / untouched
