@@ -9,11 +9,12 @@ SRCS      := $(CSRC)/api.cu $(CSRC)/costvol.cu $(CSRC)/warp.cu $(CSRC)/criterion
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := back2future_b200/libb2f_cuda.so
 ORACLE    := oracle/c/libb2f_cpu.so
+CHECK64   := oracle/c/libb2f_check64.so
 # the reference's own sampler (test-only parity pin), compiled from where it lies; only when the reference is mounted
 REFROOT   ?= /root/reference
 REFLIB    := oracle/_ref/libstn_ref.so
 
-all: $(LIB) $(ORACLE)
+all: $(LIB) $(ORACLE) $(CHECK64)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh include/b2f.h
 	@mkdir -p $(OBJDIR)
@@ -25,6 +26,10 @@ $(LIB): $(OBJS)
 $(ORACLE): oracle/c/b2f_cpu.c
 	$(HOSTCC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -fvisibility=hidden -o $@ $< -lm
 
+# float64 closed-form checker used for the full-size parity gates (tests/test_bench_parity.py, bench.py `parity`)
+$(CHECK64): oracle/c/b2f_check64.c
+	$(HOSTCC) -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp -fPIC -shared -fvisibility=hidden -o $@ $< -lm
+
 # Reference sampler: unmodified extras/stnbhwd/{utils.c,BilinearSamplerBHWD.cu} against the stand-in Torch7
 # headers in oracle/ref_shim (the reference's own CMake build wants luarocks + TH/THC/luaT and -arch=sm_30).
 $(REFLIB): oracle/ref_shim/stn_ref.cu $(wildcard oracle/ref_shim/*.h)
@@ -35,6 +40,6 @@ $(REFLIB): oracle/ref_shim/stn_ref.cu $(wildcard oracle/ref_shim/*.h)
 ref: $(REFLIB)
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(ORACLE)
+	rm -rf $(OBJDIR) $(LIB) $(ORACLE) $(CHECK64)
 
 .PHONY: all clean ref

@@ -56,6 +56,7 @@ const char* b2f_status_string(int status) {
 }
 
 int b2f_release_scratch(void) { return b2f::release_scratch_for_thread(); }
+int b2f_reserve_scratch(size_t bytes) { return b2f::reserve_scratch_for_thread(bytes); }
 
 int b2f_debug_costvol_path(int mode) {
   int prev = b2f::g_force_generic;

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace b2f {
 namespace {
@@ -66,6 +67,17 @@ __device__ __forceinline__ void finish_loss(float local, const LossOut& lo) {
 // (calls on one stream are ordered, so reuse is safe); b2f_release_scratch() frees the calling thread's
 // buffers.  (A per-call cudaMallocAsync/cudaFreeAsync pair cost milliseconds: the default pool's release
 // threshold is 0, so every synchronisation handed the memory back to the driver.)
+//
+// Lifetime rules that make the scratch safe under CUDA graphs (a captured kernel node has its partials / ticket /
+// result pointers baked in):
+//   * nothing is ever freed before b2f_release_scratch(): a buffer that has to grow is RETIRED, not freed, and no
+//     entry is evicted, so a graph captured earlier never replays into freed memory;
+//   * a call issued while its stream is CAPTURING gets a slice of its own from the graph arena reserved with
+//     b2f_reserve_scratch() (bump-allocated, never reused), so a replay on any stream cannot race with eager
+//     criterion calls -- or with another captured call -- on the ticket counter.  Without a reserved arena the
+//     captured call falls back to the capture stream's buffer (which must then already be large enough:
+//     allocating is illegal during capture) and the caller must not run eager criterion calls on that stream
+//     while the graph replays.
 struct ScratchEntry {
   int dev;
   cudaStream_t st;
@@ -73,8 +85,10 @@ struct ScratchEntry {
   size_t bytes;
 };
 struct ScratchCache {
-  ScratchEntry e[16];
-  int n = 0;
+  std::vector<ScratchEntry> e;
+  std::vector<void*> retired;          // outgrown buffers, kept alive for graphs captured earlier
+  struct Arena { int dev; char* mem; size_t bytes, used; };
+  std::vector<Arena> arenas;           // graph arenas (b2f_reserve_scratch), one or more per device
   ~ScratchCache() {}   // device memory is released explicitly (b2f_release_scratch) or at process exit
 };
 thread_local ScratchCache g_scratch;
@@ -84,25 +98,31 @@ int get_scratch(size_t bytes, cudaStream_t st, void** out) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
   ScratchCache& c = g_scratch;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+  if (cap == cudaStreamCaptureStatusActive) {
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    for (auto& a : c.arenas)
+      if (a.dev == dev && a.bytes - a.used >= need) {
+        *out = a.mem + a.used;      // zeroed at reserve time; every kernel leaves its ticket at zero
+        a.used += need;
+        return B2F_OK;
+      }
+  }
   int slot = -1;
-  for (int i = 0; i < c.n; ++i)
-    if (c.e[i].dev == dev && c.e[i].st == st) slot = i;
+  for (size_t i = 0; i < c.e.size(); ++i)
+    if (c.e[i].dev == dev && c.e[i].st == st) slot = (int)i;
   if (slot < 0) {
-    if (c.n == 16) {   // evict the oldest entry
-      cudaFree(c.e[0].mem);
-      for (int i = 1; i < 16; ++i) c.e[i - 1] = c.e[i];
-      c.n = 15;
-    }
-    slot = c.n++;
-    c.e[slot] = {dev, st, nullptr, 0};
+    slot = (int)c.e.size();
+    c.e.push_back({dev, st, nullptr, 0});
   }
   ScratchEntry& s = c.e[slot];
   if (s.bytes < bytes) {
+    if (cap == cudaStreamCaptureStatusActive)
+      return fail(B2F_ENOMEM, "criterion scratch: %zu bytes needed while the stream is capturing; call "
+                  "b2f_reserve_scratch() before the capture (allocation is illegal during capture)", bytes);
     if (s.mem) {
-      // earlier kernels on this stream may still be using the old buffer
-      e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize(scratch grow)");
-      cudaFree(s.mem);
+      c.retired.push_back(s.mem);   // a graph captured earlier may still point into it
       s.mem = nullptr;
       s.bytes = 0;
     }
@@ -152,9 +172,27 @@ struct LossScratch {
 
 int release_scratch_for_thread() {
   ScratchCache& c = g_scratch;
-  for (int i = 0; i < c.n; ++i)
-    if (c.e[i].mem) cudaFree(c.e[i].mem);
-  c.n = 0;
+  for (auto& en : c.e)
+    if (en.mem) cudaFree(en.mem);
+  for (void* p : c.retired) cudaFree(p);
+  for (auto& a : c.arenas) cudaFree(a.mem);
+  c.e.clear();
+  c.retired.clear();
+  c.arenas.clear();
+  return B2F_OK;
+}
+
+int reserve_scratch_for_thread(size_t bytes) {
+  if (bytes == 0) return fail(B2F_EINVAL, "b2f_reserve_scratch: bytes must be positive");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  void* mem = nullptr;
+  e = cudaMalloc(&mem, bytes);
+  if (e != cudaSuccess) return fail(B2F_ENOMEM, "b2f_reserve_scratch: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(mem, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(mem); return cuda_fail(e, "cudaMemset(graph arena)"); }
+  g_scratch.arenas.push_back({dev, reinterpret_cast<char*>(mem), bytes, 0});
   return B2F_OK;
 }
 

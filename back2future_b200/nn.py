@@ -47,8 +47,22 @@ def _dev(t, what):
 
 
 def _contig(t, what):
+    """The C ABI takes dense tensors.  A strided view is REJECTED, not copied: `.contiguous()` would launch a torch
+    kernel on the product path (north_star: torch owns memory and streams, it does not launch work).  The Lua shims
+    call :contiguous() at the same places, i.e. there the copy is the caller's Torch7, as in the reference."""
     _dev(t, what)
-    return t if t.is_contiguous() else t.contiguous()
+    if not t.is_contiguous():
+        raise ValueError("%s: non-contiguous tensor (strides %r for shape %r); pass a dense tensor -- this path does "
+                         "not copy behind the caller's back" % (what, tuple(t.stride()), tuple(t.shape)))
+    return t
+
+
+def _zeros_like(t):
+    """A zero-filled buffer without a torch kernel: torch allocates, b2f_zero_async (cudaMemsetAsync on the
+    current stream) fills -- what `gradInput:zero()` is in the reference's wrapper (BilinearSamplerBHWD.lua:99-102)."""
+    z = torch.empty_like(t)
+    _lib.check(_lib.load().b2f_zero_async(_p(z), z.numel() * 4, _stream()))
+    return z
 
 
 def _p(t):
@@ -201,7 +215,7 @@ class CostVolMulti(Module):
 
     def updateGradInput(self, input, gradOutput):
         """CostVolMulti.lua:111-181.  ``gradOutput`` may be a narrow of a wider buffer (batch-
-        strided); anything else non-contiguous is copied first."""
+        strided); anything else non-contiguous is rejected."""
         lib = _lib.load()
         frames = self._check(input)
         B, Cn, h, w = frames[0].shape
@@ -209,7 +223,8 @@ class CostVolMulti(Module):
         go = _dev(gradOutput, "CostVolMulti gradOutput")
         assert tuple(go.shape) == (B, ww, h, w), "gradOutput size mismatch"
         if go.stride()[1:] != (h * w, w, 1):
-            go = go.contiguous()
+            raise ValueError("CostVolMulti gradOutput: only a batch-strided (B, win*win, h, w) view is accepted, got "
+                             "strides %r" % (tuple(go.stride()),))
         gbs = go.stride(0) if B > 1 else ww * h * w
         if len(self.gradInput) != len(frames):
             self.gradInput = [torch.empty(0) for _ in frames]
@@ -257,7 +272,7 @@ class BilinearSamplerBHWD(Module):
         img = _img.unsqueeze(0) if squeeze else _img
         grid = _grid.unsqueeze(0) if squeeze else _grid
         self.check((img, grid))
-        grid = grid if grid.is_contiguous() else grid.contiguous()
+        grid = _contig(grid, "grids")
         B, H, W, Cn = img.shape
         _, Hg, Wg, _ = grid.shape
         if self.output.shape != (B, Hg, Wg, Cn) or self.output.device != img.device:
@@ -278,11 +293,11 @@ class BilinearSamplerBHWD(Module):
         grid = _grid.unsqueeze(0) if squeeze else _grid
         go = _go.unsqueeze(0) if squeeze else _go
         self.check((img, grid), go)
-        grid = grid if grid.is_contiguous() else grid.contiguous()
-        go = go if go.is_contiguous() else go.contiguous()
+        grid = _contig(grid, "grids")
+        go = _contig(go, "gradOutput")
         B, H, W, Cn = img.shape
         _, Hg, Wg, _ = grid.shape
-        gimg = torch.zeros_like(img)
+        gimg = _zeros_like(img)
         ggrid = torch.empty_like(grid)
         _lib.check(lib.b2f_warp_bhwd_backward(_p(img), _p(grid), _p(go), None if only_grid else _p(gimg),
                                               _p(ggrid), B, H, W, Cn, Hg, Wg, _stream()))
@@ -314,8 +329,7 @@ class WarpingUnit(Module):
         lib = _lib.load()
         I, F = _dev(input[0], "I"), _dev(input[1], "F")
         self.check((I, F))
-        I = I if I.is_contiguous() else I.contiguous()
-        F = F if F.is_contiguous() else F.contiguous()
+        I, F = _contig(I, "I"), _contig(F, "F")
         B, Cn, H, W = I.shape
         if self.output.shape != I.shape or self.output.device != I.device:
             self.output = torch.empty_like(I)
@@ -326,11 +340,9 @@ class WarpingUnit(Module):
         lib = _lib.load()
         I, F, go = _dev(input[0], "I"), _dev(input[1], "F"), _dev(gradOutput, "gradOutput")
         self.check((I, F), go)
-        I = I if I.is_contiguous() else I.contiguous()
-        F = F if F.is_contiguous() else F.contiguous()
-        go = go if go.is_contiguous() else go.contiguous()
+        I, F, go = _contig(I, "I"), _contig(F, "F"), _contig(go, "gradOutput")
         B, Cn, H, W = I.shape
-        gI = torch.zeros_like(I)
+        gI = _zeros_like(I)
         gF = torch.empty_like(F)
         _lib.check(lib.b2f_warp_bdhw_backward(_p(I), _p(F), self.flow_scale, _p(go), None if only_grid else _p(gI),
                                               _p(gF), B, Cn, H, W, _stream()))
@@ -343,11 +355,24 @@ class WarpingUnit(Module):
 # ---------------------------------------------------------------------------------------
 
 class Criterion:
+    """nn.Criterion protocol.
+
+    The reference's criterions recompute everything in updateGradInput (e.g. OBCCriterion.lua:121-240), and so do
+    these by default: updateOutput runs the fused kernel without gradient outputs (loss only), updateGradInput runs
+    it again with them.  Nothing computed in the forward is handed out later, so a buffer that was rewritten in
+    between -- through this library's raw pointers, invisibly to torch's version counters -- is always seen.
+
+    `fuse_backward = True` (an extension, off by default) makes updateOutput produce the gradients in the same
+    pass and updateGradInput hand them out, IF it is called with the very same objects (`is`) and unchanged
+    criterion fields; the caller then guarantees that the buffers are not rewritten between the two calls, which is
+    train.lua's pattern (forward at :428-444 immediately followed by backward at :445-475)."""
+
+    fuse_backward = False
+
     def __init__(self):
         self.output = 0
         self.gradInput = torch.empty(0)
-        self._cache_key = None
-        self._cache = None
+        self._held = None       # (objects, params, grads) of the last fused forward
 
     def forward(self, input, target=None):
         return self.updateOutput(input, target)
@@ -363,15 +388,24 @@ class Criterion:
 
     def clear(self):
         """The non-standard :clear() train.lua calls after each level (train.lua:433, 454, 461)."""
-        self._cache_key = None
-        self._cache = None
+        self._held = None
 
-    # The reference recomputes everything in updateGradInput; the fused kernel already produced
-    # the gradients during updateOutput, so they are handed out if the inputs are the very same
-    # buffers at the same version, and recomputed otherwise.
-    @staticmethod
-    def _key(tensors):
-        return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors if t is not None)
+    def _params(self):
+        return ()
+
+    def _hold(self, objects, grads):
+        self._held = (tuple(objects), self._params(), grads) if self.fuse_backward else None
+
+    def _take(self, objects):
+        """Gradients of the fused forward if it saw exactly these objects and fields; None otherwise."""
+        held, self._held = self._held, None
+        if held is None or not self.fuse_backward:
+            return None
+        objs, params, grads = held
+        objects = tuple(objects)
+        if len(objs) != len(objects) or any(a is not b for a, b in zip(objs, objects)) or params != self._params():
+            return None
+        return grads
 
 
 def _loss_call(fn, *args):
@@ -398,44 +432,48 @@ class _OBBase(Criterion):
         self.beta = 1.0
         self.gamma = 1.0
 
-    def _run(self, input, target):
+    def _params(self):
+        return (self._gradient_terms, _pen(self.p), float(self.penalty_out), float(self.alpha), float(self.beta),
+                float(self.gamma), float(self.pwc_flow_scaling), bool(self.past_flow), bool(self.gradCheck),
+                bool(self.sizeAverage), int(self.F))
+
+    def _objects(self, input, target):
+        warp_start = 3 if self.past_flow else 2  # 0-based index of the first warped frame
+        return [input[0], input[1] if self.past_flow else None, input[warp_start - 1], input[warp_start],
+                input[warp_start + 1], target]
+
+    def _run(self, input, target, want_grads):
         lib = _lib.load()
         assert len(input) >= 4, "expecting at least four inputs"
-        warp_start = 3 if self.past_flow else 2  # 0-based index of the first warped frame
         if self.F != 3:
             raise _lib.B2FError(-2, "OBCC/OBGCC: only F = 3 (two warped frames) is implemented, got F=%r" % self.F)
-        flow = _contig(input[0], "flow")
-        bflow = _contig(input[1], "bflow") if self.past_flow else None
-        occ = _contig(input[warp_start - 1], "occ")
-        wp = _contig(input[warp_start], "warped frame 1")
-        wf = _contig(input[warp_start + 1], "warped frame 2")
-        tgt = _contig(target, "target")
+        o_flow, o_bflow, o_occ, o_wp, o_wf, o_tgt = self._objects(input, target)
+        flow = _contig(o_flow, "flow")
+        bflow = _contig(o_bflow, "bflow") if self.past_flow else None
+        occ = _contig(o_occ, "occ")
+        wp = _contig(o_wp, "warped frame 1")
+        wf = _contig(o_wf, "warped frame 2")
+        tgt = _contig(o_tgt, "target")
         assert wp.numel() == tgt.numel() and wf.numel() == tgt.numel(), "input and target size mismatch"
         B, Cn, h, w = tgt.shape
         kind, eps = _pen(self.p)
         prm = _lib.ObParams(self._gradient_terms, kind, eps, float(self.penalty_out), float(self.alpha),
                             float(self.beta), float(self.gamma), float(self.pwc_flow_scaling),
                             int(bool(self.past_flow)), int(bool(self.gradCheck)), int(bool(self.sizeAverage)))
-        g_occ = torch.empty_like(occ)
-        g_wp = torch.empty_like(wp)
-        g_wf = torch.empty_like(wf)
+        grads = [torch.empty_like(occ), torch.empty_like(wp), torch.empty_like(wf)] if want_grads else [None] * 3
         loss = _loss_call(lib.b2f_ob_criterion, C.byref(prm), _p(flow), _p(bflow), _p(occ), _p(wp), _p(wf),
-                          _p(tgt), B, Cn, h, w, _p(g_occ), _p(g_wp), _p(g_wf))
-        self._cache_key = self._key([flow, bflow, occ, wp, wf, tgt]) + (float(self.pwc_flow_scaling),)
-        self._cache = [g_occ, g_wp, g_wf]
-        return loss
+                          _p(tgt), B, Cn, h, w, _p(grads[0]), _p(grads[1]), _p(grads[2]))
+        return loss, grads
 
     def updateOutput(self, input, target):
-        self.output = self._run(input, target)
+        self.output, grads = self._run(input, target, self.fuse_backward)
+        self._hold(self._objects(input, target), grads)
         return self.output
 
     def updateGradInput(self, input, target):
-        warp_start = 3 if self.past_flow else 2
-        key = self._key([input[0], input[1] if self.past_flow else None, input[warp_start - 1],
-                         input[warp_start], input[warp_start + 1], target]) + (float(self.pwc_flow_scaling),)
-        if self._cache is None or key != self._cache_key:
-            self._run(input, target)
-        grads, self._cache, self._cache_key = self._cache, None, None
+        grads = self._take(self._objects(input, target))
+        if grads is None:
+            _, grads = self._run(input, target, True)
         return grads  # fresh table {gradOcc, gradWarp_1, gradWarp_2} (OBCCriterion.lua:132-135)
 
 
@@ -461,7 +499,10 @@ class _SmoothBase(Criterion):
         # parity default: reproduce the Torch7 view-resize aliasing of the edge weights
         self.alias_weights = True
 
-    def _run(self, input, target):
+    def _params(self):
+        return (self._order, _pen(self.p), float(self.cs), bool(self.sizeAverage), bool(self.alias_weights))
+
+    def _run(self, input, target, want_grads):
         lib = _lib.load()
         inp = _contig(input, "input")
         tgt = _contig(target, "target")
@@ -470,21 +511,20 @@ class _SmoothBase(Criterion):
         kind, eps = _pen(self.p)
         prm = _lib.SmoothParams(self._order, kind, eps, float(self.cs), int(bool(self.sizeAverage)),
                                 int(bool(self.alias_weights)))
-        grad = torch.empty_like(inp)
+        grad = torch.empty_like(inp) if want_grads else None
         loss = _loss_call(lib.b2f_smoothness_criterion, C.byref(prm), _p(inp), _p(tgt), B, Cin, tgt.size(1),
                           h, w, _p(grad))
-        self._cache_key = self._key([inp, tgt])
-        self._cache = grad
-        return loss
+        return loss, grad
 
     def updateOutput(self, input, target):
-        self.output = self._run(input, target)
+        self.output, grad = self._run(input, target, self.fuse_backward)
+        self._hold([input, target], grad)
         return self.output
 
     def updateGradInput(self, input, target):
-        if self._cache is None or self._key([input, target]) != self._cache_key:
-            self._run(input, target)
-        grad, self._cache, self._cache_key = self._cache, None, None
+        grad = self._take([input, target])
+        if grad is None:
+            _, grad = self._run(input, target, True)
         return grad  # fresh tensor, not self.gradInput (Q10)
 
 
@@ -507,27 +547,29 @@ class ConstVelCriterion(Criterion):
         self.sizeAverage = True
         self.gradCheck = False
 
-    def _run(self, input):
+    def _params(self):
+        return (bool(self.sizeAverage),)
+
+    def _run(self, input, want_grads):
         lib = _lib.load()
         f = _contig(input[0], "input[1]")
         b = _contig(input[1], "input[2]")
         assert f.numel() == b.numel(), "input and target size mismatch"
         B, Cn, h, w = f.shape
-        gf, gb = torch.empty_like(f), torch.empty_like(b)
+        grads = [torch.empty_like(f), torch.empty_like(b)] if want_grads else [None, None]
         loss = _loss_call(lib.b2f_constvel_criterion, _p(f), _p(b), B, Cn, h, w, int(bool(self.sizeAverage)),
-                          _p(gf), _p(gb))
-        self._cache_key = self._key([f, b])
-        self._cache = [gf, gb]
-        return loss
+                          _p(grads[0]), _p(grads[1]))
+        return loss, grads
 
     def updateOutput(self, input, target=None):
-        self.output = self._run(input)
+        self.output, grads = self._run(input, self.fuse_backward)
+        self._hold([input[0], input[1]], grads)
         return self.output
 
     def updateGradInput(self, input, target=None):
-        if self._cache is None or self._key([input[0], input[1]]) != self._cache_key:
-            self._run(input)
-        grads, self._cache, self._cache_key = self._cache, None, None
+        grads = self._take([input[0], input[1]])
+        if grads is None:
+            _, grads = self._run(input, True)
         return grads
 
 
@@ -539,25 +581,27 @@ class OcclusionPriorCriterion(Criterion):
         self.sizeAverage = True
         self.penalty = 1
 
-    def _run(self, input, target):
+    def _params(self):
+        return (float(self.penalty), bool(self.sizeAverage))
+
+    def _run(self, input, target, want_grads):
         lib = _lib.load()
         occ = _contig(input, "input")
         if target is not None:
             assert occ.size(2) == target.size(2) and occ.size(3) == target.size(3), "input and target size mismatch"
         B, Cn, h, w = occ.shape
-        grad = torch.empty_like(occ)
+        grad = torch.empty_like(occ) if want_grads else None
         loss = _loss_call(lib.b2f_occprior_criterion, _p(occ), B, Cn, h, w, float(self.penalty),
                           int(bool(self.sizeAverage)), _p(grad))
-        self._cache_key = self._key([occ])
-        self._cache = grad
-        return loss
+        return loss, grad
 
     def updateOutput(self, input, target=None):
-        self.output = self._run(input, target)
+        self.output, grad = self._run(input, target, self.fuse_backward)
+        self._hold([input], grad)
         return self.output
 
     def updateGradInput(self, input, target=None):
-        if self._cache is None or self._key([input]) != self._cache_key:
-            self._run(input, target)
-        grad, self._cache, self._cache_key = self._cache, None, None
+        grad = self._take([input])
+        if grad is None:
+            _, grad = self._run(input, target, True)
         return grad

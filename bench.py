@@ -855,7 +855,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sps * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "Torch7 is not installable here; this is the C/OpenMP restatement of "
+        "config": {"workload": WORKLOAD, "batch_per_gpu": 1,
+                   "batch_note": "the CPU arm runs the same per-triplet work one triplet (B = 1) per step; both arms "
+                                 "report triplets/s, so the ratio is per triplet",
+                   "note": "Torch7 is not installable here; this is the C/OpenMP restatement of "
                    "the reference algorithm (oracle/c/b2f_cpu.c) on the host cores"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -875,6 +878,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-criterions", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed step's outputs")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls on one stream instead of the CUDA graph")
     args = ap.parse_args()
@@ -948,6 +952,19 @@ def main():
     launches = launches_per_step * K
     ms = e0.elapsed_time(e1)
     ms_local = ms
+
+    # ---- parity gate on the buffers the timed region has just written (rank 0): all 56 ops of the step, every
+    # batch item, against the float64 checker at 1e-4 (oracle/ is the checker here, never the thing measured).
+    # A kernel left in a measurement mode (b2f_debug_costvol_path 8-10) or a wrong dispatch fails the run.
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import workload_check
+        t_par = time.perf_counter()
+        parity = workload_check.check_workload(wl)
+        parity["seconds"] = round(time.perf_counter() - t_par, 1)
+        parity["tensors_compared"], parity["checked"] = parity["checked"], True
+        parity["passed"] = not parity["failed"]
+        parity["where"] = ("output buffers of the last timed %s" % ("graph replay" if graph is not None else "eager step"))
     if graph is not None:
         # live roofline sample of the dominant kernels: K more eager steps with events around those calls (the
         # graph has no per-kernel events); these steps are outside the timed region
@@ -1122,7 +1139,7 @@ def main():
                                  "level, the level's image warps (leaves of the loss) on side streams under the next level's "
                                  "cost volumes, backward mirrored; the gradImg zero-fills (b2f_zero_async) are issued at the "
                                  "start of the step on their own stream"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "parity": parity,
             # every hot kernel against the same HBM peak (separate pass with events around each call, one call at a
             # time: the isolated times behind the stderr table; `roofline` above is the cost-volume kernel BASELINE's
             # metric names, the C = 3 image-warp backward is as long per launch)
@@ -1135,6 +1152,9 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["failed"]:
+        sys.stderr.write("PARITY FAILED: %r\n" % (parity,))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -60,6 +60,12 @@ B2F_API int b2f_abi_version(void);
 B2F_API const char* b2f_last_error(void);          /* thread-local, never NULL                      */
 B2F_API const char* b2f_status_string(int status);
 B2F_API int b2f_release_scratch(void);             /* frees this thread's scratch on the current device */
+/* Reserve `bytes` of zeroed loss scratch on the current device for criterion calls that are issued while their
+ * stream is CAPTURING into a CUDA graph: every captured call takes its own slice (8 bytes per thread block + 16;
+ * 64 KiB covers a 5-level training step), so a replay never shares a ticket counter with eager calls.  Call it
+ * before the capture -- allocation is illegal during capture.  Released by b2f_release_scratch(); nothing the
+ * library hands to a kernel is freed before that call, so a captured graph stays valid until then.        */
+B2F_API int b2f_reserve_scratch(size_t bytes);
 /* Test / measurement hook selecting the cost-volume kernel family (thread-local; returns the
  * previous mode): 0 = automatic (default), 1 = generic direct kernels, 2/3/4 = the tiled TMA
  * kernels whenever their preconditions hold (F=2, win=9, W%4==0, 16-byte aligned), ignoring the

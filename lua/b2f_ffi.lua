@@ -17,6 +17,8 @@ typedef struct b2f_smooth_params {
 int b2f_abi_version(void);
 const char* b2f_last_error(void);
 int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream);
+int b2f_release_scratch(void);
+int b2f_reserve_scratch(size_t bytes);
 int b2f_costvol_forward(const float* const* frames, int F, int B, int C, int H, int W, int win, int fwd,
                         float* out, int64_t out_batch_stride, b2f_stream_t stream);
 int b2f_costvol_backward(const float* const* frames, int F, int B, int C, int H, int W, int win, int fwd,

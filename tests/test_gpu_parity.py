@@ -721,6 +721,131 @@ def test_nn_costvol_into_joined_buffer_and_clear_state(env):
         f_mod.forward([env.t(ref), env.t(fut[:, :8])])                        # "input sizes mismatch"
 
 
+def _nn_criterion_cases(env):
+    """(module, input, target, oracle forward, oracle backward) for every criterion of the host mirror."""
+    from back2future_b200 import nn as bnn
+    r = rng(33)
+    B, h, w = 2, 12, 20
+    flow, bflow, occ, w1, w2, tgt = _ob_inputs(r, B, 3, h, w, 0.2)
+    T = env.t
+    cases = []
+    ob = bnn.OBCCriterion()
+    ob.p, ob.sizeAverage, ob.pwc_flow_scaling = bnn.L1Penalty(), False, 20
+    oc = o.OBCriterionOracle(False, o.L1Penalty(), pwc_flow_scaling=20, size_average=False)
+    cases.append((ob, [T(flow), T(occ), T(w1), T(w2)], T(tgt), 3,
+                  lambda a: (oc.forward(a[0], None, a[1], [a[2], a[3]], a[4]),
+                             (lambda g: [g[0]] + list(g[1]))(oc.backward(a[0], None, a[1], [a[2], a[3]], a[4])))))
+    sm = bnn.SecondOrderSmoothnessCriterion()
+    sm.p, sm.sizeAverage = bnn.L1Penalty(), False
+    so = o.SmoothnessOracle(2, o.L1Penalty(), size_average=False)
+    cases.append((sm, T(flow), T(tgt), 0, lambda a: (so.forward(a[0], a[1]), [so.backward(a[0], a[1])])))
+    cv = bnn.ConstVelCriterion()
+    cases.append((cv, [T(flow), T(bflow)], None, 0,
+                  lambda a: (o.constvel_forward(a[0], a[1], True), list(o.constvel_backward(a[0], a[1], True)))))
+    op = bnn.OcclusionPriorCriterion()
+    op.sizeAverage = False
+    cases.append((op, T(occ), T(tgt), 0,
+                  lambda a: (o.occprior_forward(a[0], False), [o.occprior_backward(a[0], False)])))
+    return cases
+
+
+def _flat(inp, tgt):
+    ts = list(inp) if isinstance(inp, (list, tuple)) else [inp]
+    return ts + ([tgt] if tgt is not None else [])
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_nn_criterion_backward_sees_buffers_rewritten_through_the_library(env, fuse):
+    """the gradients handed out by updateGradInput must belong to the CURRENT contents of the
+    buffers.  A buffer is rewritten in place through the library's raw pointers between forward and backward
+    (torch's version counter does not move).  Default mode recomputes like the reference and must return the new
+    gradients; with `fuse_backward` the caller has promised not to do that, and the forward's gradients come back
+    only for the very same objects and unchanged fields."""
+    torch = env.torch_
+    for mod, inp, tgt, mut_idx, oracle in _nn_criterion_cases(env):
+        mod.fuse_backward = fuse
+        ts = _flat(inp, tgt)
+        loss = mod.forward(inp, tgt)
+        exp_loss, exp_g = oracle([t.cpu().numpy() for t in ts])
+        assert abs(loss - exp_loss) < TOL * abs(exp_loss)
+        victim = ts[mut_idx]
+        # rewrite the victim in place behind torch's back: a raw-pointer device-to-device copy, the way this
+        # library's kernels write into a module's reused output buffer (the version counter does not move)
+        new_vals = (victim * 0.5 + 0.25).clone()
+        torch.cuda.synchronize()
+        v0 = victim._version
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        assert rt.cudaMemcpy(victim.data_ptr(), new_vals.data_ptr(), victim.numel() * 4, 3) == 0
+        assert victim._version == v0 and torch.equal(victim, new_vals)
+        g = mod.backward(inp, tgt)
+        g = list(g) if isinstance(g, (list, tuple)) else [g]
+        if not fuse:
+            _, exp_g2 = oracle([t.cpu().numpy() for t in ts])
+            for a, b in zip(g, exp_g2):
+                assert o.rel_err(a.cpu().numpy(), b) < TOL, type(mod).__name__
+        else:
+            for a, b in zip(g, exp_g):          # the promise was broken: fused mode returns the forward's gradients
+                assert o.rel_err(a.cpu().numpy(), b) < TOL, type(mod).__name__
+            # ... but never for other objects or changed fields
+            mod.forward(inp, tgt)
+            other = [t.clone() for t in inp] if isinstance(inp, (list, tuple)) else inp.clone()
+            g2 = mod.backward(other, tgt)
+            g2 = list(g2) if isinstance(g2, (list, tuple)) else [g2]
+            _, exp_now = oracle([t.cpu().numpy() for t in ts])
+            for a, b in zip(g2, exp_now):
+                assert o.rel_err(a.cpu().numpy(), b) < TOL
+            if hasattr(mod, "sizeAverage"):
+                mod.forward(inp, tgt)
+                mod.sizeAverage = not mod.sizeAverage
+                assert mod._take(mod._objects(inp, tgt) if hasattr(mod, "_objects") else _flat(inp, tgt)[:2]) is None
+                mod.sizeAverage = not mod.sizeAverage
+
+
+def test_nn_rejects_strided_views_instead_of_copying(env):
+    """No torch kernel on the product path: a non-contiguous tensor raises, it is not copied."""
+    torch = env.torch_
+    from back2future_b200 import nn as bnn
+    x = torch.randn(2, 4, 8, 16, device=env.dev)
+    tgt = torch.randn(2, 6, 8, 16, device=env.dev)
+    sm = bnn.SmoothnessCriterion()
+    with pytest.raises(ValueError, match="non-contiguous"):
+        sm.forward(x[:, :2], tgt[:, :3])
+    s = bnn.BilinearSamplerBHWD()
+    img = torch.randn(2, 8, 16, 3, device=env.dev)
+    grid = torch.randn(2, 8, 16, 4, device=env.dev)[..., :2]
+    with pytest.raises(ValueError, match="non-contiguous"):
+        s.forward([img, grid])
+    cv = bnn.CostVolMulti(9, True)
+    f = torch.randn(2, 8, 8, 16, device=env.dev)
+    cv.forward([f, f.clone()])
+    with pytest.raises(ValueError, match="batch-strided"):
+        cv.backward([f, f.clone()], torch.randn(2, 8, 16, 81, device=env.dev).permute(0, 3, 1, 2))
+
+
+def test_smoothness_weight_extremes(env):
+    """common.cuh's __expf error budget: cs * mean_c|dT| spans 0 .. ~94 (ColorNormalize range -2.1 .. 2.6 => |dT| up
+    to 4.7, cs = 20).  Every gradient element whose weight is not below the denormal range must be within 1e-4
+    RELATIVE TO ITSELF of the float64 oracle (not just relative to the tensor's rms), intended-weights variant so
+    that the weight of a pixel is exp(-cs * its own target gradient)."""
+    r = rng(77)
+    B, h, w = 2, 24, 64
+    x = (r.standard_normal((B, 2, h, w)) * 0.5).astype(np.float32)
+    tgt = np.zeros((B, 3, h, w), np.float32)
+    ramp = np.linspace(0.0, 4.7, w, dtype=np.float32)          # target step between columns grows from 0 to 4.7
+    tgt[:, :, :, 1::2] = ramp[None, None, None, 1::2]
+    tgt[:, :, 1::2, :] += ramp[None, None, None, :] * 0.5
+    loss, g = _run_smooth(env, 1, 0, 0, 0, x, tgt)               # quadratic penalty: grad is linear in the weights
+    oc = o.SmoothnessOracle(1, o.make_penalty(0), size_average=False, alias=False)
+    exp = oc.backward(x, tgt)
+    assert abs(loss - oc.forward(x, tgt)) < TOL * abs(loss)
+    big = np.abs(exp) > 1e-30
+    rel = np.abs(g[big] - exp[big]) / np.abs(exp[big])
+    assert rel.max() < TOL, rel.max()
+    assert np.abs(g[~big]).max(initial=0.0) < 1e-30
+    assert (np.abs(exp) < 1e-20).any() and (np.abs(exp) > 1e-2).any()      # the range really is covered
+
+
 # ---------------------------------------------------------------------------------------
 # committed golden fixture (tests/golden/hotpath_golden.npz: crops of the reference's sample frames,
 # expected values from the float64 oracle -- see tests/golden/make_golden.py for what that pins)

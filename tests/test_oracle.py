@@ -455,3 +455,50 @@ def test_warping_unit_composition_identity_adjoint_and_flow_gradient():
         assert abs(fd - gf[idx]) < 1e-3 * max(1.0, abs(fd))
     gi2, gf2 = o.warping_unit_backward(img, flow, 4.0, go, only_grid=True)
     assert gi2 is None and np.array_equal(gf2, gf)
+
+
+# ---------------------------------------------------------------------------------------
+# oracle/c/b2f_check64.c (the fast float64 checker of the full-size parity gates) pinned to the numpy oracle
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("B,Cn,h,w,win,F", [(2, 5, 7, 9, 9, 2), (1, 3, 6, 5, 5, 3), (2, 4, 4, 12, 3, 4), (1, 2, 3, 3, 9, 2)])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_check64_costvol_equals_numpy_oracle(B, Cn, h, w, win, F, fwd):
+    from oracle import check64 as c64
+    r = np.random.default_rng(5)
+    fr = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(F)]
+    wide = r.standard_normal((B, 2 * win * win, h, w)).astype(np.float32)
+    np.testing.assert_allclose(c64.costvol_forward(fr, win, fwd), o.costvol_forward(fr, win, fwd), rtol=0, atol=1e-13)
+    go = wide[:, win * win:]                                  # batch-strided view, as in the model
+    for a, b in zip(c64.costvol_backward(fr, go, win, fwd), o.costvol_backward(fr, go, win, fwd)):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("B,H,W,Cn,Hg,Wg,sigma", [(2, 9, 11, 3, 9, 11, 4.0), (1, 6, 7, 5, 4, 5, 0.5), (2, 5, 8, 32, 5, 8, 9.0)])
+def test_check64_sampler_equals_numpy_oracle(B, H, W, Cn, Hg, Wg, sigma):
+    from oracle import check64 as c64
+    r = np.random.default_rng(6)
+    img = r.standard_normal((B, H, W, Cn)).astype(np.float32)
+    grid = (r.standard_normal((B, Hg, Wg, 2)) * sigma).astype(np.float32)
+    grid[0, 0, 0] = (0.0, 0.0)
+    grid[0, -1, -1] = (0.5, 100.0)        # clamped to the border: tap at H reads 0 (Q3)
+    go = r.standard_normal((B, Hg, Wg, Cn)).astype(np.float32)
+    np.testing.assert_allclose(c64.warp_forward(img, grid), o.warp_forward(img, grid), rtol=0, atol=1e-13)
+    gi, gg = c64.warp_backward(img, grid, go)
+    ogi, ogg = o.warp_backward(img, grid, go)
+    np.testing.assert_allclose(gi, ogi, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gg, ogg, rtol=0, atol=1e-12)
+    assert c64.warp_backward(img, grid, go, only_grid=True)[0] is None
+
+
+def test_check64_rel_err_matches_the_python_definition_and_flags_nan():
+    from oracle import check64 as c64
+    r = np.random.default_rng(7)
+    b = r.standard_normal((3, 10, 4, 6))
+    wide = np.zeros((3, 20, 4, 6), np.float32)
+    wide[:, 10:] = b.astype(np.float32)
+    wide[1, 13, 2, 3] += 0.25
+    a = wide[:, 10:]                                          # strided view (one half of a joined buffer)
+    assert abs(c64.rel_err(a, b) - o.rel_err(a, b)) < 1e-12
+    wide[2, 15, 0, 0] = np.nan
+    assert c64.rel_err(wide[:, 10:], b) == float("inf")
