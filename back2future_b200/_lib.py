@@ -54,6 +54,19 @@ SIGNATURES = {
     "b2f_flo_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "b2f_flo_read_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2f_flo_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "b2f_conv3x3_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
+    "b2f_conv3x3_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2f_conv3x3_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p]),
+    "b2f_avgpool2x2_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2f_upsample_bilinear2x_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_float,
+                                                  C.c_void_p]),
+    "b2f_upsample_nearest_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p]),
+    "b2f_softmax_channels_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p]),
     "b2f_costvol_forward": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "b2f_costvol_backward": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

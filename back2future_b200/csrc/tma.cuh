@@ -48,6 +48,22 @@ inline int make_tmap4(CUtensorMap* tm, const float* base, const uint64_t dims[4]
   return B2F_OK;
 }
 
+// 2-D variant (packed convolution weights: rows of Cout floats, one row per (input channel, tap))
+inline int make_tmap2(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t stride1_elems,
+                      uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(B2F_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {d0, d1};
+  cuuint64_t gstr[1] = {stride1_elems * 4};
+  cuuint32_t bx[2] = {b0, b1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2F_EINVAL, "cuTensorMapEncodeTiled (2-D) failed with CUresult %d", (int)r);
+  return B2F_OK;
+}
+
 // 5-D variant (the gradOut slab: x, y, window row, window column, batch)
 inline int make_tmap5(CUtensorMap* tm, const float* base, const uint64_t dims[5],
                       const uint64_t strides_elems[4], const uint32_t box[5], bool swizzle128 = false) {
@@ -226,6 +242,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       " [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
       "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
 // ---- device: 4-byte cp.async with zero-fill, completion signalled on an mbarrier --------

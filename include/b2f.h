@@ -193,6 +193,43 @@ B2F_API int b2f_warp_bdhw_backward(const float* img, const float* flow, float fl
                                    const float* gradOut, float* gradImg, float* gradFlow,
                                    int B, int C, int H, int W, b2f_stream_t stream);
 
+/* ---- conv trunk of the PWC network ---------------------------------------
+ * The reference builds its network from cudnn.SpatialConvolution(nIn, nOut, 3, 3, s, s, 1, 1) + nn.LeakyReLU(0.2)
+ * (models/pwc.lua:58-65 convUnit, :76-85 decoder) wired by nngraph (:139-492).  These entries are the per-module
+ * replacements; the graph itself is host code (back2future_b200/pwc.py mirrors createModelMulti, lua/models/pwc_b2f.lua
+ * is the shim).  All tensors fp32 BDHW.
+ *
+ * Weights live in a PACKED layout [Cin * 9][CoutP], CoutP = Cout rounded up to 64, tap index ky * 3 + kx
+ * (b2f_conv3x3_packed_floats floats); b2f_conv3x3_pack_weights converts Torch's (Cout, Cin, 3, 3) weight into it
+ * (unpack != 0: the other way, e.g. to torch.save a checkpoint the reference can read).                       */
+B2F_API int64_t b2f_conv3x3_packed_floats(int Cin, int Cout);
+B2F_API int b2f_conv3x3_pack_weights(const float* w_torch, float* w_packed, int Cout, int Cin, int unpack,
+                                     b2f_stream_t stream);
+/* out = LeakyReLU_slope(conv3x3(x, w) + bias), zero padding 1, stride 1 or 2 (leaky_slope = 1: no activation).
+ * x (B, Cin, H, W) and out (B, Cout, Ho, Wo) may be channel slices of wider buffers: pass the slice's base pointer
+ * and the buffer's batch stride in elements (0 = contiguous).  out2 (may be NULL) receives a second copy with its
+ * own batch stride -- the reference features of a level go to the next convUnit AND into the decoder's joined
+ * input (nn.JoinTable of pwc.lua:298-305, 334 disappears).  bias may be NULL.
+ * Replaces SpatialConvolution:updateOutput + LeakyReLU:updateOutput (pwc.lua:58-65, 76-85).                    */
+B2F_API int b2f_conv3x3_forward(const float* x, int64_t x_batch_stride, const float* w_packed, const float* bias,
+                                float* out, int64_t out_batch_stride, float* out2, int64_t out2_batch_stride,
+                                int B, int Cin, int H, int W, int Cout, int stride, float leaky_slope,
+                                b2f_stream_t stream);
+/* nn.SpatialAveragePooling(2, 2, 2, 2) (pwc.lua:153): x (B, C, H, W) -> out (B, C, H/2, W/2).                  */
+B2F_API int b2f_avgpool2x2_forward(const float* x, float* out, int B, int C, int H, int W, b2f_stream_t stream);
+/* nn.SpatialUpSamplingBilinear(2) (pwc.lua:359-380; THNN's align-corners mapping src = dst * (in-1)/(out-1)):
+ * x (B, C, H, W) with batch stride -> up to three destinations (B, C, 2H, 2W), each with its own batch stride
+ * (0 = contiguous): the up-sampled flow feeds the next level's two decoders, its warps and the next up-sampling.
+ * mul scales the result (1 = nn.SpatialUpSamplingBilinear alone; rescale_flow's MulConstant(2) otherwise).     */
+B2F_API int b2f_upsample_bilinear2x_forward(const float* x, int64_t x_batch_stride, int B, int C, int H, int W,
+                                            float* const* outs, const int64_t* out_batch_strides, int n_outs,
+                                            float mul, b2f_stream_t stream);
+/* nn.SpatialUpSamplingNearest(scale) (pwc.lua:308-316; two stacked x2 modules = scale 4).                     */
+B2F_API int b2f_upsample_nearest_forward(const float* x, float* out, int B, int C, int H, int W, int scale,
+                                         b2f_stream_t stream);
+/* nn.SpatialSoftMax (pwc.lua:305): softmax over the channel dimension of (B, C, H, W).                         */
+B2F_API int b2f_softmax_channels_forward(const float* x, float* out, int B, int C, int H, int W, b2f_stream_t stream);
+
 /* ---- Middlebury .flo files -- HOST buffers, no device work ----------------
  * File layout (flowExtensions.lua:254-287): float32 tag 202021.25 ("PIEH"), int32 width, int32
  * height, then height*width interleaved (u, v) float32 pairs, all little-endian.  The reference
