@@ -46,6 +46,7 @@ SIGNATURES = {
     "b2f_reserve_scratch": (C.c_int, [C.c_size_t]),
     "b2f_debug_costvol_path": (C.c_int, [C.c_int]),
     "b2f_zero_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b2f_copy2d_async": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "b2f_launch_count": (C.c_int64, [C.c_int]),
     "b2f_warp_bdhw_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p]),

@@ -72,6 +72,19 @@ int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream) {
   return B2F_OK;
 }
 
+int b2f_copy2d_async(float* dst, int64_t dst_row_stride, const float* src, int64_t src_row_stride, int64_t row_elems,
+                     int64_t rows, b2f_stream_t stream) {
+  if (rows < 0 || row_elems < 0) return b2f::fail(B2F_EINVAL, "copy2d_async: negative extent");
+  if (!rows || !row_elems) return B2F_OK;
+  if (!dst || !src) return b2f::fail(B2F_EINVAL, "copy2d_async: NULL pointer");
+  if (dst_row_stride < row_elems || src_row_stride < row_elems)
+    return b2f::fail(B2F_EINVAL, "copy2d_async: row stride smaller than the row");
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_row_stride * 4, src, (size_t)src_row_stride * 4, (size_t)row_elems * 4,
+                                    (size_t)rows, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return b2f::cuda_fail(e, "cudaMemcpy2DAsync");
+  return B2F_OK;
+}
+
 // ---- .flo files: host-side wire format of flow fields (flowExtensions.lua:254-287) ----
 namespace {
 constexpr float kFloTag = 202021.25f;

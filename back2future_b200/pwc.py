@@ -1,0 +1,410 @@
+"""The multi-frame PWC network of the reference as a graph executor over libb2f_cuda.so.
+
+Mirrors `createModelMulti(opt)` of models/pwc.lua:87-508 for the Ours-Hard / Ours-Soft family (frames 3,
+two_frame 0, pwc_sum_cvs false, residual 0, occ_input 0, rescale_flow 0, siamese 1, skip > 0): same inputs
+((B, 9, H, W), three ColorNormalized RGB frames stacked on the channel axis), same output table (finest level first:
+{flow, [past flow,] occlusion, warped frame 1, warped frame 3} per level, pwc.lua:459-489) and the same
+`flow_scale` / `past_flow` fields (:493-494).  nngraph's node-by-node interpreter is replaced by a PLAN: the list of
+C-ABI calls of one forward pass, built once per input shape over preallocated buffers and replayed either call by
+call or as one CUDA graph.  What disappears relative to the reference's graph:
+
+  * nn.JoinTable(2) (:267, 298-305, 334): both cost volumes, the reference features (second destination of the
+    convolution that produces them) and the up-sampled flow are written straight into the decoders' joined input;
+  * nn.Narrow + the siamese clones (:141-146, 186-195): the three frames run through the shared convUnits as one
+    batch of 3B (slot order past, future, reference);
+  * nn.Transpose x 3 + nn.MulConstant around every sampler (:68-73, 404, 443): b2f_warp_bdhw_forward;
+  * the second decoder input of the Soft models ({cvs, ref, ubfs}, :336): the joined buffer carries BOTH up-sampled
+    flows and each decoder's first convolution has zero weights for the one it does not see.
+
+torch owns device memory, streams, events and the CUDA graph object -- nothing else; every kernel is ours.  There
+is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FEAT = (3, 16, 32, 64, 96, 128, 192)      # featMaps (pwc.lua:89, d = 16)
+DEC = (128, 128, 96, 64, 32, 2)           # decoder(nChannels) widths (pwc.lua:76-85)
+
+
+class Opt:
+    """The opts.lua fields createModelMulti reads (pwc.lua:100-113), reference defaults (opts.lua:83-98)."""
+
+    def __init__(self, **kw):
+        self.pwc_ws = 9
+        self.frames = 3
+        self.levels = 7
+        self.pwc_skip = 2
+        self.flownet_factor = 20
+        self.past_flow = False
+        self.two_frame = 0
+        self.pwc_sum_cvs = False
+        self.residual = 0
+        self.occ_input = 0
+        self.rescale_flow = 0
+        self.pwc_siamese = 1
+        self.nGPU = 1
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError("createModelMulti: unknown option %r" % k)
+            setattr(self, k, v)
+        if (self.frames != 3 or self.two_frame or self.pwc_sum_cvs or self.residual or self.occ_input
+                or self.rescale_flow or self.pwc_siamese != 1 or self.pwc_skip < 1):
+            raise NotImplementedError("only the published model family is built (frames 3, two_frame 0, pwc_sum_cvs "
+                                      "false, residual 0, occ_input 0, rescale_flow 0, pwc_siamese 1, pwc_skip >= 1)")
+
+    @property
+    def l_st(self):
+        return max(self.pwc_skip + 1, 1)
+
+
+def conv_shapes(opt):
+    """Ordered (name, Cout, Cin, stride) of every convolution: feat.l<l>.<0|1> (shared convUnits, pwc.lua:176-195),
+    occ / flow / bflow .l<l>.<0..5> (decoders, :288-338)."""
+    shapes = []
+    for l in range(2, opt.levels + 1):
+        shapes.append(("feat.l%d.0" % l, FEAT[l - 1], FEAT[l - 2], 2))
+        shapes.append(("feat.l%d.1" % l, FEAT[l - 1], FEAT[l - 1], 1))
+    nd = 2 * opt.pwc_ws ** 2
+    for l in range(opt.levels, opt.l_st - 1, -1):
+        n_occ = nd + FEAT[l - 1] + (2 if l != opt.levels else 0)
+        n_flow = nd if l == opt.levels else nd + FEAT[l - 1] + 2
+        kinds = (("occ", n_occ), ("flow", n_flow)) + ((("bflow", n_flow),) if opt.past_flow else ())
+        for kind, n_in in kinds:
+            cin = n_in
+            for i, cout in enumerate(DEC):
+                shapes.append(("%s.l%d.%d" % (kind, l, i), cout, cin, 1))
+                cin = cout
+    return shapes
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _Conv:
+    __slots__ = ("w", "b", "cin", "cout", "stride")
+
+
+class PWCNet:
+    """`createModelMulti(opt)` + `:cuda()`.  `params`: dict name -> array in Torch's layout ((Cout, Cin, 3, 3) weight,
+    (Cout,) bias) with the names of `conv_shapes`; None = nn.SpatialConvolution:reset()'s uniform(-1/sqrt(9 nIn), ..)
+    drawn from numpy's default_rng(seed)."""
+
+    def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("PWCNet: no CUDA device; the B200 path has no CPU fallback")
+        self.opt = opt or Opt()
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self.image_warps = bool(image_warps)
+        o = self.opt
+        self.past_flow = bool(o.past_flow)                                             # model.past_flow, pwc.lua:494
+        self.flow_scale = [o.flownet_factor / 2.0 ** (l - o.l_st) for l in range(o.levels, o.l_st - 1, -1)]   # :451-455
+        self.n_unit_out = 5 if self.past_flow else 4
+        self._plans = {}
+        self._convs = {}
+        if params is None:
+            params = self.random_params(self.opt, seed)
+        self.load_params(params)
+
+    # ---- parameters -------------------------------------------------------------------------------------
+    @staticmethod
+    def random_params(opt, seed=2, scale=1.0):
+        rng = np.random.default_rng(seed)
+        params = {}
+        for name, cout, cin, _s in conv_shapes(opt):
+            s = scale / math.sqrt(9.0 * cin)
+            params[name + ".weight"] = rng.uniform(-s, s, (cout, cin, 3, 3)).astype(np.float32)
+            params[name + ".bias"] = rng.uniform(-s, s, (cout,)).astype(np.float32)
+        return params
+
+    def n_params(self):
+        return sum(co * ci * 9 + co for _n, co, ci, _s in conv_shapes(self.opt))
+
+    def load_params(self, params):
+        """Upload and repack every convolution ((Cout, Cin, 3, 3) -> [Cin * 9][CoutP]).  For the Soft models the first
+        convolution of each level < levels decoder is widened to the shared joined input {cvs, ref, ufs, ubfs} with zero
+        weights on the up-sampled flow it does not read."""
+        o = self.opt
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            for name, cout, cin, stride in conv_shapes(o):
+                w = np.ascontiguousarray(np.asarray(params[name + ".weight"], np.float32))
+                b = np.ascontiguousarray(np.asarray(params[name + ".bias"], np.float32))
+                if w.shape != (cout, cin, 3, 3) or b.shape != (cout,):
+                    raise ValueError("%s: expected weight %r / bias %r, got %r / %r" %
+                                     (name, (cout, cin, 3, 3), (cout,), w.shape, b.shape))
+                kind, lvl, idx = name.split(".")
+                l = int(lvl[1:])
+                if self.past_flow and idx == "0" and kind in ("occ", "flow", "bflow") and l != o.levels:
+                    wide = np.zeros((cout, cin + 2, 3, 3), np.float32)
+                    wide[:, :cin - 2] = w[:, :cin - 2]
+                    if kind == "bflow":
+                        wide[:, cin:cin + 2] = w[:, cin - 2:]
+                    else:
+                        wide[:, cin - 2:cin] = w[:, cin - 2:]
+                    w, cin = wide, cin + 2
+                cv = _Conv()
+                cv.cin, cv.cout, cv.stride = cin, cout, stride
+                wt = torch.from_numpy(w).to(self.device)
+                cv.w = torch.empty(int(self.lib.b2f_conv3x3_packed_floats(cin, cout)), device=self.device,
+                                   dtype=torch.float32)
+                _lib.check(self.lib.b2f_conv3x3_pack_weights(_vp(wt), _vp(cv.w), cout, cin, 0, st))
+                cv.b = torch.from_numpy(b).to(self.device)
+                self._convs[name] = cv
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # ---- plan -------------------------------------------------------------------------------------------
+    def _build(self, B, H, W):
+        o, lib, dev = self.opt, self.lib, self.device
+        levels, l_st, win = o.levels, o.l_st, o.pwc_ws
+        if H % (1 << (levels - 1)) or W % (1 << (levels - 1)):
+            raise ValueError("PWCNet: input %dx%d is not a multiple of %d (back2future.lua:54-67 rescales to one)" %
+                             (W, H, 1 << (levels - 1)))
+        nd = win * win
+        E = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        plan = _Plan(B, H, W)
+        x = plan.x = E(B, 9, H, W)
+        hw = lambda l: (H >> (l - 1), W >> (l - 1))
+        ops = plan.ops
+        P = _vp
+
+        def conv(name, xin, xbs, xb, cin, h, w, out, obs, out2=None, obs2=0, slope=0.2, lane=0):
+            cv = self._convs[name]
+            assert cv.cin == cin, (name, cv.cin, cin)
+            ops.append((lane, lib.b2f_conv3x3_forward,
+                        (xin, xbs, P(cv.w), P(cv.b), out, obs, out2, obs2, xb, cin, h, w, cv.cout, cv.stride,
+                         C.c_float(slope))))
+
+        def sl(t, b0=0, c0=0):
+            """device pointer of t[b0, c0]"""
+            return C.c_void_p(t.data_ptr() + 4 * (b0 * t.stride(0) + c0 * t.stride(1)))
+
+        # -- joined decoder inputs J[l]: {cvs_fwd 81, cvs_bwd 81, ref features C_l, [ufs 2, [ubfs 2]]} ------------
+        nfl = 4 if self.past_flow else 2
+        J = {}
+        for l in range(l_st, levels + 1):
+            h, w = hw(l)
+            J[l] = E(B, 2 * nd + FEAT[l - 1] + (nfl if l != levels else 0), h, w)
+        plan.J = J
+
+        # -- frames 1 and 3 as dense images + their average-pooled pyramid (ds, pwc.lua:149-158) ------------------
+        n_ds = levels - l_st + 1
+        ds = [E(2 * B, 3, H >> k, W >> k) for k in range(n_ds)] if self.image_warps else []
+        if self.image_warps:
+            for i, f in enumerate((0, 2)):
+                ops.append((1, lib.b2f_copy2d_async, (sl(ds[0], i * B), 3 * H * W, sl(x, 0, 3 * f), 9 * H * W,
+                                                      3 * H * W, B)))
+            for k in range(1, n_ds):
+                ops.append((1, lib.b2f_avgpool2x2_forward, (P(ds[k - 1]), P(ds[k]), 2 * B, 3, H >> (k - 1), W >> (k - 1))))
+        plan.ds = ds
+
+        # -- siamese feature pyramid on the 3B batch (slots: past, future, reference) -----------------------------
+        feats = {}
+        slot_of_frame = (0, 2, 1)     # frame index 0, 1, 2 (past, ref, future) -> slot
+        prev = None
+        for l in range(2, levels + 1):
+            h, w = hw(l)
+            c_in, c_out = FEAT[l - 2], FEAT[l - 1]
+            tmp = E(3 * B, c_out, h, w)
+            feats[l] = E(3 * B, c_out, h, w)
+            if l == 2:
+                for f in range(3):
+                    conv("feat.l2.0", sl(x, 0, 3 * f), 9 * H * W, B, 3, H, W, sl(tmp, slot_of_frame[f] * B), 0)
+            else:
+                conv("feat.l%d.0" % l, P(prev), 0, 3 * B, c_in, 2 * h, 2 * w, P(tmp), 0)
+            name = "feat.l%d.1" % l
+            conv(name, P(tmp), 0, 2 * B, c_out, h, w, P(feats[l]), 0)
+            if l >= l_st:     # the reference frame's features also go into the joined decoder input
+                conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0, sl(J[l], 0, 2 * nd), J[l].stride(0))
+            else:
+                conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0)
+            plan.keep.append(tmp)
+            prev = feats[l]
+        plan.feats = feats
+
+        # -- levels, coarse to fine ---------------------------------------------------------------------------
+        outs = {}
+        warped = {}
+        ufs = {}
+        for l in range(levels, l_st - 1, -1):
+            h, w = hw(l)
+            Cl = FEAT[l - 1]
+            ref = sl(feats[l], 2 * B)
+            past = sl(feats[l], 0) if l == levels else sl(warped[l], 0)
+            fut = sl(feats[l], B) if l == levels else sl(warped[l], B)
+            Jl = J[l]
+            jbs = Jl.stride(0)
+            for fwd, frame, c0 in ((1, fut, 0), (0, past, nd)):
+                ops.append((0, lib.b2f_costvol_forward, (_lib.ptr_array([ref.value, frame.value]), 2, B, Cl, h, w, win, fwd,
+                                                         sl(Jl, 0, c0), jbs)))
+            ops.append(("fork", 2))      # lane 2 (occlusion decoder) may start: J[l] is complete
+            cj = Jl.shape[1]
+
+            def decoder(kind, lane, x0, cin0):
+                t, tb, cin = x0, jbs, cin0
+                for i, cout in enumerate(DEC):
+                    out = E(B, cout, h, w)
+                    plan.keep.append(out)
+                    conv("%s.l%d.%d" % (kind, l, i), t, tb, B, cin, h, w, P(out), 0, slope=0.2 if i < 5 else 1.0, lane=lane)
+                    t, tb, cin = P(out), 0, cout
+                return out
+
+            # occlusion decoder -> softmax -> nearest x 2^(l_st-1) (pwc.lua:288-317)
+            occ_logit = decoder("occ", 2, P(Jl), cj)
+            occ = E(B, 2, h, w)
+            ops.append((2, lib.b2f_softmax_channels_forward, (P(occ_logit), P(occ), B, 2, h, w)))
+            up = 1 << (l_st - 1)
+            skip_occ = E(B, 2, h * up, w * up)
+            ops.append((2, lib.b2f_upsample_nearest_forward, (P(occ), P(skip_occ), B, 2, h, w, up)))
+            plan.occ[l] = occ
+
+            # flow decoder(s) (pwc.lua:322-349)
+            flows = []
+            for kind in ("flow",) + (("bflow",) if self.past_flow else ()):
+                f = decoder(kind, 0, P(Jl), 2 * nd if l == levels else cj)
+                flows.append(f)
+            plan.fs[l] = flows
+
+            # up-sampling: ufs[l] (next level's decoder input + feature warps), skip_ufs[l] (output + image warps)
+            ufs[l] = []
+            skips = []
+            for i, f in enumerate(flows):
+                u = E(B, 2, 2 * h, 2 * w)
+                dst = [u.data_ptr()]
+                dbs = [0]
+                if l > l_st:
+                    Jn = J[l - 1]
+                    dst.append(Jn.data_ptr() + 4 * (2 * nd + FEAT[l - 2] + 2 * i) * Jn.stride(1))
+                    dbs.append(Jn.stride(0))
+                ops.append((0, lib.b2f_upsample_bilinear2x_forward,
+                            (P(f), 0, B, 2, h, w, _lib.ptr_array(dst), (C.c_int64 * len(dbs))(*dbs), len(dst),
+                             C.c_float(1.0))))
+                ufs[l].append(u)
+            if l > l_st:      # feature warps for the next level (pwc.lua:394-409); always with the FUTURE flow
+                hn, wn = hw(l - 1)
+                Cn = FEAT[l - 2]
+                warped[l - 1] = E(2 * B, Cn, hn, wn)
+                for slot, sgn in ((0, -1.0), (1, 1.0)):
+                    sc = o.flownet_factor * sgn / 2.0 ** (l - 2)
+                    ops.append((0, lib.b2f_warp_bdhw_forward, (sl(feats[l - 1], slot * B), P(ufs[l][0]), C.c_float(sc),
+                                                               sl(warped[l - 1], slot * B), B, Cn, hn, wn)))
+            ops.append(("fork", 1))      # lane 1: output-resolution up-sampling + image warps, off the critical path
+            for u in ufs[l]:
+                t = u
+                for i in range(2, l_st):
+                    hh, ww = t.shape[2], t.shape[3]
+                    t2 = E(B, 2, 2 * hh, 2 * ww)
+                    ops.append((1, lib.b2f_upsample_bilinear2x_forward,
+                                (P(t), 0, B, 2, hh, ww, _lib.ptr_array([t2.data_ptr()]), (C.c_int64 * 1)(0), 1,
+                                 C.c_float(1.0))))
+                    t = t2
+                skips.append(t)
+            unit = list(skips) + [skip_occ]
+            if self.image_warps:
+                k = l - l_st
+                hh, ww = H >> k, W >> k
+                iw = E(2 * B, 3, hh, ww)
+                for slot, sgn in ((0, -1.0), (1, 1.0)):
+                    fl = skips[1] if (self.past_flow and slot == 0) else skips[0]      # pwc.lua:426-437
+                    sc = o.flownet_factor * sgn / 2.0 ** (l - l_st)                    # :443
+                    ops.append((1, lib.b2f_warp_bdhw_forward, (sl(ds[k], slot * B), P(fl), C.c_float(sc), sl(iw, slot * B),
+                                                               B, 3, hh, ww)))
+                unit += [iw[:B], iw[B:]]
+            outs[l] = unit
+        plan.ufs = ufs
+        plan.warped = warped
+        plan.output = [t for l in range(l_st, levels + 1) for t in outs[l]]
+        return plan
+
+    # ---- execution --------------------------------------------------------------------------------------
+    def plan(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._plans:
+            with torch.cuda.device(self.device):
+                self._plans[key] = self._build(B, H, W)
+        return self._plans[key]
+
+    def forward(self, x, graph=True):
+        """model:forward(x): x (B, 9, H, W) float32 on this device (or a pinned / pageable HOST tensor: it is copied
+        into the plan's input buffer on the current stream).  Returns the output table (views of the plan's buffers,
+        valid until the next forward of the same shape)."""
+        if x.dim() != 4 or x.size(1) != 9:
+            raise ValueError("PWCNet: expected a (B, 9, H, W) input, got %r" % (tuple(x.shape),))
+        if x.dtype != torch.float32:
+            raise TypeError("PWCNet: expected float32")
+        p = self.plan(x.size(0), x.size(2), x.size(3))
+        with torch.cuda.device(self.device):
+            p.x.copy_(x, non_blocking=True)      # a cudaMemcpyAsync (H2D or D2D), no kernel
+            self.run(p, graph=graph)
+        self.output = p.output
+        return p.output
+
+    def run(self, p, graph=True):
+        """Execute the plan on the current stream (inputs already in p.x)."""
+        if not graph:
+            p.launch()
+            return
+        if p.graph is None:
+            p.launch()                            # warm-up outside capture: TMA descriptors, func attributes
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.graph(g, stream=cap):
+                p.launch()
+            p.graph = g
+        p.graph.replay()
+
+    def evaluate(self):
+        return self
+
+    def cuda(self):
+        return self
+
+
+class _Plan:
+    def __init__(self, B, H, W):
+        self.shape = (B, H, W)
+        self.ops = []
+        self.keep = []
+        self.occ = {}
+        self.fs = {}
+        self.graph = None
+        self._lanes = None
+        self.n_launches = 0
+
+    def launch(self):
+        """Issue every call.  Lane 0 is the current stream (the critical path: cost volumes -> flow decoder -> up-sampling
+        -> feature warps -> next level); lanes 1 (output up-sampling, image warps) and 2 (occlusion decoders) are side
+        streams forked from lane 0 by events and joined at the end."""
+        cur = torch.cuda.current_stream()
+        if self._lanes is None:
+            self._lanes = {1: torch.cuda.Stream(), 2: torch.cuda.Stream()}
+        lanes = {0: cur, 1: self._lanes[1], 2: self._lanes[2]}
+        used = set()
+        check = _lib.check
+        n = 0
+        for op in self.ops:
+            if op[0] == "fork":
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                lanes[op[1]].wait_event(ev)
+                used.add(op[1])
+                continue
+            lane, fn, args = op
+            if lane and lane not in used:      # work that depends on the input only
+                lanes[lane].wait_stream(cur)
+                used.add(lane)
+            check(fn(*args, C.c_void_p(lanes[lane].cuda_stream)))
+            n += 1
+        for lane in used:
+            cur.wait_stream(lanes[lane])
+        self.n_launches = n

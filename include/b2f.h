@@ -80,6 +80,11 @@ B2F_API int b2f_debug_costvol_path(int mode);
 /* Stream-ordered zero-fill of a device buffer (what the sampler's Lua wrapper does with
  * gradInput:zero() before the native call, BilinearSamplerBHWD.lua:99-102).                  */
 B2F_API int b2f_zero_async(void* ptr, size_t bytes, b2f_stream_t stream);
+/* Stream-ordered device-to-device copy of `rows` rows of `row_elems` floats with independent row strides (in
+ * elements): what nn.Narrow(2, a, 3) followed by a :contiguous() / nn.JoinTable(2) copy is in the reference's
+ * graph (pwc.lua:141-146, 267) when a channel slice of one buffer has to become a dense tensor (or the reverse).  */
+B2F_API int b2f_copy2d_async(float* dst, int64_t dst_row_stride, const float* src, int64_t src_row_stride,
+                             int64_t row_elems, int64_t rows, b2f_stream_t stream);
 /* Number of kernels (not memsets/copies) this thread has launched through the library since
  * the last reset; used by bench.py for its `gpu_launches` claim.                            */
 B2F_API int64_t b2f_launch_count(int reset);

@@ -1,0 +1,221 @@
+"""Conv trunk + whole-network forward on the GPU through the C ABI, against oracle/pwc_oracle.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _p(t, off=0):
+    return C.c_void_p(t.data_ptr() + 4 * off)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _conv(lib, _lib, x, w, b, stride, slope, out_c_total=None, out_c0=0, x_c_total=None, x_c0=0, out2=False):
+    """Run b2f_conv3x3_forward with x / out optionally embedded as channel slices of wider buffers."""
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    xt = x_c_total or Cin
+    xw = torch.zeros((B, xt, H, W), device="cuda")
+    xw[:, x_c0:x_c0 + Cin] = _dev(x)
+    ot = out_c_total or Cout
+    ow = torch.full((B, ot, Ho, Wo), 7.0, device="cuda")
+    o2 = torch.full((B, Cout + 3, Ho, Wo), 5.0, device="cuda") if out2 else None
+    wp = torch.empty(int(lib.b2f_conv3x3_packed_floats(Cin, Cout)), device="cuda")
+    wt = _dev(w)
+    _lib.check(lib.b2f_conv3x3_pack_weights(_p(wt), _p(wp), Cout, Cin, 0, _st()))
+    bt = _dev(b) if b is not None else None
+    _lib.check(lib.b2f_conv3x3_forward(_p(xw, x_c0 * H * W), xt * H * W, _p(wp), _p(bt) if bt is not None else None,
+                                       _p(ow, out_c0 * Ho * Wo), ot * Ho * Wo,
+                                       _p(o2, 1 * Ho * Wo) if out2 else None, (Cout + 3) * Ho * Wo if out2 else 0,
+                                       B, Cin, H, W, Cout, stride, slope, _st()))
+    torch.cuda.synchronize()
+    got = ow[:, out_c0:out_c0 + Cout].cpu().numpy()
+    # nothing outside the slice was touched
+    if ot != Cout:
+        rest = torch.cat([ow[:, :out_c0], ow[:, out_c0 + Cout:]], 1)
+        assert bool((rest == 7.0).all())
+    if out2:
+        assert bool((o2[:, 1:1 + Cout] == ow[:, out_c0:out_c0 + Cout]).all())
+        assert bool((o2[:, :1] == 5.0).all()) and bool((o2[:, 1 + Cout:] == 5.0).all())
+    # unpack round trip
+    back = torch.zeros_like(wt)
+    _lib.check(lib.b2f_conv3x3_pack_weights(_p(back), _p(wp), Cout, Cin, 1, _st()))
+    torch.cuda.synchronize()
+    assert bool((back == wt).all())
+    return got
+
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, stride
+    (1, 3, 64, 128, 16, 2),       # feat.l2.0
+    (2, 16, 32, 64, 16, 1),       # feat.l2.1
+    (1, 16, 32, 64, 32, 2),
+    (1, 64, 16, 32, 96, 2),       # 96 output channels: 32-wide channel tiles
+    (1, 128, 8, 16, 192, 2),
+    (1, 192, 7, 16, 192, 1),      # coarsest level of 1024 x 448
+    (1, 196, 24, 40, 128, 1),     # decoder, ragged tile rows / columns
+    (2, 354, 7, 16, 128, 1),
+    (1, 128, 16, 32, 96, 1),
+    (1, 32, 9, 36, 2, 1),         # decoder head: 2 output channels
+    (1, 5, 10, 38, 7, 1),         # W % 4 != 0 -> direct kernel (1216-wide inputs, levels 6 / 7)
+    (1, 6, 5, 19, 4, 2),
+    (3, 3, 20, 24, 16, 2),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_forward(case):
+    from back2future_b200 import _lib
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    lib = _lib.load()
+    B, Cin, H, W, Cout, stride = case
+    rng = np.random.default_rng(hash(case) % 1000)
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = po.leaky_relu(po.conv3x3(x, w, b, stride))
+    got = _conv(lib, _lib, x, w, b, stride, 0.2)
+    assert got.shape == ref.shape
+    assert o.rel_err(got, ref) < TOL
+    # no activation, no bias, embedded in wider buffers, second destination
+    ref = po.conv3x3(x, w, None, stride)
+    got = _conv(lib, _lib, x, w, None, stride, 1.0, out_c_total=Cout + 4, out_c0=4, x_c_total=Cin + 4, x_c0=4, out2=True)
+    assert o.rel_err(got, ref) < TOL
+
+
+def test_conv3x3_rejects_bad_arguments():
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(1, 3, 8, 8, device="cuda")
+    wp = torch.zeros(int(lib.b2f_conv3x3_packed_floats(3, 4)), device="cuda")
+    out = torch.zeros(1, 4, 8, 8, device="cuda")
+    assert lib.b2f_conv3x3_forward(None, 0, _p(wp), None, _p(out), 0, None, 0, 1, 3, 8, 8, 4, 1, 0.2, _st()) != 0
+    assert lib.b2f_conv3x3_forward(_p(x), 0, _p(wp), None, _p(out), 0, None, 0, 1, 3, 8, 8, 4, 3, 0.2, _st()) != 0
+    assert lib.b2f_conv3x3_forward(_p(x), 5, _p(wp), None, _p(out), 0, None, 0, 1, 3, 8, 8, 4, 1, 0.2, _st()) != 0
+    assert b"stride" in lib.b2f_last_error()
+    assert lib.b2f_conv3x3_forward(_p(x), 0, _p(wp), None, _p(out), 0, None, 0, 0, 3, 8, 8, 4, 1, 0.2, _st()) == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 7, 16), (1, 2, 5, 19), (1, 3, 1, 1), (2, 2, 28, 64)])
+def test_small_layout_ops(shape):
+    from back2future_b200 import _lib
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(shape).astype(np.float32)
+    B, Cn, H, W = shape
+    xt = _dev(x)
+    # bilinear x2 into two destinations, one of them a channel slice of a wider buffer, with a multiplier
+    a = torch.zeros(B, Cn, 2 * H, 2 * W, device="cuda")
+    wide = torch.full((B, Cn + 5, 2 * H, 2 * W), 3.0, device="cuda")
+    outs = (C.c_void_p * 2)(a.data_ptr(), wide.data_ptr() + 4 * 5 * 4 * H * W)
+    bss = (C.c_int64 * 2)(0, (Cn + 5) * 4 * H * W)
+    _lib.check(lib.b2f_upsample_bilinear2x_forward(_p(xt), 0, B, Cn, H, W, outs, bss, 2, 1.0, _st()))
+    torch.cuda.synchronize()
+    ref = po.upsample_bilinear2x(x)
+    # THNN evaluates the source coordinate ratio * dst in fp32 (the kernel does the same): lambda carries ~1e-6 of
+    # absolute error at 32-64 columns, times the neighbour difference
+    assert o.rel_err(a.cpu().numpy(), ref) < 2e-5
+    assert bool((wide[:, 5:] == a).all()) and bool((wide[:, :5] == 3.0).all())
+    _lib.check(lib.b2f_upsample_bilinear2x_forward(_p(xt), 0, B, Cn, H, W, outs, bss, 1, 2.0, _st()))
+    torch.cuda.synchronize()
+    assert o.rel_err(a.cpu().numpy(), 2 * ref) < 2e-5
+    # nearest x2 / x4
+    for s in (2, 4):
+        n = torch.zeros(B, Cn, s * H, s * W, device="cuda")
+        _lib.check(lib.b2f_upsample_nearest_forward(_p(xt), _p(n), B, Cn, H, W, s, _st()))
+        torch.cuda.synchronize()
+        assert np.array_equal(n.cpu().numpy(), po.upsample_nearest(x, s))
+    # softmax over channels
+    sm = torch.zeros_like(xt)
+    _lib.check(lib.b2f_softmax_channels_forward(_p(xt), _p(sm), B, Cn, H, W, _st()))
+    torch.cuda.synchronize()
+    assert o.rel_err(sm.cpu().numpy(), po.spatial_softmax(x.astype(np.float64))) < 1e-6
+    # average pooling
+    if H >= 2 and W % 2 == 0:
+        ap = torch.zeros(B, Cn, H // 2, W // 2, device="cuda")
+        _lib.check(lib.b2f_avgpool2x2_forward(_p(xt), _p(ap), B, Cn, H, W, _st()))
+        torch.cuda.synchronize()
+        assert o.rel_err(ap.cpu().numpy(), po.avgpool2x2(x.astype(np.float64))) < 1e-6
+
+
+def test_copy2d():
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    src = torch.arange(2 * 9 * 4 * 6, device="cuda", dtype=torch.float32).reshape(2, 9, 4, 6)
+    dst = torch.zeros(2, 3, 4, 6, device="cuda")
+    _lib.check(lib.b2f_copy2d_async(_p(dst), 3 * 24, _p(src, 6 * 24), 9 * 24, 3 * 24, 2, _st()))
+    torch.cuda.synchronize()
+    assert bool((dst == src[:, 6:9]).all())
+    assert lib.b2f_copy2d_async(_p(dst), 2, _p(src), 9 * 24, 3 * 24, 2, _st()) != 0
+
+
+def _net_case(past_flow, B, H, W, seed, graph):
+    from back2future_b200 import pwc
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    opt = pwc.Opt(past_flow=past_flow)
+    oopt = po.Opt(past_flow=past_flow)
+    params = po.init_params(oopt, seed=seed, scale=2.0)
+    net = pwc.PWCNet(opt, params)
+    rng = np.random.default_rng(seed + 1)
+    x = rng.uniform(-2.1, 2.6, (B, 9, H, W)).astype(np.float32)
+    out = net.forward(_dev(x), graph=graph)
+    torch.cuda.synchronize()
+    taps = {}
+    ref = po.pwc_forward(params, x, oopt, taps=taps)
+    assert len(out) == len(ref) == 5 * net.n_unit_out
+    p = net.plan(B, H, W)
+    worst = 0.0
+    for l in range(7, 2, -1):
+        e = o.rel_err(p.J[l][:, :162].cpu().numpy(), taps["cvs.l%d" % l])
+        worst = max(worst, e)
+        assert e < TOL, ("cvs", l, e)
+        e = o.rel_err(p.fs[l][0].cpu().numpy(), taps["fs.l%d" % l])
+        assert e < TOL, ("fs", l, e)
+        e = o.rel_err(p.occ[l].cpu().numpy(), taps["occ.l%d" % l])
+        assert e < TOL, ("occ", l, e)
+    for k, (a, b) in enumerate(zip(out, ref)):
+        assert tuple(a.shape) == b.shape
+        e = o.rel_err(a.cpu().numpy(), b)
+        worst = max(worst, e)
+        assert e < TOL, ("output", k, e)
+    return worst, net, x, out
+
+
+@pytest.mark.parametrize("past_flow", [False, True])
+def test_network_forward_matches_the_oracle(past_flow):
+    _net_case(past_flow, 1, 64, 128, 11, graph=False)
+
+
+def test_network_forward_batch2_and_graph_replay():
+    worst, net, x, out = _net_case(False, 2, 64, 64, 13, graph=False)
+    eager = [t.clone() for t in out]
+    out2 = net.forward(_dev(x), graph=True)      # captures
+    out3 = net.forward(_dev(x), graph=True)      # replays
+    torch.cuda.synchronize()
+    for a, b in zip(eager, out3):
+        assert bool((a == b).all())
+
+
+def test_network_rejects_bad_sizes():
+    from back2future_b200 import pwc
+    net = pwc.PWCNet(pwc.Opt())
+    with pytest.raises(ValueError):
+        net.forward(torch.zeros(1, 9, 100, 128, device="cuda"))
+    with pytest.raises(ValueError):
+        net.forward(torch.zeros(1, 6, 64, 128, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        pwc.Opt(two_frame=1)
