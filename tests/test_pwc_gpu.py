@@ -206,8 +206,11 @@ def test_network_forward_batch2_and_graph_replay():
     out2 = net.forward(_dev(x), graph=True)      # captures
     out3 = net.forward(_dev(x), graph=True)      # replays
     torch.cuda.synchronize()
+    # not bit-identical: the small-level cost volumes split the channel sum over CTAs and accumulate with float
+    # atomics (order varies run to run by an ulp, eager or graph alike)
+    from oracle import b2f_oracle as o
     for a, b in zip(eager, out3):
-        assert bool((a == b).all())
+        assert o.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
 
 
 def test_network_rejects_bad_sizes():
