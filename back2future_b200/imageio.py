@@ -13,9 +13,12 @@ the CPU in the reference too (back2future.lua builds the 9-channel input on the 
                        from channel 2, past from channel 1 of the occlusion map.
 * `rescale_flow`    -- back2future.lua:80-84: u, v multiplied by width / height ratios after the resize.
 
-NOT here: `image.scale` (bilinear down-scale of the input, 'simple' up-scale of flow / masks).  It belongs to the
-Torch7 `image` package, whose source is not part of the reference tree: its exact sampling convention cannot be
-pinned offline.
+* `scale`           -- `image.scale(src, width, height [, mode])` (back2future.lua:71, 82, 89-91).  The Torch7 `image`
+                       package is not part of the reference tree; its two modes are restated from the package's C
+                       source as published (generic/image.c: `scaleBilinear` = separable `scaleLinear_rowcol`, rows
+                       then columns through a temporary, align-corners interpolation when enlarging and a box average
+                       with fractional end weights when shrinking, float arithmetic; `scaleSimple` = nearest sample at
+                       floor(i * src / dst)).  Unpinned: no Torch7 here to run it against.
 """
 from __future__ import annotations
 
@@ -130,6 +133,71 @@ def color_normalize(imgs, mean=MEAN, std=STD):
 def fine_size(width, height):
     """back2future.lua:55-67: the network's input size -- both edges rounded down to a multiple of 64."""
     return width - width % 64, height - height % 64
+
+
+def _scale_linear_axis(src, dst_len):
+    """image.c `scaleLinear_rowcol` along the LAST axis of a float32 array, all other axes in parallel."""
+    src_len = src.shape[-1]
+    f32 = np.float32
+    if dst_len == src_len:
+        return src.copy()
+    dst = np.empty(src.shape[:-1] + (dst_len,), np.float32)
+    if dst_len > src_len:
+        if src_len == 1:
+            dst[...] = src[..., :1]
+            return dst
+        sc = f32(src_len - 1) / f32(dst_len - 1)
+        di = np.arange(dst_len - 1)
+        si_f = (di.astype(np.float32) * sc).astype(np.float32)
+        si_i = si_f.astype(np.int64)
+        fr = (si_f - si_i.astype(np.float32)).astype(np.float32)
+        dst[..., :-1] = (f32(1) - fr) * src[..., si_i] + fr * src[..., si_i + 1]
+        dst[..., -1] = src[..., -1]
+        return dst
+    sc = f32(src_len) / f32(dst_len)
+    si0_i, si0_f = 0, f32(0)
+    for di in range(dst_len):
+        si1_f = f32(di + 1) * sc
+        si1_i = int(si1_f)
+        si1_f = f32(si1_f - f32(si1_i))
+        acc = (f32(1) - si0_f) * src[..., si0_i]
+        n = f32(1) - si0_f
+        for si in range(si0_i + 1, si1_i):
+            acc = acc + src[..., si]
+            n = f32(n + f32(1))
+        if si1_i < src_len:
+            acc = acc + si1_f * src[..., si1_i]
+            n = f32(n + si1_f)
+        dst[..., di] = acc / n
+        si0_i, si0_f = si1_i, si1_f
+    return dst
+
+
+def scale(src, width, height, mode="bilinear"):
+    """`image.scale(src, width, height, mode)` for a (k, H, W) or (H, W) host array.
+
+    'bilinear' (the default, back2future.lua:71): rows first into a (H, width) temporary, then columns -- float32
+    throughout, like the package's FloatTensor path.  'simple' (back2future.lua:82, 89-91): dst[j, i] =
+    src[min(floor(j * H / height), H - 1), min(floor(i * W / width), W - 1)] with the ratios in float32; the dtype
+    is kept (the reference calls it on DoubleTensors and on the ByteTensor masks)."""
+    a = np.asarray(src)
+    if a.ndim not in (2, 3):
+        raise ValueError("scale: expected a (k, H, W) or (H, W) array, got %r" % (a.shape,))
+    if width <= 0 or height <= 0:
+        raise ValueError("scale: bad target size %dx%d" % (width, height))
+    H, W = a.shape[-2], a.shape[-1]
+    if mode == "simple":
+        scx = np.float32(W) / np.float32(width)
+        scy = np.float32(H) / np.float32(height)
+        ii = np.minimum((np.arange(width, dtype=np.float32) * scx).astype(np.int64), W - 1)
+        jj = np.minimum((np.arange(height, dtype=np.float32) * scy).astype(np.int64), H - 1)
+        return np.ascontiguousarray(a[..., jj[:, None], ii[None, :]])
+    if mode != "bilinear":
+        raise ValueError("scale: mode %r is not built (the reference uses 'bilinear' and 'simple')" % (mode,))
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    tmp = _scale_linear_axis(a, width)                                         # rows: (.., H, W) -> (.., H, width)
+    out = _scale_linear_axis(np.ascontiguousarray(np.swapaxes(tmp, -1, -2)), height)   # columns
+    return np.ascontiguousarray(np.swapaxes(out, -1, -2))
 
 
 def occlusion_masks(occ, threshold=OCC_THRESHOLD):

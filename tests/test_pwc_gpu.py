@@ -222,3 +222,86 @@ def test_network_rejects_bad_sizes():
         net.forward(torch.zeros(1, 6, 64, 128, device="cuda"))
     with pytest.raises(NotImplementedError):
         pwc.Opt(two_frame=1)
+
+
+def _frames(n, H, W, seed=3):
+    """Smooth random textures translating by ~2 px per frame, (3, H, W) in [0, 1]."""
+    rng = np.random.default_rng(seed)
+    base = rng.random((3, H // 8 + 4, W // 8 + 4))
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    out = []
+    for t in range(n):
+        ys, xs = (yy + 1.5 * t) / 8.0, (xx + 2.0 * t) / 8.0
+        y0, x0 = ys.astype(int), xs.astype(int)
+        fy, fx = ys - y0, xs - x0
+        im = ((1 - fy) * (1 - fx) * base[:, y0, x0] + (1 - fy) * fx * base[:, y0, x0 + 1] +
+              fy * (1 - fx) * base[:, y0 + 1, x0] + fy * fx * base[:, y0 + 1, x0 + 1])
+        out.append(im.astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize("name,occ_index", [("Ours-Hard", "occlusion"), ("Ours-Soft-ft-KITTI", "occlusion"),
+                                            ("Ours-Hard", "as_written")])
+def test_compute_flow_matches_the_oracle_pipeline(name, occ_index, tmp_path):
+    """back2future.lua:47-95 end to end on 330 x 200 images (network size 320 x 192): flow within 1e-4, masks equal
+    wherever the occlusion value is not within rounding of the 0.6666 threshold."""
+    from back2future_b200 import back2future as b2f, imageio as io
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    m = b2f.Back2Future.init(name, model_dir=str(tmp_path), seed=5, occ_index=occ_index,
+                             image_warps=occ_index == "as_written")
+    past_flow = m.model.past_flow
+    ims = _frames(3, 200, 330)
+    flow, fwd, bwd = m.computeFlow(*ims)
+    assert flow.shape == (2, 200, 330) and flow.dtype == np.float64
+    assert fwd.shape == bwd.shape == (1, 200, 330) and fwd.dtype == np.uint8
+    # the oracle pipeline
+    opt = po.Opt(past_flow=past_flow)
+    params = {k: v for k, v in b2f.pwc.PWCNet.random_params(m.model.opt, 5).items()}
+    x = io.scale(io.color_normalize(np.concatenate(ims, 0)), 320, 192)[None]
+    est = po.pwc_forward(params, x, opt)
+    rflow = io.scale(est[0][0], 330, 200, "simple")
+    rflow[1] *= 200 / 192
+    rflow[0] *= 330 / 320
+    assert o.rel_err(flow, rflow) < TOL
+    if occ_index == "as_written":
+        rocc = est[2][0][:2]
+    else:
+        rocc = est[2 if past_flow else 1][0]
+    rocc_full = io.scale(rocc, 330, 200, "simple")
+    sure = np.abs(rocc_full - io.OCC_THRESHOLD) > 1e-4
+    rf, rb = (rocc_full[1:2] >= io.OCC_THRESHOLD), (rocc_full[0:1] >= io.OCC_THRESHOLD)
+    assert np.array_equal(fwd[sure[1:2]], rf[sure[1:2]].astype(np.uint8))
+    assert np.array_equal(bwd[sure[0:1]], rb[sure[0:1]].astype(np.uint8))
+    assert sure.mean() > 0.99
+
+
+def test_compute_sequence_equals_per_triplet_calls_and_shards(tmp_path):
+    from back2future_b200 import back2future as b2f
+    m = b2f.Back2Future.init("Ours-Hard", model_dir=str(tmp_path), seed=6)
+    frames = _frames(6, 128, 192, seed=8)
+    seq = m.compute_sequence(frames)
+    assert [r[0] for r in seq] == [0, 1, 2, 3]
+    for t, flow, fwd, bwd in seq:
+        f2, a2, b2 = m.computeFlow(frames[t], frames[t + 1], frames[t + 2])
+        assert np.abs(flow - f2).max() < 1e-4 * max(1.0, np.abs(f2).max())
+        assert (fwd != a2).mean() < 1e-3 and (bwd != b2).mean() < 1e-3
+    # two ranks cover the same triplets, contiguously (SURVEY 8e)
+    parts = [m.compute_sequence(frames, rank=r, world=2) for r in range(2)]
+    assert [r[0] for r in parts[0]] == [0, 1] and [r[0] for r in parts[1]] == [2, 3]
+    for r in parts[0] + parts[1]:
+        assert np.abs(r[1] - seq[r[0]][1]).max() < 1e-4 * max(1.0, np.abs(seq[r[0]][1]).max())
+
+
+def test_init_reads_a_t7_checkpoint(tmp_path):
+    """back2future.lua:97-118: the model file is loaded when present (here: one written by t7.export_model)."""
+    from back2future_b200 import back2future as b2f, t7
+    from oracle import pwc_oracle as po
+    params = po.init_params(po.Opt(), seed=21, scale=2.0)
+    t7.save(str(tmp_path / "RoamingImages_H.t7"), t7.TorchObject("nn.DataParallelTable",
+                                                                 {"modules": [t7.export_model(params, False)]}))
+    m = b2f.Back2Future.init("Ours-Hard", model_dir=str(tmp_path), image_warps=True)
+    x = np.random.default_rng(1).uniform(-2, 2, (1, 9, 64, 64)).astype(np.float32)
+    out = m.model.forward(_dev(x))
+    ref = po.pwc_forward(params, x, po.Opt())
+    from oracle import b2f_oracle as o
+    assert o.rel_err(out[0].cpu().numpy(), ref[0]) < TOL
