@@ -210,7 +210,7 @@ def test_network_forward_batch2_and_graph_replay():
     # atomics (order varies run to run by an ulp, eager or graph alike)
     from oracle import b2f_oracle as o
     for a, b in zip(eager, out3):
-        assert o.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+        assert o.rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL
 
 
 def test_network_rejects_bad_sizes():
