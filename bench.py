@@ -419,8 +419,128 @@ def time_inference(torch, lib, dev, reps=200):
         res["hot_path_triplets_per_s"] = round(1e6 / res["us_per_triplet_smooth_flow"], 1)
         out[key] = res
         del wl, graph
-    out["note"] = ("forward-only hot path of one triplet (B = 1) as one CUDA-graph replay; whole-network inference also "
-                   "needs the conv trunk (row N1, not in this library)")
+    out["note"] = ("forward-only hot path of one triplet (B = 1) as one CUDA-graph replay; whole-network inference "
+                   "(conv trunk included) is the `whole_network` block")
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# whole network: Ours-Hard inference, device-resident and end to end from host images
+# ----------------------------------------------------------------------------------------
+
+def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
+    """Ours-Hard forward (back2future_b200.pwc.PWCNet: conv trunk + cost volumes + warps + decoders as one CUDA-graph
+    replay) at 1024 x 448.  `device`: inputs resident, B triplets per replay.  `e2e`: every step uploads the B x 9 x H x W
+    normalised frames from pinned host memory and reads flow + occlusion maps of the finest level back (what computeFlow
+    moves, back2future.lua:73-92); H2D, compute and D2H run on three streams, two input / output buffers deep.
+    `b1_*`: one triplet per replay (the reference's computeFlow call pattern) at the three BASELINE sizes.
+    `cpu`: oracle/pwc_oracle.py (numpy float32, BLAS threads) on one triplet -- the checker, timed beside it."""
+    from back2future_b200 import pwc
+    import numpy as np
+    out = {"model": "Ours-Hard (7 193 316 parameters, random init)", "batch_per_gpu": B}
+
+    def timed(fn, n, sync_streams=()):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for st in sync_streams:
+            st.wait_event(a)
+        for _ in range(n):
+            fn()
+        for st in sync_streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True)
+    p = net.plan(B, H_FULL, W_FULL)
+    p.x.copy_(torch.randn(p.x.shape, device=dev))
+    ms = timed(lambda: net.run(p), steps)
+    out["device"] = {"triplets_per_s": round(world * B / ms * 1e3, 1), "ms_per_step": round(ms, 3),
+                     "launches_per_step": p.n_launches, "outputs": "full table incl. the ten warped frames"}
+    # end to end: flow + occlusion only (computeFlow never reads the warped frames)
+    net2 = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=False)
+    p2 = net2.plan(B, H_FULL, W_FULL)
+    hin = [torch.randn(B, 9, H_FULL, W_FULL).pin_memory() for _ in range(2)]
+    din = [torch.empty(B, 9, H_FULL, W_FULL, device=dev) for _ in range(2)]
+    dout = [[torch.empty(B, 2, H_FULL, W_FULL, device=dev) for _ in range(2)] for _ in range(2)]
+    hout = [[torch.empty(B, 2, H_FULL, W_FULL).pin_memory() for _ in range(2)] for _ in range(2)]
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_cmp, ev_out = [None, None], [None, None]
+    state = {"i": 0}
+
+    def e2e_step():
+        i = state["i"] & 1
+        state["i"] += 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            if ev_cmp[i] is not None:
+                s_in.wait_event(ev_cmp[i])             # din[i] was consumed two steps ago
+            din[i].copy_(hin[i], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record()
+        cur.wait_event(ev_in)
+        p2.x.copy_(din[i], non_blocking=True)
+        net2.run(p2)
+        if ev_out[i] is not None:
+            cur.wait_event(ev_out[i])                  # dout[i] has been read back
+        dout[i][0].copy_(p2.output[0], non_blocking=True)
+        dout[i][1].copy_(p2.output[1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        ev_cmp[i] = ev
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev)
+            hout[i][0].copy_(dout[i][0], non_blocking=True)
+            hout[i][1].copy_(dout[i][1], non_blocking=True)
+            eo = torch.cuda.Event()
+            eo.record()
+            ev_out[i] = eo
+
+    ems = timed(e2e_step, steps, (s_in, s_out))
+    out["e2e"] = {"triplets_per_s": round(world * B / ems * 1e3, 1), "ms_per_step": round(ems, 3),
+                  "h2d_bytes_per_step": B * 9 * H_FULL * W_FULL * 4, "d2h_bytes_per_step": 2 * B * 2 * H_FULL * W_FULL * 4,
+                  "api": "back2future_b200.pwc.PWCNet.run on host frames (the device half of computeFlow)"}
+    del net, p, hin, din, dout, hout
+    if rank == 0 and world == 1:
+        for key, (h, w) in (("b1_1024x448", (H_FULL, W_FULL)), ("b1_config0_1216x320", (320, 1216)),
+                            ("b1_config4_1024x384", (384, 1024))):
+            q = net2.plan(1, h, w)
+            q.x.copy_(torch.randn(q.x.shape, device=dev))
+            m1 = timed(lambda: net2.run(q), 20)
+            out[key] = {"ms_per_triplet": round(m1, 3), "triplets_per_s": round(1e3 / m1, 1)}
+        # parity of this very model at a size the oracle finishes in a second
+        from oracle import pwc_oracle as po, b2f_oracle as o
+        params = pwc.PWCNet.random_params(net2.opt, 2)
+        x = np.random.default_rng(5).uniform(-2.1, 2.6, (1, 9, 64, 128)).astype(np.float32)
+        got = net2.forward(torch.from_numpy(x).to(dev))
+        torch.cuda.synchronize()
+        ref = po.pwc_forward(params, x, po.Opt())
+        per = 4
+        errs = [o.rel_err(got[2 * k].cpu().numpy(), ref[per * k]) for k in range(5)] + \
+               [o.rel_err(got[2 * k + 1].cpu().numpy(), ref[per * k + 1]) for k in range(5)]
+        out["parity"] = {"max_rel_err": float("%.3g" % max(errs)), "tol": 1e-4, "passed": max(errs) < 1e-4,
+                         "what": "flow + occlusion of all 5 levels, 1 x 9 x 64 x 128, vs oracle/pwc_oracle.py (float64)"}
+        if cpu:
+            x = np.random.default_rng(6).uniform(-2.1, 2.6, (1, 9, H_FULL, W_FULL)).astype(np.float32)
+            t0 = time.perf_counter()
+            po.pwc_forward(params, x, po.Opt(), dtype=np.float32)
+            dt = time.perf_counter() - t0
+            out["cpu"] = {"triplets_per_s": round(1.0 / dt, 3), "s_per_triplet": round(dt, 2), "kind": "port",
+                          "cores": len(os.sched_getaffinity(0)),
+                          "sample": "1 triplet at 1024x448 through oracle/pwc_oracle.py (numpy float32 / BLAS)"}
     return out
 
 
@@ -878,6 +998,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-criterions", action="store_true")
+    ap.add_argument("--no-network", action="store_true", help="skip the whole-network (conv trunk included) block")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed step's outputs")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls on one stream instead of the CUDA graph")
@@ -1109,6 +1230,9 @@ def main():
         wl.set_flow("iid4", seed=2)
     crit = time_criterions(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
     infer = time_inference(torch, lib, dev) if (rank == 0 and world == 1 and not args.no_criterions) else None
+    network = None
+    if not args.no_network:
+        network = time_network(torch, dev, world, rank, dist, cpu=not args.no_cpu)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, desc, sps, n = time_cpu(args.cpu_budget)
@@ -1148,6 +1272,7 @@ def main():
                                     for r in sorted(rows, key=lambda r: -r["ms"])[:12]] if rows else None),
             "cpu_baseline": cpu,
             "criterions": crit, "flow_variants": flow_var, "inference_shapes": infer, "allreduce": allreduce,
+            "whole_network": network,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
