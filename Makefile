@@ -8,13 +8,14 @@ OBJDIR    := build
 SRCS      := $(CSRC)/api.cu $(CSRC)/costvol.cu $(CSRC)/warp.cu $(CSRC)/criterions.cu $(CSRC)/conv.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := back2future_b200/libb2f_cuda.so
+COMMLIB   := back2future_b200/libb2f_comm.so
 ORACLE    := oracle/c/libb2f_cpu.so
 CHECK64   := oracle/c/libb2f_check64.so
 # the reference's own sampler (test-only parity pin), compiled from where it lies; only when the reference is mounted
 REFROOT   ?= /root/reference
 REFLIB    := oracle/_ref/libstn_ref.so
 
-all: $(LIB) $(ORACLE) $(CHECK64)
+all: $(LIB) $(COMMLIB) $(ORACLE) $(CHECK64)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh include/b2f.h
 	@mkdir -p $(OBJDIR)
@@ -22,6 +23,10 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/tma.cuh include/b2f.h
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker --version-script=$(CSRC)/exports.map
+
+# the gradient all-reduce behind its own C ABI (include/b2f_comm.h); NCCL is dlopen'ed, not linked
+$(COMMLIB): $(CSRC)/comm.cu include/b2f_comm.h
+	$(NVCC) -O2 -std=c++17 $(ARCH) -Xcompiler -fPIC,-fvisibility=hidden -shared -o $@ $< -ldl
 
 $(ORACLE): oracle/c/b2f_cpu.c
 	$(HOSTCC) -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -fvisibility=hidden -o $@ $< -lm
@@ -40,6 +45,6 @@ $(REFLIB): oracle/ref_shim/stn_ref.cu $(wildcard oracle/ref_shim/*.h)
 ref: $(REFLIB)
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) $(ORACLE) $(CHECK64)
+	rm -rf $(OBJDIR) $(LIB) $(COMMLIB) $(ORACLE) $(CHECK64)
 
 .PHONY: all clean ref
