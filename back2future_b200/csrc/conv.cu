@@ -59,6 +59,12 @@ struct Args {
   int64_t obs, obs2;
   int Cin, Cout, Ho, Wo, ntn;
   float slope;             // LeakyReLU negative slope; 1 = no activation
+  // backward-data use (b2f_conv3x3_backward_data): the activation derivative comes from `mask` (the forward output of
+  // the layer whose input gradient this is: factor 1 where mask > 0, `slope` elsewhere) instead of the result's own
+  // sign, and the result may be added to what `out` already holds
+  const float* mask;
+  int64_t mbs;
+  int accumulate;
 };
 
 template <int NWN, int S, int KC>
@@ -170,15 +176,22 @@ conv3x3_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ C
       const int n = n0 + wn * 8 + 2 * m + h;
       if (n >= a.Cout) continue;
       const float bv = a.bias ? __ldg(a.bias + n) : 0.f;
+      const size_t off = (size_t)n * hw + (size_t)y * a.Wo + x;
       float v[8];
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         float lo, hi;
         unpack2(acc[p][m], lo, hi);
         float t = (h ? hi : lo) + bv;
-        v[p] = t > 0.f ? t : t * a.slope;
+        if (a.mask) {
+          const float mk = (x + p < a.Wo) ? __ldg(a.mask + (size_t)b * a.mbs + off + p) : 1.f;
+          t = mk > 0.f ? t : t * a.slope;
+        } else {
+          t = t > 0.f ? t : t * a.slope;
+        }
+        if (a.accumulate && x + p < a.Wo) t += a.out[(size_t)b * a.obs + off + p];
+        v[p] = t;
       }
-      const size_t off = (size_t)n * hw + (size_t)y * a.Wo + x;
 #pragma unroll
       for (int d = 0; d < 2; ++d) {
         float* dst = d == 0 ? a.out : a.out2;
@@ -399,7 +412,7 @@ extern "C" int b2f_conv3x3_forward(const float* x, int64_t x_batch_stride, const
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int CoutP = (Cout + 63) / 64 * 64;
-  cv3::Args a{bias, out, out2, obs, obs2, Cin, Cout, Ho, Wo, 1, leaky_slope};
+  cv3::Args a{bias, out, out2, obs, obs2, Cin, Cout, Ho, Wo, 1, leaky_slope, nullptr, 0, 0};
 
   const bool vec_ok = (Wo % 4) != 0 || (aligned16(out) && obs % 4 == 0 && (!out2 || (aligned16(out2) && obs2 % 4 == 0)));
   const bool tma_ok = (W % 4) == 0 && aligned16(x) && xbs % 4 == 0 && aligned16(w_packed) && vec_ok &&
@@ -417,6 +430,103 @@ extern "C" int b2f_conv3x3_forward(const float* x, int64_t x_batch_stride, const
                                                                             B, Cin, H, W, Cout, CoutP, Ho, Wo, stride,
                                                                             leaky_slope);
   B2F_CHECK_LAUNCH("conv3x3_generic");
+  return B2F_OK;
+}
+
+// ---- backward-data ----------------------------------------------------------------------------------------------
+// gin[ci, y, x] = sum_{co, ky, kx} gout[co, (y + 1 - ky) / s, (x + 1 - kx) / s] * w[co, ci, ky, kx]   (divisible terms)
+// Stride 1 is the forward kernel again on the transposed, tap-flipped weights wT[(co * 9 + 8 - tap)][ci]
+// (b2f_conv3x3_transpose_packed); stride 2 (the six down-sampling convolutions of the feature pyramid, 3 % of the
+// network's arithmetic) and widths the TMA path cannot take use the direct kernel below on the same wT.
+namespace b2f {
+namespace {
+__global__ void conv3x3_dgrad_generic(const float* __restrict__ gout, int64_t gbs, const float* __restrict__ wt,
+                                      const float* __restrict__ act, int64_t abs_, float* __restrict__ gin, int64_t ibs,
+                                      int accumulate, int B, int Cout, int Ho, int Wo, int Cin, int CinP, int H, int W,
+                                      int S, float slope) {
+  const int64_t total = (int64_t)B * Cin * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int ci = (int)((i / ((int64_t)W * H)) % Cin), b = (int)(i / ((int64_t)W * H * Cin));
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || ty % S) continue;
+      const int yo = ty / S;
+      if (yo >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || tx % S) continue;
+        const int xo = tx / S;
+        if (xo >= Wo) continue;
+        const float* g = gout + (size_t)b * gbs + (size_t)yo * Wo + xo;
+        const float* w = wt + (size_t)(8 - (ky * 3 + kx)) * CinP + ci;
+        for (int co = 0; co < Cout; ++co)
+          acc = fmaf(__ldg(g + (size_t)co * Ho * Wo), __ldg(w + (size_t)co * 9 * CinP), acc);
+      }
+    }
+    const size_t off = ((size_t)ci * H + y) * W + x;
+    if (act) acc = __ldg(act + (size_t)b * abs_ + off) > 0.f ? acc : acc * slope;
+    float* d = gin + (size_t)b * ibs + off;
+    *d = accumulate ? *d + acc : acc;
+  }
+}
+
+// wT[(co * 9 + 8 - tap)][ci] <- w[(ci * 9 + tap)][co]
+__global__ void transpose_packed_kernel(const float* __restrict__ wp, float* __restrict__ wt, int Cout, int Cin, int CoutP,
+                                        int CinP) {
+  const int total = Cout * 9 * CinP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % CinP, t = (i / CinP) % 9, co = i / (CinP * 9);
+    wt[i] = ci < Cin ? wp[(size_t)(ci * 9 + (8 - t)) * CoutP + co] : 0.f;
+  }
+}
+}  // namespace
+}  // namespace b2f
+
+extern "C" int b2f_conv3x3_transpose_packed(const float* w_packed, float* wt_packed, int Cout, int Cin, b2f_stream_t stream) {
+  if (!w_packed || !wt_packed || Cout <= 0 || Cin <= 0) return fail(B2F_EINVAL, "conv3x3_transpose_packed: bad argument");
+  const int CoutP = (Cout + 63) / 64 * 64, CinP = (Cin + 63) / 64 * 64;
+  transpose_packed_kernel<<<ew_grid((int64_t)Cout * 9 * CinP, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w_packed, wt_packed, Cout, Cin, CoutP, CinP);
+  B2F_CHECK_LAUNCH("transpose_packed_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_conv3x3_backward_data(const float* gout, int64_t gout_batch_stride, const float* wt_packed,
+                                         const float* act, int64_t act_batch_stride, float* gin, int64_t gin_batch_stride,
+                                         int accumulate, int B, int Cin, int H, int W, int Cout, int stride,
+                                         float leaky_slope, b2f_stream_t stream) {
+  if (!gout || !wt_packed || !gin) return fail(B2F_EINVAL, "conv3x3_backward_data: NULL gout / wt_packed / gin");
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "conv3x3_backward_data: bad size");
+  if (stride != 1 && stride != 2) return fail(B2F_EUNSUPPORTED, "conv3x3_backward_data: stride %d", stride);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int64_t gbs = gout_batch_stride ? gout_batch_stride : (int64_t)Cout * Ho * Wo;
+  const int64_t ibs = gin_batch_stride ? gin_batch_stride : (int64_t)Cin * H * W;
+  const int64_t abs_ = act_batch_stride ? act_batch_stride : (int64_t)Cin * H * W;
+  if (gbs < (int64_t)Cout * Ho * Wo || ibs < (int64_t)Cin * H * W || (act && abs_ < (int64_t)Cin * H * W))
+    return fail(B2F_EINVAL, "conv3x3_backward_data: batch stride smaller than one item");
+  if (!aligned4(gout) || !aligned4(gin) || !aligned4(wt_packed) || (act && !aligned4(act)))
+    return fail(B2F_EALIGN, "conv3x3_backward_data: misaligned pointer");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int CinP = (Cin + 63) / 64 * 64;
+  const bool tma_ok = stride == 1 && (W % 4) == 0 && aligned16(gout) && gbs % 4 == 0 && aligned16(wt_packed) &&
+                      aligned16(gin) && ibs % 4 == 0 && get_encode_fn() != nullptr;
+  if (tma_ok) {
+    // the forward kernel with the roles of the channel counts exchanged: "input" = gout (Cout planes), "output" = gin
+    cv3::Args a{nullptr, gin, nullptr, ibs, 0, Cout, Cin, H, W, 1, leaky_slope, act, abs_, accumulate};
+    if (!act) a.slope = 1.f;
+    const bool n64 = Cin % 64 == 0 || Cin > 96;
+    return n64 ? launch_conv<8, 1, 8>(gout, gbs, wt_packed, CinP, a, B, Cout, H, W, st)
+               : launch_conv<4, 1, 8>(gout, gbs, wt_packed, CinP, a, B, Cout, H, W, st);
+  }
+  conv3x3_dgrad_generic<<<ew_grid((int64_t)B * Cin * H * W, 128), 128, 0, st>>>(gout, gbs, wt_packed, act, abs_, gin, ibs,
+                                                                               accumulate, B, Cout, Ho, Wo, Cin, CinP, H, W,
+                                                                               stride, leaky_slope);
+  B2F_CHECK_LAUNCH("conv3x3_dgrad_generic");
   return B2F_OK;
 }
 

@@ -1,0 +1,405 @@
+// Training-only kernels of the conv trunk ("and their backward + Adam"): weight / bias gradient of the
+// 3x3 convolution, the backward of the small layout ops, the gradient bookkeeping (axpy over strided channel slices,
+// LeakyReLU derivative) and the Adam step (optim.adam, train.lua:485-486).
+//
+// Replaces, for the modules of models/pwc.lua: SpatialConvolution:accGradParameters, LeakyReLU:updateGradInput,
+// SpatialUpSamplingBilinear / SpatialUpSamplingNearest / SpatialSoftMax :updateGradInput, nngraph's gradient
+// accumulation at fan-out nodes, and optim.adam.
+#include "tma.cuh"
+
+#include <algorithm>
+
+namespace b2f {
+namespace {
+
+// ---- weight gradient ---------------------------------------------------------------------------------------------
+// gw[(ci * 9 + tap)][co] += sum_{b, y, x} gout[b, co, y, x] * x[b, ci, y S + ky - 1, x S + kx - 1]      (packed layout)
+// gb[co]                 += sum_{b, y, x} gout[b, co, y, x]
+//
+// A GEMM with K = B * Ho * Wo (pixels): CTA = (8 input channels, 64 output channels, a share of the pixel tiles).
+// Thread (co = tid % 32, ci = tid / 32) owns the 9 taps of (ci, co) and (ci, co + 32): 18 accumulators.  A 4 x 32 pixel
+// tile of gout (64 planes) and the matching input patch (8 planes, + halo) are staged in shared memory with cp.async,
+// two stages deep; per 4 pixels a thread reads its two gout float4 (conflict-free: the plane pitch is 4 mod 32 words)
+// and, per tap row, 6 (stride 1) or 9 (stride 2) input values that are the same for the whole warp (broadcast) for
+// 72 FMAs.  The partial sums leave with atomicAdd (co is the lane index: 128-byte coalesced reductions).
+namespace wg {
+constexpr int KC = 8, NC = 64, TH = 4, TW = 32, THREADS = 256;
+constexpr int GP = TW + 4;                 // gout row pitch (words)
+constexpr int GPLANE = TH * GP + 4;        // plane pitch: 148 = 4 mod 32
+template <int S>
+struct Cfg {
+  static constexpr int XR = (TH - 1) * S + 3;          // input rows of a tile
+  static constexpr int XW = (TW - 1) * S + 3;          // input columns
+  static constexpr int XP = (XW + 3) / 4 * 4 + 4;      // row pitch, first column at word 3 so that column 1 is 16-byte aligned
+  static constexpr int G_ELEMS = NC * GPLANE;
+  static constexpr int X_ELEMS = KC * XR * XP;
+  static constexpr int STAGE = G_ELEMS + X_ELEMS;
+  static constexpr int SMEM_BYTES = 2 * STAGE * 4;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = smem_u32(dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+  const uint32_t d = smem_u32(dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int S, bool VEC>
+__global__ void __launch_bounds__(THREADS, 2)
+conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict__ gout, int64_t gbs,
+              float* __restrict__ gw, float* __restrict__ gb, int B, int Cin, int H, int W, int Cout, int CoutP, int Ho,
+              int Wo, int nco, int nsplit) {
+  using cfg = Cfg<S>;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int co_l = tid & 31, ci_l = tid >> 5;
+  const int cblk = blockIdx.x;
+  const int c0 = (cblk / nco) * KC, n0 = (cblk % nco) * NC;
+  const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
+  const int ntiles = B * tiles_y * tiles_x;
+  const int t_lo = (int)((int64_t)ntiles * blockIdx.y / nsplit), t_hi = (int)((int64_t)ntiles * (blockIdx.y + 1) / nsplit);
+
+  float acc[2][9];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[h][t] = 0.f;
+  float bsum[2] = {0.f, 0.f};
+
+  auto stage = [&](int t, int s) {
+    float* gs = smem + s * cfg::STAGE;
+    float* xs = gs + cfg::G_ELEMS;
+    const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+    const int x0 = tx * TW, y0 = ty * TH;
+    const float* gbase = gout + (size_t)b * gbs;
+    if (VEC) {
+      // 64 planes x 4 rows x 8 float4
+      for (int i = tid; i < NC * TH * (TW / 4); i += THREADS) {
+        const int q = i & 7, r = (i >> 3) & 3, c = i >> 5;
+        const int yy = y0 + r, xx = x0 + 4 * q, n = n0 + c;
+        const bool ok = n < Cout && yy < Ho && xx < Wo;      // Wo % 4 == 0: a float4 is inside or outside as a whole
+        cp_async16(gs + c * GPLANE + r * GP + 4 * q, ok ? gbase + ((size_t)n * Ho + yy) * Wo + xx : gout, ok);
+      }
+    } else {
+      for (int i = tid; i < NC * TH * TW; i += THREADS) {
+        const int q = i & 31, r = (i >> 5) & 3, c = i >> 7;
+        const int yy = y0 + r, xx = x0 + q, n = n0 + c;
+        const bool ok = n < Cout && yy < Ho && xx < Wo;
+        cp_async4(gs + c * GPLANE + r * GP + q, ok ? gbase + ((size_t)n * Ho + yy) * Wo + xx : gout, ok);
+      }
+    }
+    const float* xbase = x + (size_t)b * xbs;
+    const int xi0 = x0 * S - 1, yi0 = y0 * S - 1;
+    for (int i = tid; i < KC * cfg::XR * cfg::XW; i += THREADS) {
+      const int q = i % cfg::XW, r = (i / cfg::XW) % cfg::XR, c = i / (cfg::XW * cfg::XR);
+      const int yy = yi0 + r, xx = xi0 + q, ci = c0 + c;
+      const bool ok = ci < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp_async4(xs + (c * cfg::XR + r) * cfg::XP + 3 + q, ok ? xbase + ((size_t)ci * H + yy) * W + xx : x, ok);
+    }
+    cp_commit();
+  };
+
+  if (t_lo < t_hi) stage(t_lo, 0);
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int s = (t - t_lo) & 1;
+    if (t + 1 < t_hi) {
+      stage(t + 1, s ^ 1);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+    const float* gs = smem + s * cfg::STAGE;
+    const float* xs = gs + cfg::G_ELEMS + ci_l * cfg::XR * cfg::XP + 3;
+    const float* g0 = gs + co_l * GPLANE;
+    const float* g1 = g0 + 32 * GPLANE;
+#pragma unroll
+    for (int r = 0; r < TH; ++r) {
+#pragma unroll 2
+      for (int q = 0; q < TW / 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(g0 + r * GP + 4 * q);
+        const float4 c = *reinterpret_cast<const float4*>(g1 + r * GP + 4 * q);
+        const float ga[4] = {a.x, a.y, a.z, a.w}, gc[4] = {c.x, c.y, c.z, c.w};
+        if (ci_l == 0) {
+          bsum[0] += (a.x + a.y) + (a.z + a.w);
+          bsum[1] += (c.x + c.y) + (c.z + c.w);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* xr = xs + (r * S + ky) * cfg::XP + 4 * q * S;
+          constexpr int NX = 3 * S + 3;      // 6 / 9 input values of this row
+          float xv[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) xv[i] = xr[i];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[0][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[0][ky * 3 + kx]);
+              acc[1][ky * 3 + kx] = fmaf(gc[p], xv[p * S + kx], acc[1][ky * 3 + kx]);
+            }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int ci = c0 + ci_l;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int n = n0 + co_l + 32 * h;
+    if (n >= Cout) continue;
+    if (ci < Cin) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(gw + (size_t)(ci * 9 + t) * CoutP + n, acc[h][t]);
+    }
+    if (gb && ci_l == 0 && c0 == 0) atomicAdd(gb + n, bsum[h]);
+  }
+}
+}  // namespace wg
+
+// ---- small backward ops --------------------------------------------------------------------------------------------
+int ew_grid(int64_t total, int threads) {
+  int64_t blocks = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+// g *= (act > 0 ? 1 : slope), rows of `row` elements with independent strides
+__global__ void leaky_backward_kernel(float* __restrict__ g, int64_t gs, const float* __restrict__ act, int64_t as, int64_t row,
+                                      int64_t rows, float slope) {
+  const int64_t total = rows * row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / row, c = i % row;
+    if (!(act[r * as + c] > 0.f)) g[r * gs + c] *= slope;
+  }
+}
+
+// dst += alpha * src over rows with independent strides (nngraph's gradient accumulation at fan-out nodes; the
+// level_weights * opt.* scaling of train.lua:421-468)
+__global__ void axpy2d_kernel(float* __restrict__ dst, int64_t ds, const float* __restrict__ src, int64_t ss, int64_t row,
+                              int64_t rows, float alpha) {
+  const int64_t total = rows * row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / row, c = i % row;
+    dst[r * ds + c] = fmaf(alpha, src[r * ss + c], dst[r * ds + c]);
+  }
+}
+
+// SpatialUpSamplingBilinear(2):updateGradInput as a gather: input row i receives from the output rows h2 with
+// floor(r h2) in {i - 1, i}; the weights are recomputed with the forward's fp32 expressions.
+__device__ __forceinline__ void up_taps(int n_in, int n_out, float ratio, int i, int* idx, float* wgt, int& n) {
+  n = 0;
+  // candidates: r h2 in (i - 1, i + 1)  ->  h2 in ((i - 1) / r, (i + 1) / r); scan a safe superset
+  int lo = ratio > 0.f ? (int)floorf((float)(i - 1) / ratio) - 1 : 0;
+  int hi = ratio > 0.f ? (int)ceilf((float)(i + 1) / ratio) + 1 : n_out - 1;
+  lo = max(lo, 0);
+  hi = min(hi, n_out - 1);
+  for (int h2 = lo; h2 <= hi; ++h2) {
+    const float h1r = __fmul_rn(ratio, (float)h2);
+    const int h1 = (int)h1r;
+    const int h1p = h1 < n_in - 1 ? 1 : 0;
+    const float l1 = __fsub_rn(h1r, (float)h1), l0 = __fsub_rn(1.f, l1);
+    float w = 0.f;
+    if (h1 == i) w += l0;
+    if (h1 + h1p == i) w += l1;
+    if (h1 == i || h1 + h1p == i) {
+      if (n < 6) { idx[n] = h2; wgt[n] = w; ++n; }
+    }
+  }
+}
+__global__ void upsample_bilinear2_backward_kernel(const float* __restrict__ go, float* __restrict__ gi, int B, int C, int H,
+                                                   int W, float mul, int accumulate) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const float rh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float rw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(i % W), yh = (int)((i / W) % H);
+    const int64_t pl = i / ((int64_t)W * H);
+    int iy[6], ix[6], ny, nx;
+    float wy[6], wx[6];
+    up_taps(H, Ho, rh, yh, iy, wy, ny);
+    up_taps(W, Wo, rw, xw, ix, wx, nx);
+    const float* g = go + pl * (int64_t)Ho * Wo;
+    float acc = 0.f;
+    for (int a = 0; a < ny; ++a) {
+      float row = 0.f;
+      for (int c = 0; c < nx; ++c) row = fmaf(wx[c], __ldg(g + (int64_t)iy[a] * Wo + ix[c]), row);
+      acc = fmaf(wy[a], row, acc);
+    }
+    acc *= mul;
+    gi[i] = accumulate ? gi[i] + acc : acc;
+  }
+}
+
+// SpatialUpSamplingNearest(scale):updateGradInput: sum of the scale x scale block
+__global__ void upsample_nearest_backward_kernel(const float* __restrict__ go, float* __restrict__ gi, int64_t planes, int H,
+                                                 int W, int scale) {
+  const int64_t total = planes * H * W;
+  const int Wo = W * scale;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(i % W), yh = (int)((i / W) % H);
+    const int64_t pl = i / ((int64_t)W * H);
+    const float* g = go + (pl * H * scale + (int64_t)yh * scale) * Wo + (int64_t)xw * scale;
+    float acc = 0.f;
+    for (int a = 0; a < scale; ++a)
+      for (int c = 0; c < scale; ++c) acc += __ldg(g + (int64_t)a * Wo + c);
+    gi[i] = acc;
+  }
+}
+
+// SpatialSoftMax:updateGradInput: gi = s * (go - sum_c go_c s_c)
+__global__ void softmax_channels_backward_kernel(const float* __restrict__ s, const float* __restrict__ go,
+                                                 float* __restrict__ gi, int B, int C, int64_t hw) {
+  const int64_t total = (int64_t)B * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / hw, p = i % hw;
+    const int64_t o = b * C * hw + p;
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) dot = fmaf(go[o + c * hw], s[o + c * hw], dot);
+    for (int c = 0; c < C; ++c) gi[o + c * hw] = s[o + c * hw] * (go[o + c * hw] - dot);
+  }
+}
+
+// optim.adam (torch/optim adam.lua): m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g g; x -= step * m / (sqrt(v) + eps),
+// step = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the host; weight decay adds wd * x to g first.
+__global__ void adam_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float step, float b1, float b2, float eps, float wd) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    if (wd != 0.f) gi = fmaf(wd, x[i], gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    x[i] = x[i] - step * (mi / (sqrtf(vi) + eps));
+  }
+}
+
+}  // namespace
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stride, const float* gout,
+                                            int64_t gout_batch_stride, float* gw_packed, float* gbias, int B, int Cin,
+                                            int H, int W, int Cout, int stride, b2f_stream_t stream) {
+  if (!x || !gout || !gw_packed) return fail(B2F_EINVAL, "conv3x3_backward_weights: NULL x / gout / gw_packed");
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "conv3x3_backward_weights: bad size");
+  if (stride != 1 && stride != 2) return fail(B2F_EUNSUPPORTED, "conv3x3_backward_weights: stride %d", stride);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int64_t xbs = x_batch_stride ? x_batch_stride : (int64_t)Cin * H * W;
+  const int64_t gbs = gout_batch_stride ? gout_batch_stride : (int64_t)Cout * Ho * Wo;
+  if (xbs < (int64_t)Cin * H * W || gbs < (int64_t)Cout * Ho * Wo)
+    return fail(B2F_EINVAL, "conv3x3_backward_weights: batch stride smaller than one item");
+  if (!aligned4(x) || !aligned4(gout) || !aligned4(gw_packed) || (gbias && !aligned4(gbias)))
+    return fail(B2F_EALIGN, "conv3x3_backward_weights: misaligned pointer");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int CoutP = (Cout + 63) / 64 * 64;
+  const int nci = (Cin + wg::KC - 1) / wg::KC, nco = (Cout + wg::NC - 1) / wg::NC;
+  const int ntiles = B * ((Ho + wg::TH - 1) / wg::TH) * ((Wo + wg::TW - 1) / wg::TW);
+  // enough CTAs for ~3 waves of 2 per SM, at least 4 tiles per CTA so the two-stage pipeline has something to overlap
+  int nsplit = (num_sms() * 6 + nci * nco - 1) / (nci * nco);
+  nsplit = std::max(1, std::min(nsplit, std::max(1, ntiles / 4)));
+  if (nsplit > 65535) nsplit = 65535;
+  const bool vec = (Wo % 4) == 0 && aligned16(gout) && gbs % 4 == 0;
+  dim3 grid(nci * nco, nsplit);
+#define B2F_WG(S, V)                                                                                                  \
+  do {                                                                                                                \
+    auto kern = wg::conv3x3_wgrad<S, V>;                                                                              \
+    static thread_local int attr_dev = -1;                                                                            \
+    int dev = 0;                                                                                                      \
+    B2F_CUDA_TRY(cudaGetDevice(&dev));                                                                                \
+    if (attr_dev != dev) {                                                                                            \
+      B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::Cfg<S>::SMEM_BYTES));  \
+      attr_dev = dev;                                                                                                 \
+    }                                                                                                                 \
+    kern<<<grid, wg::THREADS, wg::Cfg<S>::SMEM_BYTES, st>>>(x, xbs, gout, gbs, gw_packed, gbias, B, Cin, H, W, Cout,   \
+                                                            CoutP, Ho, Wo, nco, nsplit);                              \
+  } while (0)
+  if (stride == 1) {
+    if (vec) B2F_WG(1, true); else B2F_WG(1, false);
+  } else {
+    if (vec) B2F_WG(2, true); else B2F_WG(2, false);
+  }
+#undef B2F_WG
+  B2F_CHECK_LAUNCH("conv3x3_wgrad");
+  return B2F_OK;
+}
+
+extern "C" int b2f_leaky_relu_backward(float* grad, int64_t grad_row_stride, const float* act, int64_t act_row_stride,
+                                       int64_t row_elems, int64_t rows, float slope, b2f_stream_t stream) {
+  if (rows < 0 || row_elems < 0) return fail(B2F_EINVAL, "leaky_relu_backward: negative extent");
+  if (!rows || !row_elems) return B2F_OK;
+  if (!grad || !act) return fail(B2F_EINVAL, "leaky_relu_backward: NULL pointer");
+  if (grad_row_stride < row_elems || act_row_stride < row_elems) return fail(B2F_EINVAL, "leaky_relu_backward: bad stride");
+  leaky_backward_kernel<<<ew_grid(rows * row_elems, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      grad, grad_row_stride, act, act_row_stride, row_elems, rows, slope);
+  B2F_CHECK_LAUNCH("leaky_backward_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_axpy2d(float* dst, int64_t dst_row_stride, const float* src, int64_t src_row_stride, int64_t row_elems,
+                          int64_t rows, float alpha, b2f_stream_t stream) {
+  if (rows < 0 || row_elems < 0) return fail(B2F_EINVAL, "axpy2d: negative extent");
+  if (!rows || !row_elems) return B2F_OK;
+  if (!dst || !src) return fail(B2F_EINVAL, "axpy2d: NULL pointer");
+  if (dst_row_stride < row_elems || src_row_stride < row_elems) return fail(B2F_EINVAL, "axpy2d: bad stride");
+  axpy2d_kernel<<<ew_grid(rows * row_elems, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dst, dst_row_stride, src, src_row_stride, row_elems, rows, alpha);
+  B2F_CHECK_LAUNCH("axpy2d_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_upsample_bilinear2x_backward(const float* grad_out, float* grad_in, int B, int C, int H, int W, float mul,
+                                                int accumulate, b2f_stream_t stream) {
+  if (!grad_out || !grad_in || B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "upsample_bilinear2x_backward: bad argument");
+  if (B == 0) return B2F_OK;
+  upsample_bilinear2_backward_kernel<<<ew_grid((int64_t)B * C * H * W, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      grad_out, grad_in, B, C, H, W, mul, accumulate);
+  B2F_CHECK_LAUNCH("upsample_bilinear2_backward_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_upsample_nearest_backward(const float* grad_out, float* grad_in, int B, int C, int H, int W, int scale,
+                                             b2f_stream_t stream) {
+  if (!grad_out || !grad_in || B < 0 || C <= 0 || H <= 0 || W <= 0 || scale < 1) return fail(B2F_EINVAL, "upsample_nearest_backward: bad argument");
+  if (B == 0) return B2F_OK;
+  upsample_nearest_backward_kernel<<<ew_grid((int64_t)B * C * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      grad_out, grad_in, (int64_t)B * C, H, W, scale);
+  B2F_CHECK_LAUNCH("upsample_nearest_backward_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_softmax_channels_backward(const float* softmax_out, const float* grad_out, float* grad_in, int B, int C,
+                                             int H, int W, b2f_stream_t stream) {
+  if (!softmax_out || !grad_out || !grad_in || B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "softmax_channels_backward: bad argument");
+  if (B == 0) return B2F_OK;
+  softmax_channels_backward_kernel<<<ew_grid((int64_t)B * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      softmax_out, grad_out, grad_in, B, C, (int64_t)H * W);
+  B2F_CHECK_LAUNCH("softmax_channels_backward_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int64_t t, b2f_stream_t stream) {
+  if (n < 0 || t < 1) return fail(B2F_EINVAL, "adam_step: n >= 0 and t >= 1 required (t = %lld)", (long long)t);
+  if (!n) return B2F_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(B2F_EINVAL, "adam_step: NULL pointer");
+  // adam.lua: biasCorrection1 = 1 - beta1^t, biasCorrection2 = 1 - beta2^t, stepSize = lr * sqrt(bc2) / bc1 (doubles)
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  const float step = (float)((double)lr * sqrt(bc2) / bc1);
+  adam_kernel<<<ew_grid(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, step,
+                                                                                  beta1, beta2, eps, weight_decay);
+  B2F_CHECK_LAUNCH("adam_kernel");
+  return B2F_OK;
+}

@@ -89,7 +89,11 @@ def _vp(t):
 
 
 class _Conv:
-    __slots__ = ("w", "b", "cin", "cout", "stride")
+    __slots__ = ("w", "b", "cin", "cout", "stride", "gw", "gb", "wt", "w_off", "b_off")
+
+
+def _round64(n):
+    return (n + 63) // 64 * 64
 
 
 class PWCNet:
@@ -135,7 +139,19 @@ class PWCNet:
         o = self.opt
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
+            # ONE flat buffer for every packed weight and bias (64-float aligned pieces): what getParameters() is to
+            # the reference (train.lua:24) -- the gradient, the Adam moments and the all-reduce use the same layout
+            sizes = []
             for name, cout, cin, stride in conv_shapes(o):
+                kind, lvl, idx = name.split(".")
+                wide = self.past_flow and idx == "0" and kind in ("occ", "flow", "bflow") and int(lvl[1:]) != o.levels
+                sizes.append((int(self.lib.b2f_conv3x3_packed_floats(cin + (2 if wide else 0), cout)), _round64(cout)))
+            total = sum(a + b for a, b in sizes)
+            if getattr(self, "flat_params", None) is None or self.flat_params.numel() != total:
+                self.flat_params = torch.empty(total, device=self.device, dtype=torch.float32)
+                _lib.check(self.lib.b2f_zero_async(_vp(self.flat_params), total * 4, st))
+            off = 0
+            for (name, cout, cin, stride), (nw, nb) in zip(conv_shapes(o), sizes):
                 w = np.ascontiguousarray(np.asarray(params[name + ".weight"], np.float32))
                 b = np.ascontiguousarray(np.asarray(params[name + ".bias"], np.float32))
                 if w.shape != (cout, cin, 3, 3) or b.shape != (cout,):
@@ -153,13 +169,35 @@ class PWCNet:
                     w, cin = wide, cin + 2
                 cv = _Conv()
                 cv.cin, cv.cout, cv.stride = cin, cout, stride
+                cv.w_off, cv.b_off = off, off + nw
                 wt = torch.from_numpy(w).to(self.device)
-                cv.w = torch.empty(int(self.lib.b2f_conv3x3_packed_floats(cin, cout)), device=self.device,
-                                   dtype=torch.float32)
+                cv.w = self.flat_params[off:off + nw]
+                assert nw == int(self.lib.b2f_conv3x3_packed_floats(cin, cout))
                 _lib.check(self.lib.b2f_conv3x3_pack_weights(_vp(wt), _vp(cv.w), cout, cin, 0, st))
-                cv.b = torch.from_numpy(b).to(self.device)
+                cv.b = self.flat_params[off + nw:off + nw + cout]
+                cv.b.copy_(torch.from_numpy(b), non_blocking=False)        # cudaMemcpy H2D
+                cv.gw = cv.gb = cv.wt = None
+                off += nw + nb
                 self._convs[name] = cv
             torch.cuda.current_stream(self.device).synchronize()
+
+    def state_params(self):
+        """Every convolution back in Torch's layout (dict of numpy arrays; the Soft models' widened first decoder
+        convolutions are narrowed again): what `torch.save(model)` would hold."""
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        out = {}
+        with torch.cuda.device(self.device):
+            for name, cout, cin0, _s in conv_shapes(self.opt):
+                cv = self._convs[name]
+                w = torch.empty((cout, cv.cin, 3, 3), device=self.device)
+                _lib.check(self.lib.b2f_conv3x3_pack_weights(_vp(w), _vp(cv.w), cout, cv.cin, 1, st))
+                w = w.cpu().numpy()
+                if cv.cin != cin0:
+                    kind = name.split(".")[0]
+                    w = np.concatenate([w[:, :cin0 - 2], w[:, cin0:cin0 + 2] if kind == "bflow" else w[:, cin0 - 2:cin0]], 1)
+                out[name + ".weight"] = np.ascontiguousarray(w)
+                out[name + ".bias"] = cv.b.cpu().numpy().copy()
+        return out
 
     # ---- plan -------------------------------------------------------------------------------------------
     def _build(self, B, H, W):
@@ -227,6 +265,7 @@ class PWCNet:
             else:
                 conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0)
             plan.keep.append(tmp)
+            plan.tmp[l] = tmp
             prev = feats[l]
         plan.feats = feats
 
@@ -250,11 +289,13 @@ class PWCNet:
 
             def decoder(kind, lane, x0, cin0):
                 t, tb, cin = x0, jbs, cin0
+                chain = []
                 for i, cout in enumerate(DEC):
                     out = E(B, cout, h, w)
-                    plan.keep.append(out)
+                    chain.append(out)
                     conv("%s.l%d.%d" % (kind, l, i), t, tb, B, cin, h, w, P(out), 0, slope=0.2 if i < 5 else 1.0, lane=lane)
                     t, tb, cin = P(out), 0, cout
+                plan.dec[(kind, l)] = (chain, cin0)
                 return out
 
             # occlusion decoder -> softmax -> nearest x 2^(l_st-1) (pwc.lua:288-317)
@@ -265,6 +306,7 @@ class PWCNet:
             skip_occ = E(B, 2, h * up, w * up)
             ops.append((2, lib.b2f_upsample_nearest_forward, (P(occ), P(skip_occ), B, 2, h, w, up)))
             plan.occ[l] = occ
+            plan.skip_occ[l] = skip_occ
 
             # flow decoder(s) (pwc.lua:322-349)
             flows = []
@@ -297,8 +339,10 @@ class PWCNet:
                     ops.append((0, lib.b2f_warp_bdhw_forward, (sl(feats[l - 1], slot * B), P(ufs[l][0]), C.c_float(sc),
                                                                sl(warped[l - 1], slot * B), B, Cn, hn, wn)))
             ops.append(("fork", 1))      # lane 1: output-resolution up-sampling + image warps, off the critical path
+            chains = []
             for u in ufs[l]:
                 t = u
+                chain = [u]
                 for i in range(2, l_st):
                     hh, ww = t.shape[2], t.shape[3]
                     t2 = E(B, 2, 2 * hh, 2 * ww)
@@ -306,7 +350,10 @@ class PWCNet:
                                 (P(t), 0, B, 2, hh, ww, _lib.ptr_array([t2.data_ptr()]), (C.c_int64 * 1)(0), 1,
                                  C.c_float(1.0))))
                     t = t2
+                    chain.append(t)
                 skips.append(t)
+                chains.append(chain)
+            plan.skip_chain[l] = chains
             unit = list(skips) + [skip_occ]
             if self.image_warps:
                 k = l - l_st
@@ -318,11 +365,259 @@ class PWCNet:
                     ops.append((1, lib.b2f_warp_bdhw_forward, (sl(ds[k], slot * B), P(fl), C.c_float(sc), sl(iw, slot * B),
                                                                B, 3, hh, ww)))
                 unit += [iw[:B], iw[B:]]
+                plan.iw[l] = iw
             outs[l] = unit
         plan.ufs = ufs
         plan.warped = warped
         plan.output = [t for l in range(l_st, levels + 1) for t in outs[l]]
         return plan
+
+    # ---- backward plan ------------------------------------------------------------------------------------
+    def _ensure_training_state(self):
+        """Gradient buffer (same flat layout as the parameters), transposed weights for backward-data, Adam moments."""
+        if getattr(self, "flat_grads", None) is not None:
+            return
+        lib, dev = self.lib, self.device
+        n = self.flat_params.numel()
+        self.flat_grads = torch.empty(n, device=dev, dtype=torch.float32)
+        self.adam_m = torch.empty(n, device=dev, dtype=torch.float32)
+        self.adam_v = torch.empty(n, device=dev, dtype=torch.float32)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for t in (self.flat_grads, self.adam_m, self.adam_v):
+            _lib.check(lib.b2f_zero_async(_vp(t), n * 4, st))
+        self.adam_t = 0
+        for name, cv in self._convs.items():
+            nw = cv.b_off - cv.w_off
+            cv.gw = self.flat_grads[cv.w_off:cv.w_off + nw]
+            cv.gb = self.flat_grads[cv.b_off:cv.b_off + cv.cout]
+            cv.wt = torch.empty(int(lib.b2f_conv3x3_packed_floats(cv.cout, cv.cin)), device=dev, dtype=torch.float32)
+
+    def _build_backward(self, plan):
+        """`model:backward(input, gradOutputs)` (train.lua:480) as a list of C-ABI calls: the forward plan walked in
+        reverse.  Gradients with several consumers (nngraph's fan-out nodes) are accumulated with b2f_axpy2d or with
+        the accumulate flag of backward-data; the LeakyReLU derivative of a layer is applied by the backward-data
+        call that produces its output gradient (decoders) or once on the summed gradient (feature pyramid)."""
+        self._ensure_training_state()
+        o, lib, dev = self.opt, self.lib, self.device
+        B, H, W = plan.shape
+        levels, l_st, win = o.levels, o.l_st, o.pwc_ws
+        nd = win * win
+        E = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        hw = lambda l: (H >> (l - 1), W >> (l - 1))
+        P = _vp
+        ops = plan.bops = []
+        nflow = 2 if self.past_flow else 1
+
+        def sl(t, b0=0, c0=0):
+            return C.c_void_p(t.data_ptr() + 4 * (b0 * t.stride(0) + c0 * t.stride(1)))
+
+        def zero(t):
+            ops.append((lib.b2f_zero_async, (P(t), t.numel() * 4)))
+
+        def axpy(dst, dstride, src, sstride, row, rows, alpha=1.0):
+            ops.append((lib.b2f_axpy2d, (dst, dstride or row, src, sstride or row, row, rows, C.c_float(alpha))))
+
+        def wgrad(name, xin, xbs, gout, gbs, nb, cin, h, w):
+            cv = self._convs[name]
+            assert cv.cin == cin
+            ops.append((lib.b2f_conv3x3_backward_weights, (xin, xbs, gout, gbs, P(cv.gw), P(cv.gb), nb, cin, h, w, cv.cout,
+                                                           cv.stride)))
+
+        def dgrad(name, gout, gbs, act, abs_, gin, ibs, acc, nb, cin, h, w, slope=0.2):
+            cv = self._convs[name]
+            ops.append((lib.b2f_conv3x3_backward_data, (gout, gbs, P(cv.wt), act, abs_, gin, ibs, int(acc), nb, cin, h, w,
+                                                        cv.cout, cv.stride, C.c_float(slope))))
+
+        # gradOutputs, in the order of the output table
+        plan.gout = [E(*t.shape) for t in plan.output]
+        per = len(plan.output) // (levels - l_st + 1)
+        zero(self.flat_grads)                                      # model:zeroGradParameters(), train.lua:251
+        for name, cv in self._convs.items():
+            ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
+        g_feats = {l: E(*plan.feats[l].shape) for l in plan.feats}
+        for l in g_feats:
+            zero(g_feats[l])
+        gJ = {l: E(*plan.J[l].shape) for l in plan.J}
+        g_warped = {l: E(*plan.warped[l].shape) for l in plan.warped}
+        plan.g_feats, plan.gJ = g_feats, gJ
+
+        for l in range(l_st, levels + 1):
+            h, w = hw(l)
+            k = l - l_st
+            Cl = FEAT[l - 1]
+            unit = plan.gout[k * per:(k + 1) * per]
+            g_skip = unit[:nflow]
+            g_skip_occ = unit[nflow]
+            hh, ww = g_skip[0].shape[2], g_skip[0].shape[3]
+            # image warps: flow gradient only (the frames are inputs), pwc.lua:441-446
+            if self.image_warps:
+                tmpf = E(B, 2, hh, ww)
+                for slot, sgn in ((0, -1.0), (1, 1.0)):
+                    fi = 1 if (self.past_flow and slot == 0) else 0
+                    sc = o.flownet_factor * sgn / 2.0 ** (l - l_st)
+                    ops.append((lib.b2f_warp_bdhw_backward, (sl(plan.ds[k], slot * B), P(plan.skip_chain[l][fi][-1]),
+                                                             C.c_float(sc), P(unit[nflow + 1 + slot]), None, P(tmpf),
+                                                             B, 3, hh, ww)))
+                    axpy(P(g_skip[fi]), 0, P(tmpf), 0, tmpf.numel(), 1)
+                plan.keep.append(tmpf)
+            g_u = []
+            for fi in range(nflow):
+                g = g_skip[fi]
+                chain = plan.skip_chain[l][fi]
+                for t in reversed(chain[:-1]):                   # output-resolution up-samplings, :374-389
+                    g2 = E(*t.shape)
+                    ops.append((lib.b2f_upsample_bilinear2x_backward, (P(g), P(g2), B, 2, t.shape[2], t.shape[3],
+                                                                       C.c_float(1.0), 0)))
+                    g = g2
+                if g is g_skip[fi]:                               # l_st == 2: the up-sampled flow IS the output
+                    g2 = E(*g.shape)
+                    ops.append((lib.b2f_copy2d_async, (P(g2), g.numel(), P(g), g.numel(), g.numel(), 1)))
+                    g = g2
+                g_u.append(g)
+                if l > l_st:                                      # the next level's decoders read ufs[l] from J[l-1]
+                    Jn = gJ[l - 1]
+                    axpy(P(g), 0, sl(Jn, 0, 2 * nd + FEAT[l - 2] + 2 * fi), Jn.stride(0), g.numel() // B, B)
+            if l > l_st:                                          # feature warps, :402-408 (future flow only)
+                hn, wn = hw(l - 1)
+                Cn = FEAT[l - 2]
+                tmpf = E(B, 2, hn, wn)
+                for slot, sgn in ((0, -1.0), (1, 1.0)):
+                    sc = o.flownet_factor * sgn / 2.0 ** (l - 2)
+                    ops.append((lib.b2f_warp_bdhw_backward, (sl(plan.feats[l - 1], slot * B), P(plan.ufs[l][0]), C.c_float(sc),
+                                                             sl(g_warped[l - 1], slot * B), sl(g_feats[l - 1], slot * B),
+                                                             P(tmpf), B, Cn, hn, wn)))
+                    axpy(P(g_u[0]), 0, P(tmpf), 0, tmpf.numel(), 1)
+                plan.keep.append(tmpf)
+            Jl, gJl = plan.J[l], gJ[l]
+            jbs = Jl.stride(0)
+
+            def decoder_backward(kind, G, first):
+                chain, cin0 = plan.dec[(kind, l)]
+                for i in range(5, -1, -1):
+                    name = "%s.l%d.%d" % (kind, l, i)
+                    if i > 0:
+                        xin, xbs, cin = P(chain[i - 1]), 0, DEC[i - 1]
+                    else:
+                        xin, xbs, cin = P(Jl), jbs, cin0
+                    wgrad(name, xin, xbs, P(G), 0, B, cin, h, w)
+                    if i > 0:
+                        gin = E(B, cin, h, w)
+                        plan.keep.append(gin)
+                        dgrad(name, P(G), 0, P(chain[i - 1]), 0, P(gin), 0, False, B, cin, h, w)
+                        G = gin
+                    else:
+                        dgrad(name, P(G), 0, None, 0, P(gJl), jbs, not first, B, cin, h, w)
+
+            # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
+            g_occ = E(B, 2, h, w)
+            ops.append((lib.b2f_upsample_nearest_backward, (P(g_skip_occ), P(g_occ), B, 2, h, w, 1 << (l_st - 1))))
+            g_logit = E(B, 2, h, w)
+            ops.append((lib.b2f_softmax_channels_backward, (P(plan.occ[l]), P(g_occ), P(g_logit), B, 2, h, w)))
+            plan.keep += [g_occ, g_logit]
+            decoder_backward("occ", g_logit, True)
+            for fi, kind in enumerate(("flow", "bflow")[:nflow]):
+                g_fs = E(B, 2, h, w)
+                plan.keep.append(g_fs)
+                ops.append((lib.b2f_upsample_bilinear2x_backward, (P(g_u[fi]), P(g_fs), B, 2, h, w, C.c_float(1.0), 0)))
+                decoder_backward(kind, g_fs, False)
+            # cost volumes: gradRef of both directions + the joined input's feature slice -> reference features
+            ref = sl(plan.feats[l], 2 * B)
+            tmp_ref, tmp_frm = E(B, Cl, h, w), E(B, Cl, h, w)
+            plan.keep += [tmp_ref, tmp_frm]
+            n_item = Cl * h * w
+            for fwd, slot, c0 in ((1, 1, 0), (0, 0, nd)):
+                frame = sl(plan.feats[l], slot * B) if l == levels else sl(plan.warped[l], slot * B)
+                gfrm = P(tmp_frm) if l == levels else sl(g_warped[l], slot * B)
+                ops.append((lib.b2f_costvol_backward, (_lib.ptr_array([ref.value, frame.value]), 2, B, Cl, h, w, win, fwd,
+                                                       sl(gJl, 0, c0), jbs, _lib.ptr_array([tmp_ref.data_ptr(), gfrm.value]))))
+                axpy(sl(g_feats[l], 2 * B), 0, P(tmp_ref), 0, B * n_item, 1)
+                if l == levels:
+                    axpy(sl(g_feats[l], slot * B), 0, P(tmp_frm), 0, B * n_item, 1)
+            axpy(sl(g_feats[l], 2 * B), n_item, sl(gJl, 0, 2 * nd), jbs, n_item, B)
+
+        # feature pyramid, coarse to fine (pwc.lua:176-211); the three frames share the weights: one batch of 3B
+        for l in range(levels, 1, -1):
+            h, w = hw(l)
+            c_in, c_out = FEAT[l - 2], FEAT[l - 1]
+            gf, f, tmp = g_feats[l], plan.feats[l], plan.tmp[l]
+            ops.append((lib.b2f_leaky_relu_backward, (P(gf), gf.numel(), P(f), f.numel(), gf.numel(), 1, C.c_float(0.2))))
+            wgrad("feat.l%d.1" % l, P(tmp), 0, P(gf), 0, 3 * B, c_out, h, w)
+            g_tmp = E(*tmp.shape)
+            plan.keep.append(g_tmp)
+            dgrad("feat.l%d.1" % l, P(gf), 0, P(tmp), 0, P(g_tmp), 0, False, 3 * B, c_out, h, w)
+            name = "feat.l%d.0" % l
+            if l == 2:
+                for fr, slot in enumerate((0, 2, 1)):
+                    wgrad(name, sl(plan.x, 0, 3 * fr), 9 * H * W, sl(g_tmp, slot * B), 0, B, 3, H, W)
+            else:
+                wgrad(name, P(plan.feats[l - 1]), 0, P(g_tmp), 0, 3 * B, c_in, 2 * h, 2 * w)
+                dgrad(name, P(g_tmp), 0, None, 0, P(g_feats[l - 1]), 0, True, 3 * B, c_in, 2 * h, 2 * w, slope=1.0)
+        plan.g_keep = (g_warped,)
+
+    def backward(self, x, gradOutputs, graph=False):
+        """model:backward(x, gradOutputs) after a forward of the same x: accumulates d loss / d parameters into
+        `flat_grads` (zeroed first, like train.lua:251's zeroGradParameters).  gradOutputs: tensors shaped like the
+        output table (device)."""
+        p = self.plan(x.size(0), x.size(2), x.size(3))
+        if not self.image_warps:
+            raise RuntimeError("backward needs the full output table: build the model with image_warps=True")
+        with torch.cuda.device(self.device):
+            if p.bops is None:
+                self._build_backward(p)
+            if len(gradOutputs) != len(p.gout):
+                raise ValueError("backward: %d gradOutputs for %d outputs" % (len(gradOutputs), len(p.gout)))
+            for dst, src in zip(p.gout, gradOutputs):
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError("backward: gradOutput of shape %r for an output of shape %r" %
+                                     (tuple(src.shape), tuple(dst.shape)))
+                dst.copy_(src, non_blocking=True)
+            self.run_backward(p, graph=graph)
+        return self.flat_grads
+
+    def run_backward(self, p, graph=False):
+        if p.bops is None:
+            self._build_backward(p)
+        if not graph:
+            p.launch_backward()
+            return
+        if p.bgraph is None:
+            saved = [g.clone() for g in p.gout]
+            p.launch_backward()
+            torch.cuda.current_stream().synchronize()
+            for g, sv in zip(p.gout, saved):
+                g.copy_(sv)
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.graph(g, stream=cap):
+                p.launch_backward()
+            p.bgraph = g
+        p.bgraph.replay()
+
+    def grad_params(self):
+        """flat_grads back in Torch's layout (dict of numpy arrays, like state_params)."""
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        out = {}
+        with torch.cuda.device(self.device):
+            for name, cout, cin0, _s in conv_shapes(self.opt):
+                cv = self._convs[name]
+                w = torch.empty((cout, cv.cin, 3, 3), device=self.device)
+                _lib.check(self.lib.b2f_conv3x3_pack_weights(_vp(w), _vp(cv.gw), cout, cv.cin, 1, st))
+                w = w.cpu().numpy()
+                if cv.cin != cin0:
+                    kind = name.split(".")[0]
+                    w = np.concatenate([w[:, :cin0 - 2], w[:, cin0:cin0 + 2] if kind == "bflow" else w[:, cin0 - 2:cin0]], 1)
+                out[name + ".weight"] = np.ascontiguousarray(w)
+                out[name + ".bias"] = cv.gb.cpu().numpy().copy()
+        return out
+
+    def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+        """optim.adam(feval, parameters, optimState) (train.lua:485-486) on the flat buffers."""
+        self._ensure_training_state()
+        self.adam_t += 1
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.b2f_adam_step(_vp(self.flat_params), _vp(self.flat_grads), _vp(self.adam_m), _vp(self.adam_v),
+                                          self.flat_params.numel(), lr, beta1, beta2, eps, weight_decay, self.adam_t, st))
 
     # ---- execution --------------------------------------------------------------------------------------
     def plan(self, B, H, W):
@@ -377,6 +672,9 @@ class _Plan:
         self.keep = []
         self.occ = {}
         self.fs = {}
+        self.tmp, self.dec, self.skip_occ, self.skip_chain, self.iw = {}, {}, {}, {}, {}
+        self.bops = None
+        self.bgraph = None
         self.graph = None
         self._lanes = None
         self.n_launches = 0
@@ -408,3 +706,9 @@ class _Plan:
         for lane in used:
             cur.wait_stream(lanes[lane])
         self.n_launches = n
+
+    def launch_backward(self):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check = _lib.check
+        for fn, args in self.bops:
+            check(fn(*args, st))

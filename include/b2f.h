@@ -235,6 +235,43 @@ B2F_API int b2f_upsample_nearest_forward(const float* x, float* out, int B, int 
 /* nn.SpatialSoftMax (pwc.lua:305): softmax over the channel dimension of (B, C, H, W).                         */
 B2F_API int b2f_softmax_channels_forward(const float* x, float* out, int B, int C, int H, int W, b2f_stream_t stream);
 
+/* ---- training: backward of the conv trunk + optimizer -------------------------------
+ * Weight gradients live in the same PACKED layout as the weights ([Cin * 9][CoutP]), so that parameters, gradients
+ * and the Adam moments of the whole network are one flat buffer each (what getParameters() gives the reference,
+ * train.lua:24) and the gradient all-reduce (b2f_comm.h) is one call; padding entries stay zero.                 */
+/* wt[(co * 9 + 8 - tap)][CinP] <- w_packed: the weights backward-data reads (CinP = Cin rounded up to 64;
+ * b2f_conv3x3_packed_floats(Cout, Cin) floats).                                                                  */
+B2F_API int b2f_conv3x3_transpose_packed(const float* w_packed, float* wt_packed, int Cout, int Cin, b2f_stream_t stream);
+/* SpatialConvolution:updateGradInput fused with the LeakyReLU:updateGradInput of the layer BELOW: gin (B, Cin, H, W)
+ * [+]= conv^T(gout (B, Cout, Ho, Wo)) * (act > 0 ? 1 : leaky_slope), act = that layer's forward output (NULL: no
+ * factor).  accumulate != 0 adds to gin (fan-out nodes of the graph).  Sizes are the FORWARD convolution's.      */
+B2F_API int b2f_conv3x3_backward_data(const float* gout, int64_t gout_batch_stride, const float* wt_packed,
+                                      const float* act, int64_t act_batch_stride, float* gin, int64_t gin_batch_stride,
+                                      int accumulate, int B, int Cin, int H, int W, int Cout, int stride,
+                                      float leaky_slope, b2f_stream_t stream);
+/* SpatialConvolution:accGradParameters: gw_packed += d loss / d weight, gbias (may be NULL) += d loss / d bias.    */
+B2F_API int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stride, const float* gout,
+                                         int64_t gout_batch_stride, float* gw_packed, float* gbias, int B, int Cin,
+                                         int H, int W, int Cout, int stride, b2f_stream_t stream);
+/* LeakyReLU:updateGradInput in place on `rows` rows of `row_elems` floats: grad *= (act > 0 ? 1 : slope).         */
+B2F_API int b2f_leaky_relu_backward(float* grad, int64_t grad_row_stride, const float* act, int64_t act_row_stride,
+                                    int64_t row_elems, int64_t rows, float slope, b2f_stream_t stream);
+/* dst += alpha * src on rows with independent strides: nngraph's gradient accumulation at fan-out nodes and the
+ * level_weights * opt.* scaling of the criterion gradients (train.lua:421-468).                                  */
+B2F_API int b2f_axpy2d(float* dst, int64_t dst_row_stride, const float* src, int64_t src_row_stride, int64_t row_elems,
+                       int64_t rows, float alpha, b2f_stream_t stream);
+/* :updateGradInput of SpatialUpSamplingBilinear(2) (sizes are the forward INPUT's; the result is multiplied by mul and
+ * optionally added to grad_in), SpatialUpSamplingNearest(scale), SpatialSoftMax (softmax_out = the forward result). */
+B2F_API int b2f_upsample_bilinear2x_backward(const float* grad_out, float* grad_in, int B, int C, int H, int W, float mul,
+                                             int accumulate, b2f_stream_t stream);
+B2F_API int b2f_upsample_nearest_backward(const float* grad_out, float* grad_in, int B, int C, int H, int W, int scale,
+                                          b2f_stream_t stream);
+B2F_API int b2f_softmax_channels_backward(const float* softmax_out, const float* grad_out, float* grad_in, int B, int C,
+                                          int H, int W, b2f_stream_t stream);
+/* optim.adam (train.lua:485-486) on flat buffers; t = 1, 2, ... is the step counter (bias correction).            */
+B2F_API int b2f_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int64_t t, b2f_stream_t stream);
+
 /* ---- Middlebury .flo files -- HOST buffers, no device work ----------------
  * File layout (flowExtensions.lua:254-287): float32 tag 202021.25 ("PIEH"), int32 width, int32
  * height, then height*width interleaved (u, v) float32 pairs, all little-endian.  The reference
