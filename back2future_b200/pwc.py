@@ -474,6 +474,7 @@ class PWCNet:
                     ops.append((lib.b2f_copy2d_async, (P(g2), g.numel(), P(g), g.numel(), g.numel(), 1)))
                     g = g2
                 g_u.append(g)
+                plan.keep.append(g)         # every buffer an op points at must outlive this function
                 if l > l_st:                                      # the next level's decoders read ufs[l] from J[l-1]
                     Jn = gJ[l - 1]
                     axpy(P(g), 0, sl(Jn, 0, 2 * nd + FEAT[l - 2] + 2 * fi), Jn.stride(0), g.numel() // B, B)
