@@ -428,6 +428,15 @@ class PWCNet:
             ops.append((lib.b2f_conv3x3_backward_data, (gout, gbs, P(cv.wt), act, abs_, gin, ibs, int(acc), nb, cin, h, w,
                                                         cv.cout, cv.stride, C.c_float(slope))))
 
+        def dec_range(l):
+            """[lo, hi) of level l's decoders in the flat parameter / gradient buffer (they are consecutive there)."""
+            kinds = ("occ", "flow") + (("bflow",) if self.past_flow else ())
+            first, last = self._convs["%s.l%d.0" % (kinds[0], l)], self._convs["%s.l%d.5" % (kinds[-1], l)]
+            return first.w_off, last.b_off + _round64(last.cout)
+
+        # Gradient buckets for the data-parallel all-reduce (SURVEY 8e): (index into bops AFTER which the flat range
+        # [lo, hi) is final).  Backward finishes the finest level's decoders first and the first convUnit last.
+        plan.bucket_marks = []
         # gradOutputs, in the order of the output table
         plan.gout = [E(*t.shape) for t in plan.output]
         per = len(plan.output) // (levels - l_st + 1)
@@ -535,6 +544,7 @@ class PWCNet:
                 if l == levels:
                     axpy(sl(g_feats[l], slot * B), 0, P(tmp_frm), 0, B * n_item, 1)
             axpy(sl(g_feats[l], 2 * B), n_item, sl(gJl, 0, 2 * nd), jbs, n_item, B)
+            plan.bucket_marks.append((len(ops), dec_range(l)))
 
         # feature pyramid, coarse to fine (pwc.lua:176-211); the three frames share the weights: one batch of 3B
         for l in range(levels, 1, -1):
@@ -553,6 +563,8 @@ class PWCNet:
             else:
                 wgrad(name, P(plan.feats[l - 1]), 0, P(g_tmp), 0, 3 * B, c_in, 2 * h, 2 * w)
                 dgrad(name, P(g_tmp), 0, None, 0, P(g_feats[l - 1]), 0, True, 3 * B, c_in, 2 * h, 2 * w, slope=1.0)
+            c0_, c1_ = self._convs["feat.l%d.0" % l], self._convs["feat.l%d.1" % l]
+            plan.bucket_marks.append((len(ops), (c0_.w_off, c1_.b_off + _round64(c1_.cout))))
         plan.g_keep = (g_warped,)
 
     def backward(self, x, gradOutputs, graph=False):
@@ -708,8 +720,9 @@ class _Plan:
             cur.wait_stream(lanes[lane])
         self.n_launches = n
 
-    def launch_backward(self):
+    def launch_backward(self, lo=0, hi=None):
+        """Issue bops[lo:hi] on the current stream."""
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check = _lib.check
-        for fn, args in self.bops:
+        for fn, args in self.bops[lo:hi]:
             check(fn(*args, st))

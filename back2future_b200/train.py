@@ -193,13 +193,36 @@ class Trainer:
         st.loss_host = torch.zeros(st.loss_dev.numel(), dtype=torch.float64).pin_memory()
         return st
 
+    def _segments(self, st):
+        """The step as a list of (launch function, gradient bucket or None): with more than one rank the backward plan
+        is cut after every point where a range of the flat gradient becomes final, so that its all-reduce runs on the
+        communication stream under the rest of the backward (train.lua's DataParallelTable reduces after the whole
+        backward).  One rank: a single segment."""
+        p = st.plan
+
+        def head():
+            p.launch()
+            s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for fn, args in st.ops:
+                _lib.check(fn(*args, s))
+
+        if self.comm is None or self.comm.world == 1:
+            return [(lambda: (head(), p.launch_backward()), None)]
+        segs, lo = [], 0
+        for k, (idx, rng) in enumerate(p.bucket_marks):
+            a, b = lo, idx
+            if k == 0:
+                segs.append((lambda a=a, b=b: (head(), p.launch_backward(a, b)), rng))
+            else:
+                segs.append((lambda a=a, b=b: p.launch_backward(a, b), rng))
+            lo = idx
+        assert lo == len(p.bops)
+        return segs
+
     def _launch(self, st):
         """forward plan -> criterions -> backward plan, on the current stream (+ the forward plan's side lanes)."""
-        st.plan.launch()
-        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for fn, args in st.ops:
-            _lib.check(fn(*args, s))
-        st.plan.launch_backward()
+        for fn, _rng in self._segments(st):
+            fn()
 
     # ---- trainBatch ---------------------------------------------------------------------------------------
     def train_batch(self, inputs, graph=True, step=True):
@@ -216,23 +239,31 @@ class Trainer:
                 _lib.check(self.lib.b2f_reserve_scratch(1 << 20))
             st = self._steps[key]
             st.plan.x.copy_(inputs, non_blocking=True)
-            if graph:
-                if st.graph is None:
-                    self._launch(st)                                   # warm-up: attributes, tensor maps, scratch
-                    torch.cuda.current_stream().synchronize()
+            cur = torch.cuda.current_stream()
+            segs = self._segments(st)
+            if graph and st.graph is None:
+                self._launch(st)                                       # warm-up: attributes, tensor maps, scratch
+                cur.synchronize()
+                st.graph = []
+                for fn, _rng in segs:
                     g = torch.cuda.CUDAGraph()
                     cap = torch.cuda.Stream(net.device)
-                    cap.wait_stream(torch.cuda.current_stream())
+                    cap.wait_stream(cur)
                     with torch.cuda.graph(g, stream=cap):
-                        self._launch(st)
-                    st.graph = g
-                st.graph.replay()
-            else:
-                self._launch(st)
-            cur = torch.cuda.current_stream()
-            if self.comm is not None and self.comm.world > 1:
-                self._comm_stream.wait_stream(cur)
-                self.comm.allreduce_sum(net.flat_grads, stream=self._comm_stream)
+                        fn()
+                    st.graph.append(g)
+            multi = self.comm is not None and self.comm.world > 1
+            for i, (fn, rng) in enumerate(segs):
+                if graph:
+                    st.graph[i].replay()
+                else:
+                    fn()
+                if multi and rng is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    self._comm_stream.wait_event(ev)
+                    self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
+            if multi:
                 cur.wait_stream(self._comm_stream)
             if step:
                 net.adam_step(self.opt.LR, self.opt.beta1, self.opt.beta2, self.opt.epsilon, self.opt.weightDecay)

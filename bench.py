@@ -545,6 +545,58 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
 
 
 # ----------------------------------------------------------------------------------------
+# training steps (BASELINE configs[2], [3]): forward + criterions + backward + all-reduce + Adam
+# ----------------------------------------------------------------------------------------
+
+def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
+    """One optimisation step of train.lua:196-496 through back2future_b200.train.Trainer at the reference's training
+    shape (8 samples per GPU, 9 x 320 x 640), inputs uploaded from pinned host memory every step (inside the timed
+    region), losses read back every step (cutorch.synchronize, train.lua:498).  With N > 1 the flat gradient is
+    all-reduced through libb2f_comm.so in 11 buckets started from events inside the backward; `allreduce_exposed_ms`
+    is the step time minus the same step without the collective."""
+    from back2future_b200 import pwc, train, comm as bcomm
+    H, W = 320, 640
+    out = {"shape": "%d x 9 x %d x %d per GPU" % (B, H, W)}
+    cm = bcomm.Communicator.from_env() if world > 1 else None
+    hin = torch.empty(B, 9, H, W).uniform_(-2.1, 2.6).pin_memory()
+    for key, past_flow, topt in (("config2_hard", False, train.TrainOpt.hard()), ("config3_soft", True, train.TrainOpt.soft())):
+        net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True)
+        res = {}
+        for label, c in ((("with_allreduce", cm),) if world > 1 else ()) + (("local", None),):
+            tr = train.Trainer(net, topt, comm=c)
+            for _ in range(2):
+                losses = tr.train_batch(hin)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                losses = tr.train_batch(hin)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            res[label] = ms
+            del tr
+        step_ms = res.get("with_allreduce", res["local"])
+        out[key] = {"ms_per_step": round(step_ms, 3), "samples_per_s": round(world * B / step_ms * 1e3, 1),
+                    "h2d_bytes_per_step": B * 9 * H * W * 4, "loss": round(losses["err"], 4),
+                    "parameters": net.n_params(), "flat_gradient_floats": int(net.flat_params.numel())}
+        if world > 1:
+            out[key]["step_without_allreduce_ms"] = round(res["local"], 3)
+            out[key]["allreduce_exposed_ms"] = round(res["with_allreduce"] - res["local"], 3)
+        del net
+        torch.cuda.empty_cache()
+    if cm is not None:
+        cm.destroy()
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # criterions (BASELINE configs[2], [3]): informational block, not part of `value`
 # ----------------------------------------------------------------------------------------
 
@@ -999,6 +1051,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-criterions", action="store_true")
     ap.add_argument("--no-network", action="store_true", help="skip the whole-network (conv trunk included) block")
+    ap.add_argument("--no-training", action="store_true", help="skip the training-step block")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed step's outputs")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--eager", action="store_true", help="time eager C-ABI calls on one stream instead of the CUDA graph")
@@ -1233,6 +1286,9 @@ def main():
     network = None
     if not args.no_network:
         network = time_network(torch, dev, world, rank, dist, cpu=not args.no_cpu)
+    training = None
+    if not args.no_training:
+        training = time_training(torch, dev, world, rank, dist)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, desc, sps, n = time_cpu(args.cpu_budget)
@@ -1272,7 +1328,7 @@ def main():
                                     for r in sorted(rows, key=lambda r: -r["ms"])[:12]] if rows else None),
             "cpu_baseline": cpu,
             "criterions": crit, "flow_variants": flow_var, "inference_shapes": infer, "allreduce": allreduce,
-            "whole_network": network,
+            "whole_network": network, "training": training,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
