@@ -1065,6 +1065,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE line (the JSON record): anything a library prints there (NCCL's version banner at
+    # communicator creation, ...) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from back2future_b200 import _lib
@@ -1218,49 +1224,32 @@ def main():
     # time alone, and the step time when it runs under the next step's kernels (outside the timed region).
     allreduce = None
     if world > 1:
-        from back2future_b200.dist import GradientAllReduce, NPARAMS_HARD
+        # the collective alone, through libb2f_comm.so (the C ABI a LuaJIT host binds); how much of it a training step
+        # exposes is measured on a real backward in the `training` block (allreduce_exposed_ms)
+        from back2future_b200 import comm as bcomm
+        from back2future_b200.dist import NPARAMS_HARD
+        cm = bcomm.Communicator.from_env()
         flat = torch.randn(NPARAMS_HARD, device=dev)
-        ar = GradientAllReduce(flat)
-
-        def timed(fn, n):
-            barrier()
-            torch.cuda.synchronize()
-            ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ta.record()
-            for _ in range(n):
-                fn()
-            tb.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([ta.elapsed_time(tb) / n], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return t.item()
-
-        def alone():
-            ar.start()
-            ar.wait()
-
-        def overlapped():
-            ar.wait()             # the previous step's reduction must be done before its buffer is reused
-            if graph is not None:
-                graph.replay()
-            else:
-                wl.step()
-            ar.start()            # "backward has produced the gradient": reduce under the next step
-
         for _ in range(3):
-            alone()
-        t_alone = timed(alone, 20)
-        for _ in range(3):
-            overlapped()
-        t_over = timed(overlapped, 30)
-        ar.wait()
+            cm.allreduce_sum(flat)
         torch.cuda.synchronize()
+        barrier()
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta.record()
+        for _ in range(20):
+            cm.allreduce_sum(flat)
+        tb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ta.elapsed_time(tb) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_alone = t.item()
         nbytes = flat.numel() * 4
-        allreduce = {"floats": flat.numel(), "bytes": nbytes, "alone_ms": round(t_alone, 4),
+        allreduce = {"api": "b2f_comm_allreduce_sum_f32 (libb2f_comm.so -> ncclAllReduce)", "floats": flat.numel(),
+                     "bytes": nbytes, "alone_ms": round(t_alone, 4),
                      "busbw_GBps": round(2 * (world - 1) / world * nbytes / (t_alone * 1e-3) / 1e9, 1),
-                     "step_ms": round(ms / K, 4), "step_with_allreduce_ms": round(t_over, 4),
-                     "backend": dist.get_backend()}
-        del flat, ar
+                     "overlap": "see training.*.allreduce_exposed_ms"}
+        cm.destroy()
+        del flat, cm
 
     # ---- per-kernel breakdown (informational) and CPU baseline (rank 0) ----------------
     rows = breakdown(torch, wl) if rank == 0 else None
@@ -1330,7 +1319,8 @@ def main():
             "criterions": crit, "flow_variants": flow_var, "inference_shapes": infer, "allreduce": allreduce,
             "whole_network": network, "training": training,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and parity["failed"]:
