@@ -1,0 +1,392 @@
+// 3x3 convolution (stride 1, pad 1) + bias + LeakyReLU on the 5th-generation tensor cores (tcgen05 / TMEM) for sm_100a.
+// The decoders of models/pwc.lua:76-85 are 93 % of the network's arithmetic: nn.SpatialConvolution
+// (nIn, nOut, 3, 3, 1, 1, 1, 1) + nn.LeakyReLU(0.2) as an implicit GEMM
+//
+//     D[128 pixels, N = Cout] += sum over taps (ky, kx), 32-channel chunks c:   A_tap,c [128, 32] * W_tap,c [N, 32]^T
+//
+// with kind::tf32 MMAs.  One TF32 pass loses 13 mantissa bits (measured 2.8e-3 relative on a 64-term dot product,
+// tools/ubench/tc_gemm.cu), far outside the 1e-4 parity bar through a six-layer decoder, so every operand is SPLIT:
+// x = x_hi + x_lo with x_hi = x & 0xFFFFE000 (exactly representable in TF32) and x_lo = x - x_hi, and the product is
+// x_hi w_hi + x_lo w_hi + x_hi w_lo (three passes, fp32 accumulation in TMEM; measured 7e-6 relative).  The fourth term
+// x_lo w_lo is below 2^-22 of the product.
+//
+// Layout (what makes the implicit GEMM free of any in-kernel gather): activations between tensor-core layers live
+// channel-minor, (B, H, W, Cp) with Cp = channels rounded up to 32, as TWO tensors (hi, lo) written by the producing
+// layer's epilogue.  One TMA box {32 channels, 18 x, 9 y} lands an input patch as 162 rows of 128 bytes -- exactly the
+// K-major SWIZZLE_128B operand layout of the MMA -- and because the MMA unit applies the swizzle to ABSOLUTE
+// shared-memory address bits (verified: a descriptor whose start address is offset by any multiple of 128 bytes reads
+// the rows shifted by that many pixels, tools/ubench/tc_gemm.cu), the operand of tap (ky, kx) is the SAME buffer with the
+// descriptor start advanced by (18 ky + kx) rows.  An output tile is 7 rows x 16 columns enumerated with the input
+// pitch (m = 18 y + x, 126 of the 128 MMA rows; x = 16, 17 are scratch columns): 112 useful pixels per 128.
+//
+// CTA = 4 warps: warp 0 lane 0 issues TMA loads (input patch hi/lo per chunk, double buffered; weights hi/lo per
+// (chunk, tap) through a 4-deep ring), warp 1 lane 0 issues the MMAs (12 per stage: 3 passes x 4 k-steps of 8) and frees
+// stages with tcgen05.commit, then all four warps read the accumulator (tcgen05.ld 32x32b), add the bias, apply the
+// activation, split, and either stage the tile in shared memory for TMA stores into the next layer's (hi, lo) tensors or
+// write planar (B, C, H, W) fp32 for the consumers outside the tensor-core chain.
+#include "tma.cuh"
+
+#include <algorithm>
+
+namespace b2f {
+namespace {
+namespace tc {
+
+constexpr int TH = 7, TW = 16, PW = TW + 2;        // output tile; PW = input pitch
+constexpr int A_ROWS = (TH + 2) * PW;               // 162 rows of 128 bytes
+constexpr int A_BYTES = A_ROWS * 128;               // one of (hi, lo)
+constexpr int A_SLOT = (A_BYTES + 4 * 128 + 1023) / 1024 * 1024;   // + the 4 rows the last taps read past the box
+constexpr int NB = 4;                               // weight stages
+constexpr int THREADS = 128;
+
+template <int N>
+struct Cfg {
+  static constexpr int B_BYTES = N * 128;           // one of (hi, lo), one (chunk, tap)
+  static constexpr int B_SLOT = 2 * B_BYTES;
+  static constexpr int A_STAGE = 2 * A_SLOT;
+  static constexpr int SMEM_MAIN = 2 * A_STAGE + NB * B_SLOT;
+  static constexpr int NG = (N + 31) / 32;          // 32-channel output groups
+  static constexpr int STAGING = NG * 2 * (TH * TW * 128);
+  static constexpr int SMEM_BYTES = (SMEM_MAIN > STAGING ? SMEM_MAIN : STAGING) + 256 + 1024;
+  static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(N % 16 == 0 && N >= 16 && N <= 256, "tcgen05.mma M = 128 needs N % 16 == 0");
+};
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  // K-major, SWIZZLE_128B (layout type 2 at bits 61-63), SBO = 1024 B (8 rows), LBO = 1 (unused), version 1
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Args {
+  const float* bias;      // [Cout] or NULL
+  float* out_planar;      // optional (B, Cout, H, W) fp32, batch stride pbs
+  int64_t pbs;
+  int nchunk;             // Cin_p / 32
+  int Cout, H, W, tiles_x, tiles_y;
+  float slope;
+  int store_split;        // TMA-store (hi, lo) channel-minor tensors
+};
+
+template <int N>
+__global__ void __launch_bounds__(THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+                  const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+                  const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol, const Args a) {
+  using cfg = Cfg<N>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_buf = smem;                                  // [2 stages][hi, lo][A_SLOT]
+  uint8_t* b_buf = smem + 2 * cfg::A_STAGE;               // [NB][hi, lo][B_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (cfg::SMEM_MAIN > cfg::STAGING ? cfg::SMEM_MAIN : cfg::STAGING));
+  uint64_t* a_full = bars;                 // [2]
+  uint64_t* a_empty = bars + 2;            // [2]
+  uint64_t* b_full = bars + 4;             // [NB]
+  uint64_t* b_empty = bars + 4 + NB;       // [NB]
+  uint64_t* acc_full = bars + 4 + 2 * NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x, b = blockIdx.y;
+  const int x0 = tx * TW, y0 = ty * TH;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer ----
+    int bs = 0;
+    for (int c = 0; c < a.nchunk; ++c) {
+      const int as = c & 1;
+      if (c >= 2) mbar_wait(&a_empty[as], ((c >> 1) - 1) & 1);
+      mbar_arrive_expect_tx(&a_full[as], 2 * A_BYTES);
+      tma_load_4d(a_buf + as * cfg::A_STAGE, &tm_xh, c * 32, x0 - 1, y0 - 1, b, &a_full[as]);
+      tma_load_4d(a_buf + as * cfg::A_STAGE + A_SLOT, &tm_xl, c * 32, x0 - 1, y0 - 1, b, &a_full[as]);
+      for (int t = 0; t < 9; ++t, ++bs) {
+        const int s = bs % NB;
+        if (bs >= NB) mbar_wait(&b_empty[s], ((bs / NB) - 1) & 1);
+        mbar_arrive_expect_tx(&b_full[s], 2 * cfg::B_BYTES);
+        tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, 0, t, 0, &b_full[s]);
+        tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, 0, t, 0, &b_full[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer ----
+    // instruction descriptor: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at bit 17,
+    // M >> 4 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int bs = 0;
+    uint32_t acc = 0;
+    for (int c = 0; c < a.nchunk; ++c) {
+      const int as = c & 1;
+      mbar_wait(&a_full[as], (c >> 1) & 1);
+      const uint32_t ah = smem_u32(a_buf + as * cfg::A_STAGE), al = ah + A_SLOT;
+      for (int t = 0; t < 9; ++t, ++bs) {
+        const int s = bs % NB;
+        mbar_wait(&b_full[s], (bs / NB) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t shift = (uint32_t)((t / 3) * PW + (t % 3)) * 128u;
+        const uint32_t bh = smem_u32(b_buf + s * cfg::B_SLOT), bl = bh + cfg::B_BYTES;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {            // hi * hi, lo * hi, hi * lo
+          const uint32_t pa = (p == 1 ? al : ah) + shift, pb = (p == 2 ? bl : bh);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_tf32(tmem, smem_desc(pa + 32u * k), smem_desc(pb + 32u * k), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&b_empty[s]);               // the weight stage is free once these MMAs have read it
+      }
+      umma_commit(&a_empty[as]);
+    }
+    umma_commit(acc_full);
+  }
+  __syncwarp();
+
+  // ---- epilogue: all four warps; warp w owns TMEM lanes 32 w .. 32 w + 31 = tile rows m ----
+  mbar_wait(acc_full, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int m = 32 * warp + lane;
+  const int ry = m / PW, rx = m % PW;
+  const bool valid = ry < TH && rx < TW;
+  const int y = y0 + ry, x = x0 + rx;
+  const bool inside = valid && y < a.H && x < a.W;
+  const int prow = ry * TW + rx;                          // row of the staged (dense 7 x 16) tile
+  const uint32_t stage0 = smem_u32(smem);
+#pragma unroll 1
+  for (int g = 0; g < cfg::NG; ++g) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * g), v);
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = 32 * g + j;
+      float t = __uint_as_float(v[j]) + ((a.bias && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
+      t = t > 0.f ? t : t * a.slope;
+      f[j] = n < a.Cout ? t : 0.f;
+    }
+    if (a.out_planar && inside) {
+      float* o = a.out_planar + (size_t)b * a.pbs + (size_t)y * a.W + x;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] = f[j];
+    }
+    if (a.store_split && valid) {
+      const uint32_t rh = stage0 + (uint32_t)((2 * g) * (TH * TW * 128) + prow * 128);
+      const uint32_t rl = rh + TH * TW * 128;
+      const uint32_t sw = (uint32_t)(prow & 7);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(f[4 * q]) & 0xFFFFE000u);
+        hi.y = __uint_as_float(__float_as_uint(f[4 * q + 1]) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(f[4 * q + 2]) & 0xFFFFE000u);
+        hi.w = __uint_as_float(__float_as_uint(f[4 * q + 3]) & 0xFFFFE000u);
+        lo.x = f[4 * q] - hi.x; lo.y = f[4 * q + 1] - hi.y; lo.z = f[4 * q + 2] - hi.z; lo.w = f[4 * q + 3] - hi.w;
+        sts128(rh + 16u * ((uint32_t)q ^ sw), hi);
+        sts128(rl + 16u * ((uint32_t)q ^ sw), lo);
+      }
+    }
+  }
+  if (a.store_split) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int g = 0; g < cfg::NG; ++g) {
+        tma_store_4d_addr(stage0 + (uint32_t)((2 * g) * (TH * TW * 128)), &tm_oh, 32 * g, x0, y0, b);
+        tma_store_4d_addr(stage0 + (uint32_t)((2 * g + 1) * (TH * TW * 128)), &tm_ol, 32 * g, x0, y0, b);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cfg::TMEM_COLS) : "memory");
+}
+
+// planar (B, C, H, W) [batch stride xbs] -> channel-minor (B, H, W, Cp) hi / lo
+__global__ void split_from_planar_kernel(const float* __restrict__ x, int64_t xbs, float* __restrict__ hi, float* __restrict__ lo,
+                                         int C, int Cp, int64_t hw) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8 threads
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t p = p0 + tx;
+    tile[i][tx] = (c < C && p < hw) ? x[(size_t)b * xbs + (size_t)c * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t p = p0 + i;
+    if (p >= hw) continue;
+    const float v = tile[tx][i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const size_t o = ((size_t)b * hw + p) * Cp + c0 + tx;
+    hi[o] = h;
+    lo[o] = v - h;
+  }
+}
+
+// Torch (Cout, Cin, 3, 3) -> [9 taps][Cout][Cin_p] hi / lo (K-major rows of the B operand)
+__global__ void pack_tc_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int Cout,
+                                       int Cin, int CinP) {
+  const int total = 9 * Cout * CinP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % CinP, n = (i / CinP) % Cout, t = i / (CinP * Cout);
+    const float v = ci < Cin ? w[((size_t)n * Cin + ci) * 9 + t] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+template <int N>
+int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
+              int CinP, int CoutP, cudaStream_t st) {
+  using cfg = Cfg<N>;
+  Args a = a0;
+  CUtensorMap txh, txl, twh, twl, toh, tol;
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)CinP, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)CinP, (uint64_t)CinP * a.W, (uint64_t)CinP * a.W * a.H};
+    const uint32_t box[4] = {32, (uint32_t)PW, (uint32_t)(TH + 2), 1};
+    if ((rc = make_tmap4(&txh, xh, dims, str, box, true))) return rc;
+    if ((rc = make_tmap4(&txl, xl, dims, str, box, true))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)CinP, (uint64_t)a.Cout, 9, 1};
+    const uint64_t str[3] = {(uint64_t)CinP, (uint64_t)CinP * a.Cout, (uint64_t)CinP * a.Cout * 9};
+    const uint32_t box[4] = {32, (uint32_t)N, 1, 1};
+    if ((rc = make_tmap4(&twh, wh, dims, str, box, true))) return rc;
+    if ((rc = make_tmap4(&twl, wl, dims, str, box, true))) return rc;
+  }
+  if (a.store_split) {
+    const uint64_t dims[4] = {(uint64_t)CoutP, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)CoutP, (uint64_t)CoutP * a.W, (uint64_t)CoutP * a.W * a.H};
+    const uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+    if ((rc = make_tmap4(&toh, oh, dims, str, box, true))) return rc;
+    if ((rc = make_tmap4(&tol, ol, dims, str, box, true))) return rc;
+  } else {
+    toh = txh;
+    tol = txl;
+  }
+  auto kern = conv3x3_tc_kernel<N>;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  B2F_CUDA_TRY(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    attr_dev = dev;
+  }
+  a.tiles_x = (a.W + TW - 1) / TW;
+  a.tiles_y = (a.H + TH - 1) / TH;
+  dim3 grid(a.tiles_x * a.tiles_y, B);
+  kern<<<grid, THREADS, cfg::SMEM_BYTES, st>>>(txh, txl, twh, twl, toh, tol, a);
+  B2F_CHECK_LAUNCH("conv3x3_tc_kernel");
+  return B2F_OK;
+}
+
+}  // namespace tc
+}  // namespace
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout) {
+  if (Cin <= 0 || Cout <= 0) return 0;
+  return (int64_t)9 * Cout * ((Cin + 31) / 32 * 32);
+}
+
+extern "C" int b2f_conv3x3_tc_pack_weights(const float* w_torch, float* w_hi, float* w_lo, int Cout, int Cin,
+                                           b2f_stream_t stream) {
+  if (!w_torch || !w_hi || !w_lo || Cout <= 0 || Cin <= 0) return fail(B2F_EINVAL, "conv3x3_tc_pack_weights: bad argument");
+  const int CinP = (Cin + 31) / 32 * 32;
+  const int total = 9 * Cout * CinP;
+  tc::pack_tc_weights_kernel<<<std::max(1, std::min((total + 255) / 256, num_sms() * 8)), 256, 0,
+                               reinterpret_cast<cudaStream_t>(stream)>>>(w_torch, w_hi, w_lo, Cout, Cin, CinP);
+  B2F_CHECK_LAUNCH("pack_tc_weights_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, float* hi, float* lo, int B, int C, int H, int W,
+                                        b2f_stream_t stream) {
+  if (!x || !hi || !lo || B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "nhwc_split_from_bdhw: bad argument");
+  if (B == 0) return B2F_OK;
+  const int Cp = (C + 31) / 32 * 32;
+  const int64_t hw = (int64_t)H * W;
+  const int64_t xbs = x_batch_stride ? x_batch_stride : (int64_t)C * hw;
+  if (B > 65535) return fail(B2F_EINVAL, "nhwc_split_from_bdhw: B > 65535");
+  dim3 grid((unsigned)((hw + 31) / 32), Cp / 32, B);
+  tc::split_from_planar_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, xbs, hi, lo, C, Cp, hw);
+  B2F_CHECK_LAUNCH("split_from_planar_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                      const float* bias, float* out_hi, float* out_lo, float* out_planar,
+                                      int64_t out_planar_batch_stride, int B, int Cin, int H, int W, int Cout,
+                                      float leaky_slope, b2f_stream_t stream) {
+  if (!x_hi || !x_lo || !w_hi || !w_lo) return fail(B2F_EINVAL, "conv3x3_tc_forward: NULL input / weights");
+  if ((out_hi == nullptr) != (out_lo == nullptr)) return fail(B2F_EINVAL, "conv3x3_tc_forward: out_hi and out_lo go together");
+  if (!out_hi && !out_planar) return fail(B2F_EINVAL, "conv3x3_tc_forward: no output");
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "conv3x3_tc_forward: bad size");
+  if (B > 65535) return fail(B2F_EINVAL, "conv3x3_tc_forward: B > 65535");
+  if (!aligned16(x_hi) || !aligned16(x_lo) || !aligned16(w_hi) || !aligned16(w_lo) || (out_hi && (!aligned16(out_hi) || !aligned16(out_lo))))
+    return fail(B2F_EALIGN, "conv3x3_tc_forward: operands must be 16-byte aligned");
+  if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: cuTensorMapEncodeTiled not available");
+  if (B == 0) return B2F_OK;
+  const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
+  tc::Args a{};
+  a.bias = bias;
+  a.out_planar = out_planar;
+  a.pbs = out_planar_batch_stride ? out_planar_batch_stride : (int64_t)Cout * H * W;
+  a.nchunk = CinP / 32;
+  a.Cout = Cout; a.H = H; a.W = W;
+  a.slope = leaky_slope;
+  a.store_split = out_hi != nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (Cout) {
+    case 32: return tc::launch_tc<32>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 64: return tc::launch_tc<64>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 96: return tc::launch_tc<96>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 128: return tc::launch_tc<128>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    default: return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: Cout = %d is not one of the decoder widths (32, 64, 96, 128)", Cout);
+  }
+}

@@ -235,6 +235,25 @@ B2F_API int b2f_upsample_nearest_forward(const float* x, float* out, int B, int 
 /* nn.SpatialSoftMax (pwc.lua:305): softmax over the channel dimension of (B, C, H, W).                         */
 B2F_API int b2f_softmax_channels_forward(const float* x, float* out, int B, int C, int H, int W, b2f_stream_t stream);
 
+/* ---- the decoders' convolutions on the tensor cores (tcgen05 / TMEM; inference) ---------------------------------
+ * Same module as b2f_conv3x3_forward with stride 1 (SpatialConvolution + LeakyReLU, pwc.lua:76-85), as a TF32 implicit
+ * GEMM with every operand split x = x_hi + x_lo (x_hi = x & 0xFFFFE000) and three MMA passes (hi*hi + lo*hi + hi*lo):
+ * fp32-level accuracy (7e-6 relative measured, tools/ubench/tc_gemm.cu) where one TF32 pass gives 3e-3.
+ * Activations between such layers are CHANNEL-MINOR (B, H, W, Cp), Cp = C rounded up to 32, as a (hi, lo) pair of
+ * tensors; b2f_nhwc_split_from_bdhw converts a planar (B, C, H, W) tensor (batch-strided: the decoder's joined input).
+ * Weights: [9 taps][Cout][Cin_p] hi / lo, b2f_conv3x3_tc_packed_floats(Cin, Cout) floats each.
+ * Outputs: out_hi / out_lo (both or neither; (B, H, W, Cout rounded up to 32)) for the next tensor-core layer and / or
+ * out_planar (B, Cout, H, W) fp32 with its batch stride (0 = dense) for every other consumer.  Cout in {32, 64, 96, 128}. */
+B2F_API int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout);
+B2F_API int b2f_conv3x3_tc_pack_weights(const float* w_torch, float* w_hi, float* w_lo, int Cout, int Cin,
+                                        b2f_stream_t stream);
+B2F_API int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, float* hi, float* lo, int B, int C, int H,
+                                     int W, b2f_stream_t stream);
+B2F_API int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                                   const float* bias, float* out_hi, float* out_lo, float* out_planar,
+                                   int64_t out_planar_batch_stride, int B, int Cin, int H, int W, int Cout,
+                                   float leaky_slope, b2f_stream_t stream);
+
 /* ---- training: backward of the conv trunk + optimizer -------------------------------
  * Weight gradients live in the same PACKED layout as the weights ([Cin * 9][CoutP]), so that parameters, gradients
  * and the Adam moments of the whole network are one flat buffer each (what getParameters() gives the reference,

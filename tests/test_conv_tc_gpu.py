@@ -1,0 +1,98 @@
+"""Tensor-core 3x3 convolution (tcgen05, three-pass TF32 split) against the float64 oracle, through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _p(t, off=0):
+    return C.c_void_p(t.data_ptr() + 4 * off) if t is not None else None
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _run(lib, _lib, x, w, b, slope, want_split, want_planar, x_c_total=None, x_c0=0):
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    cinp, coutp = (Cin + 31) // 32 * 32, (Cout + 31) // 32 * 32
+    xt = x_c_total or Cin
+    xw = torch.zeros(B, xt, H, W, device="cuda")
+    xw[:, x_c0:x_c0 + Cin] = _dev(x)
+    xh, xl = torch.empty(B, H, W, cinp, device="cuda"), torch.empty(B, H, W, cinp, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(xw, x_c0 * H * W), xt * H * W, _p(xh), _p(xl), B, Cin, H, W, _st()))
+    n = int(lib.b2f_conv3x3_tc_packed_floats(Cin, Cout))
+    wh, wl = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    wd = _dev(w)
+    _lib.check(lib.b2f_conv3x3_tc_pack_weights(_p(wd), _p(wh), _p(wl), Cout, Cin, _st()))
+    bd = _dev(b) if b is not None else None
+    oh = torch.full((B, H, W, coutp), 9.0, device="cuda") if want_split else None
+    ol = torch.full((B, H, W, coutp), 9.0, device="cuda") if want_split else None
+    op = torch.full((B, Cout + 2, H, W), 7.0, device="cuda") if want_planar else None
+    _lib.check(lib.b2f_conv3x3_tc_forward(_p(xh), _p(xl), _p(wh), _p(wl), _p(bd), _p(oh), _p(ol),
+                                          _p(op, 2 * H * W) if want_planar else None, (Cout + 2) * H * W if want_planar else 0,
+                                          B, Cin, H, W, Cout, slope, _st()))
+    torch.cuda.synchronize()
+    # the split of the input is exact and its pad channels are zero
+    xs = (xh.double() + xl.double()).cpu().numpy()
+    assert np.array_equal(xs[..., :Cin], x.transpose(0, 2, 3, 1).astype(np.float64))
+    assert not xs[..., Cin:].any()
+    assert bool(((xh.view(torch.int32) & 0x1FFF) == 0).all())
+    return oh, ol, op
+
+
+CASES = [
+    # B, Cin, H, W, Cout
+    (1, 196, 21, 40, 128),     # decoder conv 0 at level 3: channels padded 196 -> 224, ragged tile columns
+    (2, 128, 14, 32, 128),
+    (1, 128, 16, 32, 96),
+    (1, 96, 9, 20, 64),
+    (1, 64, 7, 16, 32),
+    (1, 354, 7, 16, 128),      # coarsest level
+    (1, 32, 30, 50, 64),       # ragged in both directions
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv3x3_tc_forward(case):
+    from back2future_b200 import _lib
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    lib = _lib.load()
+    B, Cin, H, W, Cout = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = po.leaky_relu(po.conv3x3(x, w, b, 1))
+    oh, ol, op = _run(lib, _lib, x, w, b, 0.2, True, True, x_c_total=Cin + 3, x_c0=3)
+    got = (oh.double() + ol.double()).cpu().numpy()
+    assert o.rel_err(got[..., :Cout].transpose(0, 3, 1, 2), ref) < TOL
+    assert not got[..., Cout:].any()
+    assert bool(((oh.view(torch.int32) & 0x1FFF) == 0).all())        # hi is exactly representable in TF32
+    assert o.rel_err(op[:, 2:].cpu().numpy(), ref) < TOL
+    assert bool((op[:, :2] == 7.0).all())
+    # planar only, no bias, no activation
+    ref2 = po.conv3x3(x, w, None, 1)
+    _, _, op2 = _run(lib, _lib, x, w, None, 1.0, False, True)
+    assert o.rel_err(op2[:, 2:].cpu().numpy(), ref2) < TOL
+
+
+def test_conv3x3_tc_rejects_bad_arguments():
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    t = torch.zeros(1, 8, 8, 32, device="cuda")
+    w = torch.zeros(int(lib.b2f_conv3x3_tc_packed_floats(32, 32)), device="cuda")
+    o = torch.zeros(1, 8, 8, 32, device="cuda")
+    assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), None, None, 0, 1, 32, 8, 8, 32, 0.2, _st()) != 0
+    assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, None, None, None, 0, 1, 32, 8, 8, 32, 0.2, _st()) != 0
+    assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), _p(o), None, 0, 1, 32, 8, 8, 2, 0.2, _st()) != 0
+    assert b"Cout" in lib.b2f_last_error()
