@@ -41,7 +41,7 @@ class Back2Future:
     # ---- back2future.init ---------------------------------------------------------------------------------
     @classmethod
     def init(cls, opt="Ours-Soft-ft-KITTI", model_dir="models", device="cuda:0", seed=2, occ_index="occlusion",
-             image_warps=False):
+             image_warps=False, tensor_cores=True):
         """back2future.lua:97-129.  The checkpoint is read with `t7.load` when the file is there; the published weights
         are not available offline, so otherwise the architecture is built with nn.SpatialConvolution:reset()'s random
         initialisation (stated in every benchmark line as `data: synthetic`).  `image_warps=False`: computeFlow never
@@ -54,7 +54,8 @@ class Back2Future:
         if os.path.exists(path):
             params, pf = t7.import_model(t7.load(path))
             past_flow = pf
-        net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), params, device=device, seed=seed, image_warps=image_warps)
+        net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), params, device=device, seed=seed, image_warps=image_warps,
+                         tensor_cores=tensor_cores)
         return cls(net, occ_index)
 
     # ---- computeFlow ----------------------------------------------------------------------------------------

@@ -89,11 +89,15 @@ def _vp(t):
 
 
 class _Conv:
-    __slots__ = ("w", "b", "cin", "cout", "stride", "gw", "gb", "wt", "w_off", "b_off")
+    __slots__ = ("w", "b", "cin", "cout", "stride", "gw", "gb", "wt", "w_off", "b_off", "tc_h", "tc_l", "tc_cin")
 
 
 def _round64(n):
     return (n + 63) // 64 * 64
+
+
+def _round32(n):
+    return (n + 31) // 32 * 32
 
 
 class PWCNet:
@@ -101,13 +105,17 @@ class PWCNet:
     (Cout,) bias) with the names of `conv_shapes`; None = nn.SpatialConvolution:reset()'s uniform(-1/sqrt(9 nIn), ..)
     drawn from numpy's default_rng(seed)."""
 
-    def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True):
+    def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True, tensor_cores=False):
+        """tensor_cores=True: the decoders' five wide convolutions run on tcgen05 (b2f_conv3x3_tc_forward, three-pass
+        TF32 split, fp32-level accuracy) over channel-minor (hi, lo) activations; inference only (the backward plan
+        reads the planar activations of the FFMA path)."""
         if not torch.cuda.is_available():
             raise RuntimeError("PWCNet: no CUDA device; the B200 path has no CPU fallback")
         self.opt = opt or Opt()
         self.device = torch.device(device)
         self.lib = _lib.load()
         self.image_warps = bool(image_warps)
+        self.tensor_cores = bool(tensor_cores)
         o = self.opt
         self.past_flow = bool(o.past_flow)                                             # model.past_flow, pwc.lua:494
         self.flow_scale = [o.flownet_factor / 2.0 ** (l - o.l_st) for l in range(o.levels, o.l_st - 1, -1)]   # :451-455
@@ -177,6 +185,22 @@ class PWCNet:
                 cv.b = self.flat_params[off + nw:off + nw + cout]
                 cv.b.copy_(torch.from_numpy(b), non_blocking=False)        # cudaMemcpy H2D
                 cv.gw = cv.gb = cv.wt = None
+                cv.tc_h = cv.tc_l = None
+                if self.tensor_cores and kind in ("occ", "flow", "bflow") and cout in (32, 64, 96, 128):
+                    # [9][Cout][Cin_p] hi / lo for the tensor-core path.  The coarsest level's flow decoder reads the
+                    # first 162 channels of the occlusion decoder's wider joined input: zero weights for the rest.
+                    wtc = w
+                    if idx == "0" and l == o.levels and kind != "occ":
+                        wtc = np.zeros((cout, 2 * o.pwc_ws ** 2 + FEAT[l - 1], 3, 3), np.float32)
+                        wtc[:, :cin] = w
+                    cv.tc_cin = wtc.shape[1]
+                    n_tc = int(self.lib.b2f_conv3x3_tc_packed_floats(cv.tc_cin, cout))
+                    cv.tc_h = torch.empty(n_tc, device=self.device, dtype=torch.float32)
+                    cv.tc_l = torch.empty(n_tc, device=self.device, dtype=torch.float32)
+                    wsrc = torch.from_numpy(np.ascontiguousarray(wtc)).to(self.device)
+                    _lib.check(self.lib.b2f_conv3x3_tc_pack_weights(_vp(wsrc), _vp(cv.tc_h), _vp(cv.tc_l), cout,
+                                                                     cv.tc_cin, st))
+                    torch.cuda.current_stream(self.device).synchronize()
                 off += nw + nb
                 self._convs[name] = cv
             torch.cuda.current_stream(self.device).synchronize()
@@ -288,6 +312,8 @@ class PWCNet:
             cj = Jl.shape[1]
 
             def decoder(kind, lane, x0, cin0):
+                if self.tensor_cores:
+                    return decoder_tc(kind, lane)
                 t, tb, cin = x0, jbs, cin0
                 chain = []
                 for i, cout in enumerate(DEC):
@@ -297,6 +323,36 @@ class PWCNet:
                     t, tb, cin = P(out), 0, cout
                 plan.dec[(kind, l)] = (chain, cin0)
                 return out
+
+            def decoder_tc(kind, lane):
+                """Five tensor-core layers over channel-minor (hi, lo) pairs; the fifth writes planar fp32 for the
+                2-channel head (FFMA kernel: N = 2 is no tensor-core shape)."""
+                xh, xl, cin = Jsplit[0], Jsplit[1], cj
+                for i, cout in enumerate(DEC[:5]):
+                    cv = self._convs["%s.l%d.%d" % (kind, l, i)]
+                    assert cv.tc_cin == cin, (kind, l, i, cv.tc_cin, cin)
+                    last = i == 4
+                    oh = None if last else E(B, h, w, _round32(cout))
+                    ol = None if last else E(B, h, w, _round32(cout))
+                    planar = E(B, cout, h, w) if last else None
+                    plan.keep += [t_ for t_ in (oh, ol, planar) if t_ is not None]
+                    ops.append((lane, lib.b2f_conv3x3_tc_forward,
+                                (P(xh), P(xl), P(cv.tc_h), P(cv.tc_l), P(cv.b), P(oh) if oh is not None else None,
+                                 P(ol) if ol is not None else None, P(planar) if last else None, 0, B, cin, h, w, cout,
+                                 C.c_float(0.2))))
+                    xh, xl, cin = oh, ol, cout
+                out = E(B, 2, h, w)
+                plan.keep.append(out)
+                conv("%s.l%d.5" % (kind, l), P(planar), 0, B, DEC[4], h, w, P(out), 0, slope=1.0, lane=lane)
+                return out
+
+            Jsplit = None
+            if self.tensor_cores:
+                cjp = _round32(cj)
+                Jsplit = (E(B, h, w, cjp), E(B, h, w, cjp))
+                plan.keep += list(Jsplit)
+                ops.append((0, lib.b2f_nhwc_split_from_bdhw, (P(Jl), jbs, P(Jsplit[0]), P(Jsplit[1]), B, cj, h, w)))
+                ops.append(("fork", 2))
 
             # occlusion decoder -> softmax -> nearest x 2^(l_st-1) (pwc.lua:288-317)
             occ_logit = decoder("occ", 2, P(Jl), cj)
@@ -572,8 +628,9 @@ class PWCNet:
         `flat_grads` (zeroed first, like train.lua:251's zeroGradParameters).  gradOutputs: tensors shaped like the
         output table (device)."""
         p = self.plan(x.size(0), x.size(2), x.size(3))
-        if not self.image_warps:
-            raise RuntimeError("backward needs the full output table: build the model with image_warps=True")
+        if not self.image_warps or self.tensor_cores:
+            raise RuntimeError("backward needs the full output table and the planar activations: build the model with "
+                               "image_warps=True, tensor_cores=False")
         with torch.cuda.device(self.device):
             if p.bops is None:
                 self._build_backward(p)

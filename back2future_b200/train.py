@@ -80,8 +80,9 @@ class Trainer:
     LOSSES = ("sflow", "cvel", "pme", "socc", "gocc")
 
     def __init__(self, net: pwc.PWCNet, opt: TrainOpt | None = None, comm=None):
-        if not net.image_warps:
-            raise ValueError("training needs the warped frames: build the model with image_warps=True")
+        if not net.image_warps or net.tensor_cores:
+            raise ValueError("training needs the warped frames and the planar activations: build the model with "
+                             "image_warps=True, tensor_cores=False")
         self.net, self.opt, self.comm = net, opt or TrainOpt(), comm
         self.lib = net.lib
         self._steps = {}

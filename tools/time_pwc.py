@@ -33,9 +33,10 @@ def main():
     ap.add_argument("--convs", action="store_true")
     ap.add_argument("--past-flow", action="store_true")
     ap.add_argument("--no-image-warps", action="store_true")
+    ap.add_argument("--tc", action="store_true", help="decoders on the tensor cores")
     a = ap.parse_args()
     lib = _lib.load()
-    net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), image_warps=not a.no_image_warps)
+    net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), image_warps=not a.no_image_warps, tensor_cores=a.tc)
     x = torch.randn(a.B, 9, a.H, a.W, device="cuda")
     p = net.plan(a.B, a.H, a.W)
     p.x.copy_(x)
@@ -58,6 +59,19 @@ def main():
     res["triplets_per_s_graph"] = a.B / res["graph_ms"] * 1e3
     res["conv_tflops_if_all_time_were_conv"] = 2 * macs / res["graph_ms"] / 1e9
     print(json.dumps(res))
+    if a.convs and a.tc:
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        tot = 0.0
+        for op in p.ops:
+            if op[0] == "fork" or op[1] is not lib.b2f_conv3x3_tc_forward:
+                continue
+            args = op[2]
+            B, Cin, H, W, Cout = args[9], args[10], args[11], args[12], args[13]
+            m = B * Cin * 9 * Cout * H * W
+            ms = time_it(lambda: lib.b2f_conv3x3_tc_forward(*args, st), iters=10, warm=2)
+            tot += ms
+            print("tc conv B=%d Cin=%3d %3dx%-4d Cout=%3d  %8.3f ms  %6.1f TFLOP/s (fp32-equivalent)" % (B, Cin, H, W, Cout, ms, 2 * m / ms / 1e9))
+        print("sum of tensor-core convs %.3f ms" % tot)
     if a.convs:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         tot = 0.0
