@@ -36,7 +36,17 @@ constexpr int TH = 7, TW = 16, PW = TW + 2;        // output tile; PW = input pi
 constexpr int A_ROWS = (TH + 2) * PW;               // 162 rows of 128 bytes
 constexpr int A_BYTES = A_ROWS * 128;               // one of (hi, lo)
 constexpr int A_SLOT = (A_BYTES + 4 * 128 + 1023) / 1024 * 1024;   // + the 4 rows the last taps read past the box
-constexpr int NB = 4;                               // weight stages
+#ifndef B2F_TC_NB
+#define B2F_TC_NB 2
+#endif
+#ifndef B2F_TC_AS
+#define B2F_TC_AS 1
+#endif
+constexpr int NB = B2F_TC_NB;                       // weight stages
+constexpr int AS = B2F_TC_AS;                       // input-patch stages
+// (AS, NB) = (1, 2): 107 KB of shared memory at N = 128 -> TWO CTAs per SM, so that one tile's prologue / epilogue
+// (TMEM allocation, first loads, accumulator read-out, stores: 29 % of a tile's residency with one CTA per SM,
+// tools/tc_trace.py) runs under the other tile's MMAs; (2, 4) is the one-CTA-per-SM deep-pipeline form.
 constexpr int THREADS = 128;
 
 template <int N>
@@ -44,9 +54,9 @@ struct Cfg {
   static constexpr int B_BYTES = N * 128;           // one of (hi, lo), one (chunk, tap)
   static constexpr int B_SLOT = 2 * B_BYTES;
   static constexpr int A_STAGE = 2 * A_SLOT;
-  static constexpr int SMEM_MAIN = 2 * A_STAGE + NB * B_SLOT;
+  static constexpr int SMEM_MAIN = AS * A_STAGE + NB * B_SLOT;
   static constexpr int NG = (N + 31) / 32;          // 32-channel output groups
-  static constexpr int STAGING = NG * 2 * (TH * TW * 128);
+  static constexpr int STAGING = 2 * 2 * (TH * TW * 128);   // two (hi, lo) group buffers, reused round-robin
   static constexpr int SMEM_BYTES = (SMEM_MAIN > STAGING ? SMEM_MAIN : STAGING) + 256 + 1024;
   static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -78,7 +88,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Timeline instrumentation (b2f_debug_tc_trace): 16 clock64 stamps per CTA, only when a buffer is registered.
+thread_local unsigned long long* g_tc_trace = nullptr;
+#define TC_STAMP(k)                                                                                              \
+  do {                                                                                                           \
+    if (a.trace) a.trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 16 + (k)] = clock64();                  \
+  } while (0)
+
 struct Args {
+  unsigned long long* trace;
   const float* bias;      // [Cout] or NULL
   float* out_planar;      // optional (B, Cout, H, W) fp32, batch stride pbs
   int64_t pbs;
@@ -89,7 +107,7 @@ struct Args {
 };
 
 template <int N>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, (AS == 1 ? 2 : 1))
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                   const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol, const Args a) {
@@ -97,10 +115,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_buf = smem;                                  // [2 stages][hi, lo][A_SLOT]
-  uint8_t* b_buf = smem + 2 * cfg::A_STAGE;               // [NB][hi, lo][B_BYTES]
+  uint8_t* b_buf = smem + AS * cfg::A_STAGE;              // [NB][hi, lo][B_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (cfg::SMEM_MAIN > cfg::STAGING ? cfg::SMEM_MAIN : cfg::STAGING));
-  uint64_t* a_full = bars;                 // [2]
-  uint64_t* a_empty = bars + 2;            // [2]
+  uint64_t* a_full = bars;                 // [AS] (two slots reserved)
+  uint64_t* a_empty = bars + 2;            // [AS]
   uint64_t* b_full = bars + 4;             // [NB]
   uint64_t* b_empty = bars + 4 + NB;       // [NB]
   uint64_t* acc_full = bars + 4 + 2 * NB;
@@ -111,6 +129,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   const int x0 = tx * TW, y0 = ty * TH;
 
   if (threadIdx.x == 0) {
+    TC_STAMP(0);
+    if (a.trace) {
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      a.trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 16 + 9] = sm;
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(acc_full, 1);
@@ -124,23 +148,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0 && lane == 0) {
-    // ---- TMA producer ----
-    int bs = 0;
+    // ---- TMA producer, weights: one (chunk, tap) stage = hi + lo rows of all N output channels ----
+    const int nstage = a.nchunk * 9;
+    for (int bs = 0; bs < nstage; ++bs) {
+      const int s = bs % NB, c = bs / 9, t = bs % 9;
+      if (bs >= NB) mbar_wait(&b_empty[s], ((bs / NB) - 1) & 1);
+      mbar_arrive_expect_tx(&b_full[s], 2 * cfg::B_BYTES);
+      tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, 0, t, 0, &b_full[s]);
+      tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, 0, t, 0, &b_full[s]);
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ---- TMA producer, input patches: its own thread, so that the patch of chunk c + 1 is requested the moment
+    // chunk c - 1 retires (a whole chunk of MMAs ahead) instead of behind the weight ring's back-pressure ----
     for (int c = 0; c < a.nchunk; ++c) {
-      const int as = c & 1;
-      if (c >= 2) mbar_wait(&a_empty[as], ((c >> 1) - 1) & 1);
+      const int as = c % AS;
+      if (c >= AS) mbar_wait(&a_empty[as], ((c / AS) - 1) & 1);
       mbar_arrive_expect_tx(&a_full[as], 2 * A_BYTES);
       tma_load_4d(a_buf + as * cfg::A_STAGE, &tm_xh, c * 32, x0 - 1, y0 - 1, b, &a_full[as]);
       tma_load_4d(a_buf + as * cfg::A_STAGE + A_SLOT, &tm_xl, c * 32, x0 - 1, y0 - 1, b, &a_full[as]);
-      for (int t = 0; t < 9; ++t, ++bs) {
-        const int s = bs % NB;
-        if (bs >= NB) mbar_wait(&b_empty[s], ((bs / NB) - 1) & 1);
-        mbar_arrive_expect_tx(&b_full[s], 2 * cfg::B_BYTES);
-        tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, 0, t, 0, &b_full[s]);
-        tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, 0, t, 0, &b_full[s]);
-      }
     }
   } else if (warp == 1 && lane == 0) {
     // ---- MMA issuer ----
@@ -150,12 +178,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     int bs = 0;
     uint32_t acc = 0;
     for (int c = 0; c < a.nchunk; ++c) {
-      const int as = c & 1;
-      mbar_wait(&a_full[as], (c >> 1) & 1);
+      const int as = c % AS;
+      mbar_wait(&a_full[as], (c / AS) & 1);
+      if (c == 0) TC_STAMP(2);
       const uint32_t ah = smem_u32(a_buf + as * cfg::A_STAGE), al = ah + A_SLOT;
       for (int t = 0; t < 9; ++t, ++bs) {
         const int s = bs % NB;
         mbar_wait(&b_full[s], (bs / NB) & 1);
+        if (bs == 0) TC_STAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t shift = (uint32_t)((t / 3) * PW + (t % 3)) * 128u;
         const uint32_t bh = smem_u32(b_buf + s * cfg::B_SLOT), bl = bh + cfg::B_BYTES;
@@ -173,12 +203,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       umma_commit(&a_empty[as]);
     }
     umma_commit(acc_full);
+    TC_STAMP(4);
   }
   __syncwarp();
 
   // ---- epilogue: all four warps; warp w owns TMEM lanes 32 w .. 32 w + 31 = tile rows m ----
   mbar_wait(acc_full, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (threadIdx.x == 0) TC_STAMP(5);
   const int m = 32 * warp + lane;
   const int ry = m / PW, rx = m % PW;
   const bool valid = ry < TH && rx < TW;
@@ -204,39 +236,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       for (int j = 0; j < 32; ++j)
         if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] = f[j];
     }
-    if (a.store_split && valid) {
-      const uint32_t rh = stage0 + (uint32_t)((2 * g) * (TH * TW * 128) + prow * 128);
-      const uint32_t rl = rh + TH * TW * 128;
-      const uint32_t sw = (uint32_t)(prow & 7);
+    if (a.store_split) {
+      // two (hi, lo) staging buffers: group g reuses the buffer of group g - 2 once its stores have read it
+      if (g >= 2) {
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+      }
+      const uint32_t rh0 = stage0 + (uint32_t)((g & 1) * 2 * (TH * TW * 128));
+      if (valid) {
+        const uint32_t rh = rh0 + (uint32_t)(prow * 128);
+        const uint32_t rl = rh + TH * TW * 128;
+        const uint32_t sw = (uint32_t)(prow & 7);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(f[4 * q]) & 0xFFFFE000u);
-        hi.y = __uint_as_float(__float_as_uint(f[4 * q + 1]) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(f[4 * q + 2]) & 0xFFFFE000u);
-        hi.w = __uint_as_float(__float_as_uint(f[4 * q + 3]) & 0xFFFFE000u);
-        lo.x = f[4 * q] - hi.x; lo.y = f[4 * q + 1] - hi.y; lo.z = f[4 * q + 2] - hi.z; lo.w = f[4 * q + 3] - hi.w;
-        sts128(rh + 16u * ((uint32_t)q ^ sw), hi);
-        sts128(rl + 16u * ((uint32_t)q ^ sw), lo);
+        for (int q = 0; q < 8; ++q) {
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(f[4 * q]) & 0xFFFFE000u);
+          hi.y = __uint_as_float(__float_as_uint(f[4 * q + 1]) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(f[4 * q + 2]) & 0xFFFFE000u);
+          hi.w = __uint_as_float(__float_as_uint(f[4 * q + 3]) & 0xFFFFE000u);
+          lo.x = f[4 * q] - hi.x; lo.y = f[4 * q + 1] - hi.y; lo.z = f[4 * q + 2] - hi.z; lo.w = f[4 * q + 3] - hi.w;
+          sts128(rh + 16u * ((uint32_t)q ^ sw), hi);
+          sts128(rl + 16u * ((uint32_t)q ^ sw), lo);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tma_store_4d_addr(rh0, &tm_oh, 32 * g, x0, y0, b);
+        tma_store_4d_addr(rh0 + TH * TW * 128, &tm_ol, 32 * g, x0, y0, b);
+        tma_store_commit();
       }
     }
   }
-  if (a.store_split) {
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int g = 0; g < cfg::NG; ++g) {
-        tma_store_4d_addr(stage0 + (uint32_t)((2 * g) * (TH * TW * 128)), &tm_oh, 32 * g, x0, y0, b);
-        tma_store_4d_addr(stage0 + (uint32_t)((2 * g + 1) * (TH * TW * 128)), &tm_ol, 32 * g, x0, y0, b);
-      }
-      tma_store_commit();
-      tma_store_wait_read();
-    }
+  if (threadIdx.x == 0) TC_STAMP(6);
+  if (a.store_split && threadIdx.x == 0) {
+    tma_store_wait_read();
+    TC_STAMP(7);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cfg::TMEM_COLS) : "memory");
+  if (threadIdx.x == 0) TC_STAMP(8);
 }
 
 // planar (B, C, H, W) [batch stride xbs] -> channel-minor (B, H, W, Cp) hi / lo
@@ -329,6 +370,11 @@ int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl
 
 using namespace b2f;
 
+extern "C" int b2f_debug_tc_trace(unsigned long long* device_buffer) {
+  tc::g_tc_trace = device_buffer;
+  return B2F_OK;
+}
+
 extern "C" int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout) {
   if (Cin <= 0 || Cout <= 0) return 0;
   return (int64_t)9 * Cout * ((Cin + 31) / 32 * 32);
@@ -374,6 +420,7 @@ extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, cons
   if (B == 0) return B2F_OK;
   const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
   tc::Args a{};
+  a.trace = tc::g_tc_trace;
   a.bias = bias;
   a.out_planar = out_planar;
   a.pbs = out_planar_batch_stride ? out_planar_batch_stride : (int64_t)Cout * H * W;

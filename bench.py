@@ -464,14 +464,23 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
             ms = t.item()
         return ms
 
-    net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True)
+    out["decoders"] = ("tcgen05 implicit GEMM, three-pass TF32 split over channel-minor (hi, lo) activations "
+                       "(b2f_conv3x3_tc_forward); feature pyramid and 2-channel heads on the FFMA2 kernel")
+    net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True, tensor_cores=True)
     p = net.plan(B, H_FULL, W_FULL)
     p.x.copy_(torch.randn(p.x.shape, device=dev))
     ms = timed(lambda: net.run(p), steps)
     out["device"] = {"triplets_per_s": round(world * B / ms * 1e3, 1), "ms_per_step": round(ms, 3),
                      "launches_per_step": p.n_launches, "outputs": "full table incl. the ten warped frames"}
+    del p, net
+    # the same network with every convolution on the fp32 FMA pipe (the training path's forward)
+    net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True, tensor_cores=False)
+    p = net.plan(B, H_FULL, W_FULL)
+    p.x.copy_(torch.randn(p.x.shape, device=dev))
+    ms_f = timed(lambda: net.run(p), steps)
+    out["device_ffma_only"] = {"triplets_per_s": round(world * B / ms_f * 1e3, 1), "ms_per_step": round(ms_f, 3)}
     # end to end: flow + occlusion only (computeFlow never reads the warped frames)
-    net2 = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=False)
+    net2 = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=False, tensor_cores=True)
     p2 = net2.plan(B, H_FULL, W_FULL)
     hin = [torch.randn(B, 9, H_FULL, W_FULL).pin_memory() for _ in range(2)]
     din = [torch.empty(B, 9, H_FULL, W_FULL, device=dev) for _ in range(2)]
@@ -514,6 +523,47 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
                   "h2d_bytes_per_step": B * 9 * H_FULL * W_FULL * 4, "d2h_bytes_per_step": 2 * B * 2 * H_FULL * W_FULL * 4,
                   "api": "back2future_b200.pwc.PWCNet.run on host frames (the device half of computeFlow)"}
     del net, p, hin, din, dout, hout
+    if rank == 0:
+        # the dominant kernel of the whole-network forward against the tensor-core roofline: one level-3 decoder layer
+        # (128 -> 128 channels at 112 x 256 x B), CUDA events around 20 launches on resident operands
+        import ctypes as C
+        from back2future_b200 import _lib
+        lib = _lib.load()
+        Hc, Wc, Cc = H_FULL // 4, W_FULL // 4, 128
+        xh = torch.randn(B, Hc, Wc, Cc, device=dev)
+        xl = torch.randn(B, Hc, Wc, Cc, device=dev) * 1e-4
+        nw = int(lib.b2f_conv3x3_tc_packed_floats(Cc, Cc))
+        wh, wl = torch.randn(nw, device=dev) * 0.03, torch.randn(nw, device=dev) * 1e-5
+        oh, ol = torch.empty_like(xh), torch.empty_like(xh)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        stc = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        call = lambda: lib.b2f_conv3x3_tc_forward(vp(xh), vp(xl), vp(wh), vp(wl), None, vp(oh), vp(ol), None, 0, B, Cc, Hc, Wc,
+                                                  Cc, 0.2, stc)
+        for _ in range(3):
+            _lib.check(call())
+        torch.cuda.synchronize()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(20):
+            call()
+        b_.record()
+        torch.cuda.synchronize()
+        cms = a_.elapsed_time(b_) / 20
+        flop = 2.0 * B * Hc * Wc * Cc * Cc * 9
+        peak_bf16 = None
+        try:
+            peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        peak_tf32 = (peak_bf16 or 2250.0) / 2
+        out["roofline"] = {"bound": "tensor", "kernel": "conv3x3_tc_kernel<128> (decoder layer 128 -> 128, level 3)",
+                           "achieved": round(3 * flop / cms / 1e9, 1), "peak": round(peak_tf32, 1), "unit": "TFLOP/s",
+                           "frac": round(3 * flop / cms / 1e9 / peak_tf32, 4), "traffic": None,
+                           "avg_launch_ms": round(cms, 4), "fp32_equivalent_tflops": round(flop / cms / 1e9, 1),
+                           "flops_per_launch": 3 * flop,
+                           "note": "achieved counts the three TF32 passes of the split (the MMAs executed); peak = half the "
+                                   "measured dense bf16 rate of MEASURED_PEAKS.json (%s)" % ("measured" if peak_bf16 else "nominal fallback")}
+        del xh, xl, wh, wl, oh, ol
     if rank == 0 and world == 1:
         for key, (h, w) in (("b1_1024x448", (H_FULL, W_FULL)), ("b1_config0_1216x320", (320, 1216)),
                             ("b1_config4_1024x384", (384, 1024))):

@@ -245,6 +245,9 @@ B2F_API int b2f_softmax_channels_forward(const float* x, float* out, int B, int 
  * Outputs: out_hi / out_lo (both or neither; (B, H, W, Cout rounded up to 32)) for the next tensor-core layer and / or
  * out_planar (B, Cout, H, W) fp32 with its batch stride (0 = dense) for every other consumer.  Cout in {32, 64, 96, 128}. */
 B2F_API int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout);
+/* Measurement hook (thread-local): while a device buffer of 16 x (number of CTAs) uint64 is registered, every CTA of
+ * b2f_conv3x3_tc_forward stores clock64 stamps of its phases there (tools/tc_trace.py); NULL switches it off.        */
+B2F_API int b2f_debug_tc_trace(unsigned long long* device_buffer);
 B2F_API int b2f_conv3x3_tc_pack_weights(const float* w_torch, float* w_hi, float* w_lo, int Cout, int Cin,
                                         b2f_stream_t stream);
 B2F_API int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, float* hi, float* lo, int B, int C, int H,

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--past-flow", action="store_true")
     ap.add_argument("--no-image-warps", action="store_true")
     ap.add_argument("--tc", action="store_true", help="decoders on the tensor cores")
+    ap.add_argument("--by-op", action="store_true", help="time every call of the plan on its own, grouped by entry point")
     a = ap.parse_args()
     lib = _lib.load()
     net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), image_warps=not a.no_image_warps, tensor_cores=a.tc)
@@ -59,6 +60,27 @@ def main():
     res["triplets_per_s_graph"] = a.B / res["graph_ms"] * 1e3
     res["conv_tflops_if_all_time_were_conv"] = 2 * macs / res["graph_ms"] / 1e9
     print(json.dumps(res))
+    if a.by_op:
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        names = {getattr(lib, n)._name if hasattr(getattr(lib, n), "_name") else n: n for n in _lib.SIGNATURES}
+        fn_name = {}
+        for n in _lib.SIGNATURES:
+            fn_name[id(getattr(lib, n))] = n
+        agg = {}
+        for op in p.ops:
+            if op[0] == "fork":
+                continue
+            fn, args = op[1], op[2]
+            ms = time_it(lambda: fn(*args, st), iters=5, warm=1)
+            key = fn_name.get(id(fn), str(fn))
+            if key == "b2f_conv3x3_forward":
+                key += " (Cout=%d, stride %d)" % (args[12], args[13]) if args[12] <= 2 or args[13] == 2 else " (trunk)" if args[9] in (16, 32, 64, 96, 128, 192) and args[12] == args[9] else ""
+            t, n = agg.get(key, (0.0, 0))
+            agg[key] = (t + ms, n + 1)
+        tot = sum(t for t, _ in agg.values())
+        for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print("%-52s %3d calls %8.3f ms %5.1f%%" % (k, n, t, 100 * t / tot))
+        print("sum of calls %.3f ms (serialised; the plan overlaps three lanes)" % tot)
     if a.convs and a.tc:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         tot = 0.0
