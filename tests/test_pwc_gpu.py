@@ -328,7 +328,9 @@ def test_init_reads_a_t7_checkpoint(tmp_path):
     params = po.init_params(po.Opt(), seed=21, scale=2.0)
     t7.save(str(tmp_path / "RoamingImages_H.t7"), t7.TorchObject("nn.DataParallelTable",
                                                                  {"modules": [t7.export_model(params, False)]}))
-    m = b2f.Back2Future.init("Ours-Hard", model_dir=str(tmp_path), image_warps=True)
+    # the FFMA path: white-noise frames with doubled weights put the tensor-core path's flow at 1.1e-4 (its
+    # accumulation is ~2e-5 relative on image-like input, see the tensor-core test above)
+    m = b2f.Back2Future.init("Ours-Hard", model_dir=str(tmp_path), image_warps=True, tensor_cores=False)
     x = np.random.default_rng(1).uniform(-2, 2, (1, 9, 64, 64)).astype(np.float32)
     out = m.model.forward(_dev(x))
     ref = po.pwc_forward(params, x, po.Opt())
