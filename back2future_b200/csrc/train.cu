@@ -256,6 +256,26 @@ __global__ void upsample_nearest_backward_kernel(const float* __restrict__ go, f
   }
 }
 
+// out (planes, 2H, 2W): x at the even coordinates, zeros elsewhere.  The input gradient of a stride-2 convolution is the
+// stride-1 input gradient of this dilated output gradient (gin[y, x] = sum_k z[y + 1 - ky, x + 1 - kx] w[k] with
+// z[2 yo, 2 xo] = gout[yo, xo]), which runs on the TMA / FFMA2 kernel: 4x the multiply-adds of the direct form, at ~20x
+// its rate (the direct kernel took 10.3 of the training step's 40 ms for 3 % of its arithmetic).
+__global__ void zero_insert2x_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t planes, int H, int W) {
+  const int Wo = 2 * W;
+  const int64_t total = planes * 2 * H * (Wo / 4);      // one float4 (two source pixels) per thread
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % (Wo / 4)), Y = (int)((i / (Wo / 4)) % (2 * H));
+    const int64_t pl = i / ((int64_t)(Wo / 4) * 2 * H);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((Y & 1) == 0) {
+      const float2 s = *reinterpret_cast<const float2*>(x + (pl * H + (Y >> 1)) * W + 2 * q);
+      v.x = s.x;
+      v.z = s.y;
+    }
+    *reinterpret_cast<float4*>(out + (pl * 2 * H + Y) * Wo + 4 * q) = v;
+  }
+}
+
 // SpatialSoftMax:updateGradInput: gi = s * (go - sum_c go_c s_c)
 __global__ void softmax_channels_backward_kernel(const float* __restrict__ s, const float* __restrict__ go,
                                                  float* __restrict__ gi, int B, int C, int64_t hw) {
@@ -367,6 +387,16 @@ extern "C" int b2f_upsample_bilinear2x_backward(const float* grad_out, float* gr
   upsample_bilinear2_backward_kernel<<<ew_grid((int64_t)B * C * H * W, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       grad_out, grad_in, B, C, H, W, mul, accumulate);
   B2F_CHECK_LAUNCH("upsample_bilinear2_backward_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_zero_insert2x(const float* x, float* out, int64_t planes, int H, int W, b2f_stream_t stream) {
+  if (!x || !out || planes < 0 || H <= 0 || W <= 0) return fail(B2F_EINVAL, "zero_insert2x: bad argument");
+  if ((W & 1) || (reinterpret_cast<uintptr_t>(x) & 7u) || !aligned16(out))
+    return fail(B2F_EUNSUPPORTED, "zero_insert2x: odd width or misaligned buffers");
+  if (planes == 0) return B2F_OK;
+  zero_insert2x_kernel<<<ew_grid(planes * 2 * H * (W / 2), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, planes, H, W);
+  B2F_CHECK_LAUNCH("zero_insert2x_kernel");
   return B2F_OK;
 }
 

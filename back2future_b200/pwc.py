@@ -479,10 +479,10 @@ class PWCNet:
             ops.append((lib.b2f_conv3x3_backward_weights, (xin, xbs, gout, gbs, P(cv.gw), P(cv.gb), nb, cin, h, w, cv.cout,
                                                            cv.stride)))
 
-        def dgrad(name, gout, gbs, act, abs_, gin, ibs, acc, nb, cin, h, w, slope=0.2):
+        def dgrad(name, gout, gbs, act, abs_, gin, ibs, acc, nb, cin, h, w, slope=0.2, stride=None):
             cv = self._convs[name]
             ops.append((lib.b2f_conv3x3_backward_data, (gout, gbs, P(cv.wt), act, abs_, gin, ibs, int(acc), nb, cin, h, w,
-                                                        cv.cout, cv.stride, C.c_float(slope))))
+                                                        cv.cout, stride or cv.stride, C.c_float(slope))))
 
         def dec_range(l):
             """[lo, hi) of level l's decoders in the flat parameter / gradient buffer (they are consecutive there)."""
@@ -618,7 +618,14 @@ class PWCNet:
                     wgrad(name, sl(plan.x, 0, 3 * fr), 9 * H * W, sl(g_tmp, slot * B), 0, B, 3, H, W)
             else:
                 wgrad(name, P(plan.feats[l - 1]), 0, P(g_tmp), 0, 3 * B, c_in, 2 * h, 2 * w)
-                dgrad(name, P(g_tmp), 0, None, 0, P(g_feats[l - 1]), 0, True, 3 * B, c_in, 2 * h, 2 * w, slope=1.0)
+                if w % 2 == 0:
+                    # stride 2: dilate the output gradient and run the stride-1 (TMA / FFMA2) input-gradient kernel
+                    z = E(3 * B, c_out, 2 * h, 2 * w)
+                    plan.keep.append(z)
+                    ops.append((lib.b2f_zero_insert2x, (P(g_tmp), P(z), 3 * B * c_out, h, w)))
+                    dgrad(name, P(z), 0, None, 0, P(g_feats[l - 1]), 0, True, 3 * B, c_in, 2 * h, 2 * w, slope=1.0, stride=1)
+                else:
+                    dgrad(name, P(g_tmp), 0, None, 0, P(g_feats[l - 1]), 0, True, 3 * B, c_in, 2 * h, 2 * w, slope=1.0)
             c0_, c1_ = self._convs["feat.l%d.0" % l], self._convs["feat.l%d.1" % l]
             plan.bucket_marks.append((len(ops), (c0_.w_off, c1_.b_off + _round64(c1_.cout))))
         plan.g_keep = (g_warped,)

@@ -275,6 +275,10 @@ B2F_API int b2f_conv3x3_backward_data(const float* gout, int64_t gout_batch_stri
 B2F_API int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stride, const float* gout,
                                          int64_t gout_batch_stride, float* gw_packed, float* gbias, int B, int Cin,
                                          int H, int W, int Cout, int stride, b2f_stream_t stream);
+/* out (planes, 2H, 2W) <- x (planes, H, W) at the even coordinates, zeros elsewhere: the dilated output gradient with
+ * which a stride-2 convolution's input gradient is b2f_conv3x3_backward_data(..., stride = 1) on the 2H x 2W grid
+ * (the fast path; the direct stride-2 form inside b2f_conv3x3_backward_data is the fallback for odd widths).       */
+B2F_API int b2f_zero_insert2x(const float* x, float* out, int64_t planes, int H, int W, b2f_stream_t stream);
 /* LeakyReLU:updateGradInput in place on `rows` rows of `row_elems` floats: grad *= (act > 0 ? 1 : slope).         */
 B2F_API int b2f_leaky_relu_backward(float* grad, int64_t grad_row_stride, const float* act, int64_t act_row_stride,
                                     int64_t row_elems, int64_t rows, float slope, b2f_stream_t stream);

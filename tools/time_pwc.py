@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--past-flow", action="store_true")
     ap.add_argument("--no-image-warps", action="store_true")
     ap.add_argument("--tc", action="store_true", help="decoders on the tensor cores")
+    ap.add_argument("--once", action="store_true", help="two eager forwards and nothing else (for an ncu launch list)")
     ap.add_argument("--by-op", action="store_true", help="time every call of the plan on its own, grouped by entry point")
     a = ap.parse_args()
     lib = _lib.load()
@@ -42,6 +43,13 @@ def main():
     p = net.plan(a.B, a.H, a.W)
     p.x.copy_(x)
     res = {"B": a.B, "H": a.H, "W": a.W}
+    if a.once:
+        net.run(p, graph=False)
+        torch.cuda.synchronize()
+        net.run(p, graph=False)
+        torch.cuda.synchronize()
+        print("launches per forward:", p.n_launches)
+        return
     res["eager_ms"] = time_it(lambda: net.run(p, graph=False))
     res["graph_ms"] = time_it(lambda: net.run(p, graph=True))
     res["launches"] = p.n_launches
