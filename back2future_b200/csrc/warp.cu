@@ -23,7 +23,7 @@
 //     (and BL/BR) taps are 6 contiguous floats, scattered with 2-3 vector reductions chosen by the
 //     address alignment instead of 6 scalar ones -- the kernel is bound by the SM's RED issue rate.
 //   * any other C: one thread per pixel, scalar.
-#include "common.cuh"
+#include "tma.cuh"
 
 namespace b2f {
 namespace {
@@ -496,6 +496,117 @@ warp_fwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, 
            reinterpret_cast<const float4*>(s_out)[threadIdx.x]);
 }
 
+// ---- C == 3, windowed forward (the large image warps) ---------------------------------------------------------
+// With scattered flow (the benchmark's i.i.d. N(0, 4 px)) every lane of a warp gathers from a different image row:
+// a global gather costs one L1 wavefront per lane and request, and warp_fwd_c3_lean is bound by L1 wavefronts
+// (~4.5 per pixel: 54 us at 8 x 448 x 1024, 33 % of the HBM roofline) with DRAM a third busy.  Here a CTA owns a
+// 32 x 64 output tile and has the TMA stage the source window of the tile +- 12 pixels (57 rows x 96 pixels, two
+// boxes of 144 floats: 65.7 KB) in shared memory while the threads fetch their flow values; the twelve tap values of a
+// pixel are then shared-memory loads (bank conflicts, ~3.5-way on random addresses, instead of 32-way wavefronts).  The
+// window position is STATIC, so the TMA is in flight from the first instruction; a pixel whose taps leave the window
+// (|flow| > 12 px: 0.5 % of an N(0, 4) field) takes the global path of the lean kernel -- the result never depends on
+// the window.  Three CTAs per SM: one tile's fill runs under the others' gathers.  Rows / columns of the window
+// outside the image read as zero or as a neighbouring batch item's rows; neither is ever used (the coordinates are
+// clamped to the image, and a tap at index W or H is masked by rin / bin).  Same arithmetic expressions as
+// warp_fwd_c3_lean: bit-identical output.
+namespace win {
+constexpr int TH = 32, TW = 64, R = 12, THREADS = 256, PPT = TH * TW / THREADS;
+constexpr int WR = TH + 2 * R + 2;          // 58 window rows (57 needed; 58 x 576 B is a multiple of 128 B)
+constexpr int BOXF = 144;                   // floats per box row (48 pixels); two boxes side by side = 96 pixels
+constexpr int WPX = 2 * BOXF / 3;           // 96
+constexpr int BOX_ELEMS = WR * BOXF;
+constexpr int SMEM_BYTES = 2 * BOX_ELEMS * 4 + (THREADS / 32) * 96 * 4 + 64 + 128;
+static_assert((BOX_ELEMS * 4) % 128 == 0, "TMA destination alignment");
+}  // namespace win
+
+__global__ void __launch_bounds__(win::THREADS, 3)
+warp_fwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restrict__ img,
+                const float* __restrict__ grid, float* __restrict__ out, int H, int W, unsigned total) {
+  using namespace win;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const uint32_t box0 = smem_u32(smem);
+  float* s_out = reinterpret_cast<float*>(smem) + 2 * BOX_ELEMS;             // [warp][96]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_out + (THREADS / 32) * 96);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int wx0 = x0 - R, wy0 = y0 - R;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, 2 * BOX_ELEMS * 4);
+    tma_load_2d(smem, &tm_img, wx0 * 3, b * H + wy0, bar);
+    tma_load_2d(smem + BOX_ELEMS * 4, &tm_img, wx0 * 3 + BOXF, b * H + wy0, bar);
+  }
+  // thread -> pixels: warp w walks rows w, w + 8, ...; lanes cover 32 consecutive columns of one half-row
+  Geo g[PPT];
+  bool live[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int idx = k * THREADS + tid;                 // 0 .. 2047
+    const int ry = idx >> 6, rx = idx & 63;
+    const int yo = y0 + ry, xo = x0 + rx;
+    live[k] = yo < H && xo < W;
+    float2 gxy = make_float2(0.f, 0.f);
+    if (live[k]) gxy = __ldg(reinterpret_cast<const float2*>(grid) + ((unsigned)b * H + yo) * W + xo);
+    g[k] = geometry(gxy.x, gxy.y, live[k] ? xo : 0, live[k] ? yo : 0, H, W);
+  }
+  __syncthreads();                                     // the barrier is initialised
+  mbar_wait(bar, 0);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int idx = k * THREADS + tid;
+    const int ry = idx >> 6, rx = idx & 63;
+    const Geo& q = g[k];
+    float top[6], bot[6];
+    const int cx = q.xi - wx0, cy = q.yi - wy0;
+    const bool inwin = cx >= 0 && cx + 1 < WPX && cy >= 0 && cy + 1 < WR;
+    if (live[k]) {
+      if (inwin) {
+        const int c = cx * 3;
+        // the six floats of a tap row may straddle the two boxes (c = 141 .. 143): per-element box select
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int ci = c + i;
+          const uint32_t a = box0 + 4u * (uint32_t)((ci < BOXF ? ci : BOX_ELEMS + ci - BOXF) + cy * BOXF);
+          float v0, v1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a + 4u * BOXF));
+          top[i] = v0;
+          bot[i] = v1;
+        }
+      } else {
+        const unsigned a = (((unsigned)b * H + q.yi) * W + q.xi) * 3u;
+        const unsigned ab = q.bin ? a + (unsigned)W * 3u : a;
+        const Chunks9 rt = load_chunks(img, a, total);
+        const Chunks9 rb = load_chunks(img, ab, total);
+        shift_out(rt, a & 3u, top);
+        shift_out(rb, ab & 3u, bot);
+      }
+    }
+    const float w_tl = q.wx * q.wy, w_tr = (1.f - q.wx) * q.wy;
+    const float w_bl = q.wx * (1.f - q.wy), w_br = (1.f - q.wx) * (1.f - q.wy);
+    const bool both = q.rin && q.bin;
+    float* so = s_out + warp * 96 + lane * 3;
+    __syncwarp();
+    if (live[k]) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        so[c] = w_tl * top[c] + w_tr * (q.rin ? top[3 + c] : 0.f) + w_bl * (q.bin ? bot[c] : 0.f) +
+                w_br * (both ? bot[3 + c] : 0.f);
+    }
+    __syncwarp();
+    // the warp's 32 pixels are 96 contiguous floats of one output row (W % 4 == 0: 16-byte aligned segments)
+    const int yo = y0 + ry, xw = x0 + (rx & 32);
+    if (yo < H && lane < 24) {
+      const int nq = (min(32, W - xw) * 3) >> 2;       // float4 count of the live part of the segment
+      if (lane < nq)
+        __stcs(reinterpret_cast<float4*>(out + (size_t)(((unsigned)b * H + yo) * W + xw) * 3) + lane,
+               reinterpret_cast<const float4*>(s_out + warp * 96)[lane]);
+    }
+  }
+}
+
 template <bool ONLY_GRID>
 __global__ void __launch_bounds__(PIX_THREADS)
 warp_bwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, const float* __restrict__ gout,
@@ -535,6 +646,101 @@ warp_bwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, 
       const float br0 = g.rin ? w_br * v0 : 0.f, br1 = g.rin ? w_br * v1 : 0.f, br2 = g.rin ? w_br * v2 : 0.f;
       const float vb[6] = {w_bl * v0, w_bl * v1, w_bl * v2, br0, br1, br2};
       red_chunks(gimg, ab, total, vb);
+    }
+  }
+}
+
+// ---- C == 3, windowed backward: the four taps of the flow gradient come from the staged window (as in the forward);
+// the image-gradient scatter stays a global reduction (shared-memory fp32 atomics are CAS loops on sm_100a) ----------
+template <bool ONLY_GRID>
+__global__ void __launch_bounds__(win::THREADS, 3)
+warp_bwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restrict__ img, const float* __restrict__ grid,
+                const float* __restrict__ gout, float* __restrict__ gimg, float* __restrict__ ggrid, int H, int W,
+                unsigned total) {
+  using namespace win;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const uint32_t box0 = smem_u32(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem) + 2 * BOX_ELEMS + (THREADS / 32) * 96);
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int wx0 = x0 - R, wy0 = y0 - R;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, 2 * BOX_ELEMS * 4);
+    tma_load_2d(smem, &tm_img, wx0 * 3, b * H + wy0, bar);
+    tma_load_2d(smem + BOX_ELEMS * 4, &tm_img, wx0 * 3 + BOXF, b * H + wy0, bar);
+  }
+  Geo g[PPT];
+  bool live[PPT];
+  float go[PPT][3];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int idx = k * THREADS + tid;
+    const int yo = y0 + (idx >> 6), xo = x0 + (idx & 63);
+    live[k] = yo < H && xo < W;
+    float2 gxy = make_float2(0.f, 0.f);
+    go[k][0] = go[k][1] = go[k][2] = 0.f;
+    if (live[k]) {
+      const unsigned pix = ((unsigned)b * H + yo) * W + xo;
+      gxy = __ldg(reinterpret_cast<const float2*>(grid) + pix);
+      const float* gp = gout + (size_t)pix * 3;
+      go[k][0] = __ldcs(gp); go[k][1] = __ldcs(gp + 1); go[k][2] = __ldcs(gp + 2);
+    }
+    g[k] = geometry(gxy.x, gxy.y, live[k] ? xo : 0, live[k] ? yo : 0, H, W);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    if (!live[k]) continue;
+    const int idx = k * THREADS + tid;
+    const int yo = y0 + (idx >> 6), xo = x0 + (idx & 63);
+    const unsigned pix = ((unsigned)b * H + yo) * W + xo;
+    const Geo& q = g[k];
+    const float v0 = go[k][0], v1 = go[k][1], v2 = go[k][2];
+    float top[6], bot[6];
+    const int cx = q.xi - wx0, cy = q.yi - wy0;
+    const unsigned a = (((unsigned)b * H + q.yi) * W + q.xi) * 3u;
+    const unsigned ab = q.bin ? a + (unsigned)W * 3u : a;
+    if (cx >= 0 && cx + 1 < WPX && cy >= 0 && cy + 1 < WR) {
+      const int c = cx * 3;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int ci = c + i;
+        const uint32_t sa = box0 + 4u * (uint32_t)((ci < BOXF ? ci : BOX_ELEMS + ci - BOXF) + cy * BOXF);
+        float t0, t1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(sa));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(sa + (q.bin ? 4u * BOXF : 0u)));
+        top[i] = t0;
+        bot[i] = t1;
+      }
+    } else {
+      const Chunks9 rt = load_chunks(img, a, total);
+      const Chunks9 rb = load_chunks(img, ab, total);
+      shift_out(rt, a & 3u, top);
+      shift_out(rb, ab & 3u, bot);
+    }
+    const float w_tl = q.wx * q.wy, w_tr = (1.f - q.wx) * q.wy;
+    const float w_bl = q.wx * (1.f - q.wy), w_br = (1.f - q.wx) * (1.f - q.wy);
+    const float d_tl = top[0] * v0 + top[1] * v1 + top[2] * v2;
+    const float d_tr = q.rin ? top[3] * v0 + top[4] * v1 + top[5] * v2 : 0.f;
+    const float d_bl = q.bin ? bot[0] * v0 + bot[1] * v1 + bot[2] * v2 : 0.f;
+    const float d_br = (q.rin && q.bin) ? bot[3] * v0 + bot[4] * v1 + bot[5] * v2 : 0.f;
+    float2 r;
+    r.x = -q.wy * d_tl + q.wy * d_tr - (1.f - q.wy) * d_bl + (1.f - q.wy) * d_br;
+    r.y = -q.wx * d_tl + q.wx * d_bl - (1.f - q.wx) * d_tr + (1.f - q.wx) * d_br;
+    reinterpret_cast<float2*>(ggrid)[pix] = r;
+    if (!ONLY_GRID) {
+      const float tr0 = q.rin ? w_tr * v0 : 0.f, tr1 = q.rin ? w_tr * v1 : 0.f, tr2 = q.rin ? w_tr * v2 : 0.f;
+      const float vt[6] = {w_tl * v0, w_tl * v1, w_tl * v2, tr0, tr1, tr2};
+      red_chunks(gimg, a, total, vt);
+      if (q.bin) {
+        const float br0 = q.rin ? w_br * v0 : 0.f, br1 = q.rin ? w_br * v1 : 0.f, br2 = q.rin ? w_br * v2 : 0.f;
+        const float vb[6] = {w_bl * v0, w_bl * v1, w_bl * v2, br0, br1, br2};
+        red_chunks(gimg, ab, total, vb);
+      }
     }
   }
 }
@@ -750,6 +956,16 @@ bool c3_lean_ok(int B, int H, int W, int Hg, int Wg) {
   return !legacy && (total & 3u) == 0 && total < (1ull << 31) && gpix * 3 < (1ull << 31) && (Wg & 3) == 0;
 }
 
+// the windowed forward: the lean preconditions, output grid = image grid, rows of 16-byte multiples (TMA), at least a
+// few waves of 32 x 64 tiles; B2F_WARP_C3_WIN=0 switches it off (experiments)
+bool c3_win_ok(int B, int H, int W, int Hg, int Wg) {
+  static const bool off = [] { const char* e = getenv("B2F_WARP_C3_WIN"); return e && e[0] == '0'; }();
+  if (off || !c3_lean_ok(B, H, W, Hg, Wg) || H != Hg || W != Wg || (W & 3) != 0) return false;
+  if ((int64_t)B * H > (1ll << 30)) return false;
+  const int64_t tiles = (int64_t)B * ((H + win::TH - 1) / win::TH) * ((W + win::TW - 1) / win::TW);
+  return tiles >= 2 * (int64_t)num_sms() && get_encode_fn() != nullptr;
+}
+
 int check_args(const float* img, const float* grid, int B, int H, int W, int C, int Hg, int Wg) {
   if (!img || !grid) return fail(B2F_EINVAL, "warp: NULL img/grid");
   if (B < 0 || H <= 0 || W <= 0 || C <= 0 || Hg <= 0 || Wg <= 0)
@@ -779,7 +995,20 @@ extern "C" int b2f_warp_bhwd_forward(const float* img, const float* grid, float*
     B2F_CHECK_LAUNCH("warp_fwd_vec4");
   } else if (C == 3) {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
-    if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && aligned16(out)) {
+    if (c3_win_ok(B, H, W, Hg, Wg) && aligned16(img) && aligned16(out)) {
+      CUtensorMap tm;
+      if ((rc = make_tmap2(&tm, img, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)W * 3, win::BOXF, win::WR))) return rc;
+      static thread_local int attr_dev = -1;
+      int dev = 0;
+      B2F_CUDA_TRY(cudaGetDevice(&dev));
+      if (attr_dev != dev) {
+        B2F_CUDA_TRY(cudaFuncSetAttribute(warp_fwd_c3_win, cudaFuncAttributeMaxDynamicSharedMemorySize, win::SMEM_BYTES));
+        attr_dev = dev;
+      }
+      dim3 gw((W + win::TW - 1) / win::TW, (H + win::TH - 1) / win::TH, B);
+      warp_fwd_c3_win<<<gw, win::THREADS, win::SMEM_BYTES, st>>>(tm, img, grid, out, H, W, (unsigned)((size_t)B * H * W * 3));
+      B2F_CHECK_LAUNCH("warp_fwd_c3_win");
+    } else if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && aligned16(out)) {
       warp_fwd_c3_lean<<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, out, H, W, Hg, Wg, (unsigned)((size_t)B * H * W * 3));
       B2F_CHECK_LAUNCH("warp_fwd_c3_lean");
     } else {
@@ -813,7 +1042,25 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
   } else if (C == 3) {
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
     const size_t elems = (size_t)B * H * W * 3;
-    if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && (only || aligned16(gradImg))) {
+    // the windowed form pays only for the flow-gradient-only backward (45 vs 53 us at 8 x 448 x 1024, i.i.d. 4 px flow):
+    // with the image-gradient scatter in the same kernel it measured 111 vs 113 us on scattered flow and 94-98 vs 84-88 us
+    // on smooth flow -- the reductions, not the gathers, bound that kernel, and eight pixels per thread serialise them
+    if (only && c3_win_ok(B, H, W, Hg, Wg) && aligned16(img)) {
+      CUtensorMap tm;
+      if ((rc = make_tmap2(&tm, img, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)W * 3, win::BOXF, win::WR))) return rc;
+      static thread_local int attr_dev = -1;
+      int dev = 0;
+      B2F_CUDA_TRY(cudaGetDevice(&dev));
+      if (attr_dev != dev) {
+        B2F_CUDA_TRY(cudaFuncSetAttribute(warp_bwd_c3_win<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, win::SMEM_BYTES));
+        B2F_CUDA_TRY(cudaFuncSetAttribute(warp_bwd_c3_win<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, win::SMEM_BYTES));
+        attr_dev = dev;
+      }
+      dim3 gw((W + win::TW - 1) / win::TW, (H + win::TH - 1) / win::TH, B);
+      if (only) warp_bwd_c3_win<true><<<gw, win::THREADS, win::SMEM_BYTES, st>>>(tm, img, grid, gradOut, gradImg, gradGrid, H, W, (unsigned)elems);
+      else warp_bwd_c3_win<false><<<gw, win::THREADS, win::SMEM_BYTES, st>>>(tm, img, grid, gradOut, gradImg, gradGrid, H, W, (unsigned)elems);
+      B2F_CHECK_LAUNCH("warp_bwd_c3_win");
+    } else if (c3_lean_ok(B, H, W, Hg, Wg) && aligned16(img) && (only || aligned16(gradImg))) {
       if (only) warp_bwd_c3_lean<true><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, (unsigned)elems);
       else warp_bwd_c3_lean<false><<<grid_dim, PIX_THREADS, 0, st>>>(img, grid, gradOut, gradImg, gradGrid, H, W, Hg, Wg, (unsigned)elems);
       B2F_CHECK_LAUNCH("warp_bwd_c3_lean");
