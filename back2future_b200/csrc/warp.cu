@@ -500,22 +500,24 @@ warp_fwd_c3_lean(const float* __restrict__ img, const float* __restrict__ grid, 
 // With scattered flow (the benchmark's i.i.d. N(0, 4 px)) every lane of a warp gathers from a different image row:
 // a global gather costs one L1 wavefront per lane and request, and warp_fwd_c3_lean is bound by L1 wavefronts
 // (~4.5 per pixel: 54 us at 8 x 448 x 1024, 33 % of the HBM roofline) with DRAM a third busy.  Here a CTA owns a
-// 32 x 64 output tile and has the TMA stage the source window of the tile +- 12 pixels (57 rows x 96 pixels, two
-// boxes of 144 floats: 65.7 KB) in shared memory while the threads fetch their flow values; the twelve tap values of a
+// 32 x 64 output tile and has the TMA stage the source window of the tile +- 12 pixels (58 rows x 96 pixels: one box of the
+// image viewed as 16-pixel groups, 66.8 KB) in shared memory while the threads fetch their flow values; the twelve tap values of a
 // pixel are then shared-memory loads (bank conflicts, ~3.5-way on random addresses, instead of 32-way wavefronts).  The
 // window position is STATIC, so the TMA is in flight from the first instruction; a pixel whose taps leave the window
-// (|flow| > 12 px: 0.5 % of an N(0, 4) field) takes the global path of the lean kernel -- the result never depends on
+// (|flow| > 12 px vertically, 15 px horizontally: 0.3 % of an N(0, 4) field) takes the global path of the lean kernel -- the result never depends on
 // the window.  Three CTAs per SM: one tile's fill runs under the others' gathers.  Rows / columns of the window
 // outside the image read as zero or as a neighbouring batch item's rows; neither is ever used (the coordinates are
 // clamped to the image, and a tap at index W or H is masked by rin / bin).  Same arithmetic expressions as
 // warp_fwd_c3_lean: bit-identical output.
 namespace win {
-constexpr int TH = 32, TW = 64, R = 12, THREADS = 256, PPT = TH * TW / THREADS;
-constexpr int WR = TH + 2 * R + 2;          // 58 window rows (57 needed; 58 x 576 B is a multiple of 128 B)
-constexpr int BOXF = 144;                   // floats per box row (48 pixels); two boxes side by side = 96 pixels
-constexpr int WPX = 2 * BOXF / 3;           // 96
-constexpr int BOX_ELEMS = WR * BOXF;
-constexpr int SMEM_BYTES = 2 * BOX_ELEMS * 4 + (THREADS / 32) * 96 * 4 + 64 + 128;
+constexpr int TH = 32, TW = 64, THREADS = 256, PPT = TH * TW / THREADS;
+constexpr int RX = 16, RY = 12;             // window margins: 16 columns (the box starts on a 16-pixel group), 12 rows
+constexpr int WR = TH + 2 * RY + 2;         // 58 window rows
+constexpr int WPX = TW + 2 * RX;            // 96 window columns = 6 groups of 16 pixels (48 floats)
+constexpr int PITCH = WPX * 3;              // 288 floats: ONE box {48 floats, 6 groups, 58 rows} of the image viewed as
+                                            // (48, W / 16, B H) lands the window with contiguous rows
+constexpr int BOX_ELEMS = WR * PITCH;
+constexpr int SMEM_BYTES = BOX_ELEMS * 4 + (THREADS / 32) * 96 * 4 + 64 + 128;
 static_assert((BOX_ELEMS * 4) % 128 == 0, "TMA destination alignment");
 }  // namespace win
 
@@ -526,17 +528,16 @@ warp_fwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restr
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const uint32_t box0 = smem_u32(smem);
-  float* s_out = reinterpret_cast<float*>(smem) + 2 * BOX_ELEMS;             // [warp][96]
+  float* s_out = reinterpret_cast<float*>(smem) + BOX_ELEMS;                 // [warp][96]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_out + (THREADS / 32) * 96);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int wx0 = x0 - R, wy0 = y0 - R;
+  const int wx0 = x0 - RX, wy0 = y0 - RY;
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(bar, 2 * BOX_ELEMS * 4);
-    tma_load_2d(smem, &tm_img, wx0 * 3, b * H + wy0, bar);
-    tma_load_2d(smem + BOX_ELEMS * 4, &tm_img, wx0 * 3 + BOXF, b * H + wy0, bar);
+    mbar_arrive_expect_tx(bar, BOX_ELEMS * 4);
+    tma_load_4d(smem, &tm_img, 0, wx0 / 16, b * H + wy0, 0, bar);
   }
   // thread -> pixels: warp w walks rows w, w + 8, ...; lanes cover 32 consecutive columns of one half-row
   Geo g[PPT];
@@ -563,17 +564,11 @@ warp_fwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restr
     const bool inwin = cx >= 0 && cx + 1 < WPX && cy >= 0 && cy + 1 < WR;
     if (live[k]) {
       if (inwin) {
-        const int c = cx * 3;
-        // the six floats of a tap row may straddle the two boxes (c = 141 .. 143): per-element box select
+        const uint32_t a = box0 + 4u * (uint32_t)(cy * PITCH + cx * 3);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const int ci = c + i;
-          const uint32_t a = box0 + 4u * (uint32_t)((ci < BOXF ? ci : BOX_ELEMS + ci - BOXF) + cy * BOXF);
-          float v0, v1;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(a));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(a + 4u * BOXF));
-          top[i] = v0;
-          bot[i] = v1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(top[i]) : "r"(a + 4u * i));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bot[i]) : "r"(a + 4u * (PITCH + i)));
         }
       } else {
         const unsigned a = (((unsigned)b * H + q.yi) * W + q.xi) * 3u;
@@ -661,16 +656,15 @@ warp_bwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restr
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const uint32_t box0 = smem_u32(smem);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem) + 2 * BOX_ELEMS + (THREADS / 32) * 96);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem) + BOX_ELEMS + (THREADS / 32) * 96);
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int wx0 = x0 - R, wy0 = y0 - R;
+  const int wx0 = x0 - RX, wy0 = y0 - RY;
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(bar, 2 * BOX_ELEMS * 4);
-    tma_load_2d(smem, &tm_img, wx0 * 3, b * H + wy0, bar);
-    tma_load_2d(smem + BOX_ELEMS * 4, &tm_img, wx0 * 3 + BOXF, b * H + wy0, bar);
+    mbar_arrive_expect_tx(bar, BOX_ELEMS * 4);
+    tma_load_4d(smem, &tm_img, 0, wx0 / 16, b * H + wy0, 0, bar);
   }
   Geo g[PPT];
   bool live[PPT];
@@ -705,16 +699,12 @@ warp_bwd_c3_win(const __grid_constant__ CUtensorMap tm_img, const float* __restr
     const unsigned a = (((unsigned)b * H + q.yi) * W + q.xi) * 3u;
     const unsigned ab = q.bin ? a + (unsigned)W * 3u : a;
     if (cx >= 0 && cx + 1 < WPX && cy >= 0 && cy + 1 < WR) {
-      const int c = cx * 3;
+      const uint32_t sa = box0 + 4u * (uint32_t)(cy * PITCH + cx * 3);
+      const uint32_t sb = sa + (q.bin ? 4u * PITCH : 0u);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const int ci = c + i;
-        const uint32_t sa = box0 + 4u * (uint32_t)((ci < BOXF ? ci : BOX_ELEMS + ci - BOXF) + cy * BOXF);
-        float t0, t1;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(sa));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(sa + (q.bin ? 4u * BOXF : 0u)));
-        top[i] = t0;
-        bot[i] = t1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(top[i]) : "r"(sa + 4u * i));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bot[i]) : "r"(sb + 4u * i));
       }
     } else {
       const Chunks9 rt = load_chunks(img, a, total);
@@ -960,10 +950,18 @@ bool c3_lean_ok(int B, int H, int W, int Hg, int Wg) {
 // few waves of 32 x 64 tiles; B2F_WARP_C3_WIN=0 switches it off (experiments)
 bool c3_win_ok(int B, int H, int W, int Hg, int Wg) {
   static const bool off = [] { const char* e = getenv("B2F_WARP_C3_WIN"); return e && e[0] == '0'; }();
-  if (off || !c3_lean_ok(B, H, W, Hg, Wg) || H != Hg || W != Wg || (W & 3) != 0) return false;
+  if (off || !c3_lean_ok(B, H, W, Hg, Wg) || H != Hg || W != Wg || (W & 15) != 0) return false;
   if ((int64_t)B * H > (1ll << 30)) return false;
   const int64_t tiles = (int64_t)B * ((H + win::TH - 1) / win::TH) * ((W + win::TW - 1) / win::TW);
   return tiles >= 2 * (int64_t)num_sms() && get_encode_fn() != nullptr;
+}
+
+// the (B, H, W, 3) image as (48 floats = 16 pixels, W / 16 groups, B H rows): one box is the whole window
+int win_tmap(CUtensorMap* tm, const float* img, int B, int H, int W) {
+  const uint64_t dims[4] = {48, (uint64_t)W / 16, (uint64_t)B * H, 1};
+  const uint64_t str[3] = {48, (uint64_t)W * 3, (uint64_t)W * 3 * B * H};
+  const uint32_t box[4] = {48, win::WPX / 16, (uint32_t)win::WR, 1};
+  return make_tmap4(tm, img, dims, str, box);
 }
 
 int check_args(const float* img, const float* grid, int B, int H, int W, int C, int Hg, int Wg) {
@@ -997,7 +995,7 @@ extern "C" int b2f_warp_bhwd_forward(const float* img, const float* grid, float*
     dim3 grid_dim((Wg + PIX_THREADS - 1) / PIX_THREADS, Hg, B);
     if (c3_win_ok(B, H, W, Hg, Wg) && aligned16(img) && aligned16(out)) {
       CUtensorMap tm;
-      if ((rc = make_tmap2(&tm, img, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)W * 3, win::BOXF, win::WR))) return rc;
+      if ((rc = win_tmap(&tm, img, B, H, W))) return rc;
       static thread_local int attr_dev = -1;
       int dev = 0;
       B2F_CUDA_TRY(cudaGetDevice(&dev));
@@ -1047,7 +1045,7 @@ extern "C" int b2f_warp_bhwd_backward(const float* img, const float* grid, const
     // on smooth flow -- the reductions, not the gathers, bound that kernel, and eight pixels per thread serialise them
     if (only && c3_win_ok(B, H, W, Hg, Wg) && aligned16(img)) {
       CUtensorMap tm;
-      if ((rc = make_tmap2(&tm, img, (uint64_t)W * 3, (uint64_t)B * H, (uint64_t)W * 3, win::BOXF, win::WR))) return rc;
+      if ((rc = win_tmap(&tm, img, B, H, W))) return rc;
       static thread_local int attr_dev = -1;
       int dev = 0;
       B2F_CUDA_TRY(cudaGetDevice(&dev));
