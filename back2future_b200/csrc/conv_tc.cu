@@ -366,6 +366,8 @@ int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl
 
 }  // namespace tc
 }  // namespace
+// the registered timeline buffer, shared with the tensor-core cost volume (costvol_tc.cu)
+unsigned long long* tc_trace_buffer() { return tc::g_tc_trace; }
 }  // namespace b2f
 
 using namespace b2f;

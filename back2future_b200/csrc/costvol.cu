@@ -20,6 +20,9 @@
 #include <type_traits>
 
 namespace b2f {
+// costvol_tc.cu: the forward on the tensor cores (tcgen05, three-pass TF32 split)
+int launch_costvol_fwd_tc(const float* ref, const float* frm, float* out, int64_t obs, int B, int C, int H, int W, float kdiv,
+                          int sgn, int dbg, cudaStream_t st);
 namespace {
 
 constexpr int kMaxFrames = 8;
@@ -878,6 +881,10 @@ extern "C" int b2f_costvol_forward(const float* const* frames, int F, int B, int
   const int sgn = fwd ? 1 : -1;
 
   const int path = costvol_path();
+  // 16 forces the tensor-core forward, 17 forbids it
+  // (18 / 19: measurement modes of the tensor-core kernel without global stores / without TMEM loads: WRONG results)
+  if ((path == 16 || path == 18 || path == 19) && F == 2 && win == 9 && (W % 4) == 0 && aligned16(frames[0]) && aligned16(frames[1]))
+    return launch_costvol_fwd_tc(frames[0], frames[1], out, obs, B, C, H, W, kdiv, sgn, path == 18 ? 1 : (path == 19 ? 2 : 0), st);
   const bool tma_ok = path != 1 && F == 2 && win == 9 && (W % 4) == 0 && aligned16(frames[0]) &&
                       aligned16(frames[1]) && aligned16(out) && (obs % 4) == 0 && get_encode_fn() != nullptr;
   if (tma_ok) {

@@ -74,8 +74,12 @@ B2F_API int b2f_reserve_scratch(size_t bytes);
  * 6 / 7 = force / forbid the persistent software-pipelined forward (FFMA2 + TMA-store epilogue).
  * 13 / 14 / 15 = backward with nine slab buffers and one CTA per SM / with the double-buffered ring
  * and two CTAs per SM / with 64-column tiles and a 3-deep ring.
+ * 16 = the forward on the tensor cores (tcgen05 / TMEM, three-pass TF32 split; costvol_tc.cu) whenever F=2,
+ * win=9, W%4==0 and the maps are 16-byte aligned; it is parity-green and measured level with the FFMA2
+ * kernel, so the automatic mode does not select it.
  * 8, 9, 10 are measurement aids that produce WRONG results: the tiled kernels without their
- * arithmetic (8), without their stores (9), or with neither (10) -- they time the TMA feed.       */
+ * arithmetic (8), without their stores (9), or with neither (10) -- they time the TMA feed; 18 / 19 are the
+ * same for the tensor-core forward (no global stores / no TMEM loads).                              */
 B2F_API int b2f_debug_costvol_path(int mode);
 /* Stream-ordered zero-fill of a device buffer (what the sampler's Lua wrapper does with
  * gradInput:zero() before the native call, BilinearSamplerBHWD.lua:99-102).                  */

@@ -132,6 +132,23 @@ def test_costvol_forward_tiled(env, mode, B, Cn, h, w, fwd):
     assert o.rel_err(out, o.costvol_forward(frames, 9, fwd)) < TOL
 
 
+# tensor-core forward (costvol_tc.cu, mode 16): one tile, several tiles per CTA and image, two / three / six channel
+# chunks, channels and image sizes that are not multiples of the tile (zero-filled operand rows, clipped stores),
+# more tiles than SMs (persistent CTAs walk the TMEM slot ring more than once)
+@pytest.mark.parametrize("B,Cn,h,w", [(1, 32, 8, 16), (2, 32, 16, 32), (1, 64, 24, 48), (2, 40, 13, 20), (1, 96, 9, 72),
+                                      (3, 3, 5, 8), (1, 192, 7, 16), (8, 32, 40, 96)])
+@pytest.mark.parametrize("fwd", [True, False])
+def test_costvol_forward_tensor_cores(env, B, Cn, h, w, fwd):
+    r = rng(16)
+    frames = [r.standard_normal((B, Cn, h, w)).astype(np.float32) for _ in range(2)]
+    env.lib.b2f_debug_costvol_path(16)
+    try:
+        out = _costvol_fwd(env, frames, 9, fwd, wide=True)
+    finally:
+        env.lib.b2f_debug_costvol_path(0)
+    assert o.rel_err(out, o.costvol_forward(frames, 9, fwd)) < TOL
+
+
 @pytest.mark.parametrize("win,F,B,Cn,h,w", [(9, 2, 2, 16, 11, 13), (5, 3, 1, 6, 12, 15), (3, 4, 2, 5, 8, 9),
                                             (9, 2, 1, 192, 7, 16), (1, 2, 1, 4, 3, 3)])
 @pytest.mark.parametrize("fwd", [True, False])
