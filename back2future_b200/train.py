@@ -242,30 +242,44 @@ class Trainer:
             st.plan.x.copy_(inputs, non_blocking=True)
             cur = torch.cuda.current_stream()
             segs = self._segments(st)
+            multi = self.comm is not None and self.comm.world > 1
             if graph and st.graph is None:
                 self._launch(st)                                       # warm-up: attributes, tensor maps, scratch
+                if multi:
+                    # NCCL allocates its channels on a communicator's first collective: not inside a capture
+                    self.comm.allreduce_sum(net.flat_grads, 0, min(1024, net.flat_grads.numel()), stream=cur)
                 cur.synchronize()
-                st.graph = []
-                for fn, _rng in segs:
-                    g = torch.cuda.CUDAGraph()
-                    cap = torch.cuda.Stream(net.device)
-                    cap.wait_stream(cur)
-                    with torch.cuda.graph(g, stream=cap):
+                # ONE graph for the whole step.  With more than one rank the bucket all-reduces are captured INTO it
+                # (NCCL records its kernels on a capturing stream): the communication stream forks from the capture
+                # stream behind the kernels that make a bucket final and joins before the end, so the reductions
+                # are graph nodes that run under the rest of the backward -- no host round trip per bucket (ten graph
+                # launches and ten event waits per step before: 0.94 ms exposed at 8 GPUs for a 0.14 ms collective).
+                g = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream(net.device)
+                cap.wait_stream(cur)
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                    for fn, rng in segs:
                         fn()
-                    st.graph.append(g)
-            multi = self.comm is not None and self.comm.world > 1
-            for i, (fn, rng) in enumerate(segs):
-                if graph:
-                    st.graph[i].replay()
-                else:
+                        if multi and rng is not None:
+                            ev = torch.cuda.Event()
+                            ev.record(cap)
+                            self._comm_stream.wait_event(ev)
+                            self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
+                    if multi:
+                        cap.wait_stream(self._comm_stream)
+                st.graph = g
+            if graph:
+                st.graph.replay()
+            else:
+                for fn, rng in segs:
                     fn()
-                if multi and rng is not None:
-                    ev = torch.cuda.Event()
-                    ev.record(cur)
-                    self._comm_stream.wait_event(ev)
-                    self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
-            if multi:
-                cur.wait_stream(self._comm_stream)
+                    if multi and rng is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(cur)
+                        self._comm_stream.wait_event(ev)
+                        self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
+                if multi:
+                    cur.wait_stream(self._comm_stream)
             if step:
                 net.adam_step(self.opt.LR, self.opt.beta1, self.opt.beta2, self.opt.epsilon, self.opt.weightDecay)
             st.loss_host.copy_(st.loss_dev, non_blocking=True)

@@ -325,3 +325,21 @@ def test_train_batch_matches_the_oracle_step(kind):
         gk = g[k].astype(np.float64)
         want = lr * gk / (np.abs(gk) + topt.epsilon / np.sqrt(1 - topt.beta2))
         assert np.allclose(d, want, rtol=2e-2, atol=lr * 2e-3), k
+
+
+@pytest.mark.gpu
+def test_data_parallel_step_with_captured_collectives_two_ranks():
+    """Two ranks (when the box has two GPUs): the one-graph training step with the bucket all-reduces captured into the
+    graph (libb2f_comm.so -> ncclAllReduce on the forked communication stream) against the eager step, and the
+    reduced gradient identical on both ranks (tools/check_train_multi.py)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29571", os.path.join(root, "tools", "check_train_multi.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
