@@ -237,7 +237,7 @@ __device__ __forceinline__ void fma2_window_row(Acc2<A>& acc, const Operands2<A>
     const int odd = j & 1;
     const f32x2 s = pack2(o.rv[j], o.rv[j]);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) acc.pair[j][m] = fma2(s, o.fe[(j + odd + 2 * m) >> 1], acc.pair[j][m]);
+    for (int m = 0; m < 4; ++m) fma2_acc(acc.pair[j][m], s, o.fe[(j + odd + 2 * m) >> 1]);
     float lo, hi;
     unpack2(o.fe[odd ? (j - 1) >> 1 : (j + 8) >> 1], lo, hi);
     acc.single[j] = fmaf(o.rv[j], odd ? hi : lo, acc.single[j]);
@@ -350,7 +350,9 @@ costvol_fwd_tma(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         // two operand sets: the loads of the next channel are issued before the FFMAs of the current one
         Operands2<A> o0, o1;
         load_operands2<A>(o0, rs, fs);
-#pragma unroll 1
+        // fully unrolled: with one trip per two channels ptxas closed every trip with ~30 MOVs (phi copies of
+        // accumulator pairs it had renamed inside the body: 19 % of the loop's issue slots)
+#pragma unroll
         for (int cc = 0; cc < CK; cc += 2) {
           load_operands2<A>(o1, rs + RSTEP, fs + FSTEP);
           fma2_window_row<A>(acc2, o0);

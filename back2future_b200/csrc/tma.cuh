@@ -199,6 +199,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+// accumulating form: the accumulator is ONE read-write operand, so the PTX has a single virtual register per accumulator
+// across a loop back-edge (with the value-returning form ptxas left 30 MOVs per two channels at the end of the
+// cost-volume forward's channel loop: the phi copies of accumulators it had renamed, 19 % of the loop's issue slots)
+__device__ __forceinline__ void fma2_acc(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
   f32x2 d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
