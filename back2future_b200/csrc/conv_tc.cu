@@ -317,6 +317,27 @@ __global__ void pack_tc_weights_kernel(const float* __restrict__ w, float* __res
   }
 }
 
+// packed FFMA layout [Cin * 9][CoutP] (conv.cu) -> tensor-core layout [9][N][Kp] hi / lo, on the device: the training
+// path re-packs the decoders' weights at the start of every step (Adam updates the flat packed parameters).
+// transpose = 0: the forward operand, N = Cout, K = input channels (zero beyond Cin up to Kp);
+// transpose = 1: the input-gradient operand, N = Cin, K = output channels, taps mirrored (w'[ci][co][t] = w[co][ci][8 - t]).
+__global__ void pack_tc_from_packed_kernel(const float* __restrict__ wp, float* __restrict__ hi, float* __restrict__ lo, int Cout,
+                                           int Cin, int CoutP, int N, int Kp, int transpose) {
+  const int total = 9 * N * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Kp, n = (i / Kp) % N, t = i / (Kp * N);
+    float v = 0.f;
+    if (!transpose) {
+      if (k < Cin && n < Cout) v = wp[((size_t)k * 9 + t) * CoutP + n];
+    } else {
+      if (k < Cout && n < Cin) v = wp[((size_t)n * 9 + (8 - t)) * CoutP + k];
+    }
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
 template <int N>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
               int CinP, int CoutP, cudaStream_t st) {
@@ -390,6 +411,19 @@ extern "C" int b2f_conv3x3_tc_pack_weights(const float* w_torch, float* w_hi, fl
   tc::pack_tc_weights_kernel<<<std::max(1, std::min((total + 255) / 256, num_sms() * 8)), 256, 0,
                                reinterpret_cast<cudaStream_t>(stream)>>>(w_torch, w_hi, w_lo, Cout, Cin, CinP);
   B2F_CHECK_LAUNCH("pack_tc_weights_kernel");
+  return B2F_OK;
+}
+
+extern "C" int b2f_conv3x3_tc_pack_from_packed(const float* w_packed, float* w_hi, float* w_lo, int Cout, int Cin, int K,
+                                               int transpose, b2f_stream_t stream) {
+  if (!w_packed || !w_hi || !w_lo || Cout <= 0 || Cin <= 0) return fail(B2F_EINVAL, "conv3x3_tc_pack_from_packed: bad argument");
+  const int kmin = transpose ? Cout : Cin;
+  if (K < kmin) return fail(B2F_EINVAL, "conv3x3_tc_pack_from_packed: K = %d smaller than the %d channels of the weights", K, kmin);
+  const int Kp = (K + 31) / 32 * 32, N = transpose ? Cin : Cout, CoutP = (Cout + 63) / 64 * 64;
+  const int total = 9 * N * Kp;
+  tc::pack_tc_from_packed_kernel<<<std::max(1, std::min((total + 255) / 256, num_sms() * 8)), 256, 0,
+                                   reinterpret_cast<cudaStream_t>(stream)>>>(w_packed, w_hi, w_lo, Cout, Cin, CoutP, N, Kp, transpose);
+  B2F_CHECK_LAUNCH("pack_tc_from_packed_kernel");
   return B2F_OK;
 }
 

@@ -105,10 +105,13 @@ class PWCNet:
     (Cout,) bias) with the names of `conv_shapes`; None = nn.SpatialConvolution:reset()'s uniform(-1/sqrt(9 nIn), ..)
     drawn from numpy's default_rng(seed)."""
 
-    def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True, tensor_cores=False):
+    def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True, tensor_cores=False,
+                 train_planar=False):
         """tensor_cores=True: the decoders' five wide convolutions run on tcgen05 (b2f_conv3x3_tc_forward, three-pass
-        TF32 split, fp32-level accuracy) over channel-minor (hi, lo) activations; inference only (the backward plan
-        reads the planar activations of the FFMA path)."""
+        TF32 split, fp32-level accuracy) over channel-minor (hi, lo) activations.  The backward plan reads PLANAR
+        activations: with train_planar=True every tensor-core layer also writes its planar output (its second
+        destination) and the forward plan starts by re-packing the decoders' (hi, lo) weights from the flat parameter
+        buffer (Adam updates it every step) -- the training configuration of the tensor-core forward."""
         if not torch.cuda.is_available():
             raise RuntimeError("PWCNet: no CUDA device; the B200 path has no CPU fallback")
         self.opt = opt or Opt()
@@ -116,6 +119,7 @@ class PWCNet:
         self.lib = _lib.load()
         self.image_warps = bool(image_warps)
         self.tensor_cores = bool(tensor_cores)
+        self.train_planar = bool(train_planar) and self.tensor_cores
         o = self.opt
         self.past_flow = bool(o.past_flow)                                             # model.past_flow, pwc.lua:494
         self.flow_scale = [o.flownet_factor / 2.0 ** (l - o.l_st) for l in range(o.levels, o.l_st - 1, -1)]   # :451-455
@@ -293,6 +297,13 @@ class PWCNet:
             prev = feats[l]
         plan.feats = feats
 
+        # -- training with the tensor-core forward: the (hi, lo) decoder weights follow the flat parameters ---------
+        if self.train_planar:
+            for name, cv in self._convs.items():
+                if cv.tc_h is not None:
+                    ops.append((0, lib.b2f_conv3x3_tc_pack_from_packed,
+                                (P(cv.w), P(cv.tc_h), P(cv.tc_l), cv.cout, cv.cin, cv.tc_cin, 0)))
+
         # -- levels, coarse to fine ---------------------------------------------------------------------------
         outs = {}
         warped = {}
@@ -313,7 +324,7 @@ class PWCNet:
 
             def decoder(kind, lane, x0, cin0):
                 if self.tensor_cores:
-                    return decoder_tc(kind, lane)
+                    return decoder_tc(kind, lane, cin0)
                 t, tb, cin = x0, jbs, cin0
                 chain = []
                 for i, cout in enumerate(DEC):
@@ -324,26 +335,32 @@ class PWCNet:
                 plan.dec[(kind, l)] = (chain, cin0)
                 return out
 
-            def decoder_tc(kind, lane):
+            def decoder_tc(kind, lane, cin0):
                 """Five tensor-core layers over channel-minor (hi, lo) pairs; the fifth writes planar fp32 for the
-                2-channel head (FFMA kernel: N = 2 is no tensor-core shape)."""
+                2-channel head (FFMA kernel: N = 2 is no tensor-core shape).  train_planar: every layer also writes its
+                planar output, the activations the backward plan reads (plan.dec, as the FFMA decoder records them)."""
                 xh, xl, cin = Jsplit[0], Jsplit[1], cj
+                chain = []
                 for i, cout in enumerate(DEC[:5]):
                     cv = self._convs["%s.l%d.%d" % (kind, l, i)]
                     assert cv.tc_cin == cin, (kind, l, i, cv.tc_cin, cin)
                     last = i == 4
                     oh = None if last else E(B, h, w, _round32(cout))
                     ol = None if last else E(B, h, w, _round32(cout))
-                    planar = E(B, cout, h, w) if last else None
+                    planar = E(B, cout, h, w) if (last or self.train_planar) else None
                     plan.keep += [t_ for t_ in (oh, ol, planar) if t_ is not None]
+                    chain.append(planar)
                     ops.append((lane, lib.b2f_conv3x3_tc_forward,
                                 (P(xh), P(xl), P(cv.tc_h), P(cv.tc_l), P(cv.b), P(oh) if oh is not None else None,
-                                 P(ol) if ol is not None else None, P(planar) if last else None, 0, B, cin, h, w, cout,
-                                 C.c_float(0.2))))
+                                 P(ol) if ol is not None else None, P(planar) if planar is not None else None, 0, B, cin,
+                                 h, w, cout, C.c_float(0.2))))
                     xh, xl, cin = oh, ol, cout
                 out = E(B, 2, h, w)
                 plan.keep.append(out)
+                chain.append(out)
                 conv("%s.l%d.5" % (kind, l), P(planar), 0, B, DEC[4], h, w, P(out), 0, slope=1.0, lane=lane)
+                if self.train_planar:
+                    plan.dec[(kind, l)] = (chain, cin0)
                 return out
 
             Jsplit = None
@@ -635,9 +652,9 @@ class PWCNet:
         `flat_grads` (zeroed first, like train.lua:251's zeroGradParameters).  gradOutputs: tensors shaped like the
         output table (device)."""
         p = self.plan(x.size(0), x.size(2), x.size(3))
-        if not self.image_warps or self.tensor_cores:
+        if not self.image_warps or (self.tensor_cores and not self.train_planar):
             raise RuntimeError("backward needs the full output table and the planar activations: build the model with "
-                               "image_warps=True, tensor_cores=False")
+                               "image_warps=True and tensor_cores=False (or tensor_cores=True, train_planar=True)")
         with torch.cuda.device(self.device):
             if p.bops is None:
                 self._build_backward(p)

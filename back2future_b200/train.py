@@ -80,9 +80,9 @@ class Trainer:
     LOSSES = ("sflow", "cvel", "pme", "socc", "gocc")
 
     def __init__(self, net: pwc.PWCNet, opt: TrainOpt | None = None, comm=None):
-        if not net.image_warps or net.tensor_cores:
+        if not net.image_warps or (net.tensor_cores and not net.train_planar):
             raise ValueError("training needs the warped frames and the planar activations: build the model with "
-                             "image_warps=True, tensor_cores=False")
+                             "image_warps=True and tensor_cores=False (or tensor_cores=True, train_planar=True)")
         self.net, self.opt, self.comm = net, opt or TrainOpt(), comm
         self.lib = net.lib
         self._steps = {}

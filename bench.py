@@ -609,31 +609,37 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
     out = {"shape": "%d x 9 x %d x %d per GPU" % (B, H, W)}
     cm = bcomm.Communicator.from_env() if world > 1 else None
     hin = torch.empty(B, 9, H, W).uniform_(-2.1, 2.6).pin_memory()
+    def timed(net, topt, c):
+        tr = train.Trainer(net, topt, comm=c)
+        for _ in range(2):
+            losses = tr.train_batch(hin)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            losses = tr.train_batch(hin)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        del tr
+        return ms, losses
+
     for key, past_flow, topt in (("config2_hard", False, train.TrainOpt.hard()), ("config3_soft", True, train.TrainOpt.soft())):
-        net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True)
+        # forward: the decoders on tcgen05 (planar activations as second outputs for the backward plan, (hi, lo) weights
+        # re-packed from the flat parameters every step); backward: FFMA kernels
+        net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True, tensor_cores=True, train_planar=True)
         res = {}
         for label, c in ((("with_allreduce", cm),) if world > 1 else ()) + (("local", None),):
-            tr = train.Trainer(net, topt, comm=c)
-            for _ in range(2):
-                losses = tr.train_batch(hin)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(steps):
-                losses = tr.train_batch(hin)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / steps
-            if world > 1:
-                t = torch.tensor([ms], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = t.item()
-            res[label] = ms
-            del tr
+            res[label], losses = timed(net, topt, c)
         step_ms = res.get("with_allreduce", res["local"])
         out[key] = {"ms_per_step": round(step_ms, 3), "samples_per_s": round(world * B / step_ms * 1e3, 1),
+                    "forward": "decoders on tcgen05 (three-pass TF32 split), feature pyramid + heads FFMA2",
                     "h2d_bytes_per_step": B * 9 * H * W * 4, "loss": round(losses["err"], 4),
                     "parameters": net.n_params(), "flat_gradient_floats": int(net.flat_params.numel())}
         if world > 1:
@@ -641,6 +647,12 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
             out[key]["allreduce_exposed_ms"] = round(res["with_allreduce"] - res["local"], 3)
         del net
         torch.cuda.empty_cache()
+        if world == 1:
+            net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True)
+            ms, _l = timed(net, topt, None)
+            out[key]["ms_per_step_ffma_forward"] = round(ms, 3)
+            del net
+            torch.cuda.empty_cache()
     if cm is not None:
         cm.destroy()
     return out

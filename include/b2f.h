@@ -254,6 +254,12 @@ B2F_API int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout);
 B2F_API int b2f_debug_tc_trace(unsigned long long* device_buffer);
 B2F_API int b2f_conv3x3_tc_pack_weights(const float* w_torch, float* w_hi, float* w_lo, int Cout, int Cin,
                                         b2f_stream_t stream);
+/* The same (hi, lo) tensor-core weights from the PACKED layout of b2f_conv3x3_pack_weights, on the device (the training
+ * path re-packs after every Adam step).  K = number of input channels the operand is padded to (>= Cin; the coarsest
+ * flow decoder reads a wider joined input with zero weights).  transpose = 1 builds the operand of the INPUT-GRADIENT
+ * convolution instead: N = Cin output rows, K (>= Cout) input channels, taps mirrored.                              */
+B2F_API int b2f_conv3x3_tc_pack_from_packed(const float* w_packed, float* w_hi, float* w_lo, int Cout, int Cin, int K,
+                                            int transpose, b2f_stream_t stream);
 B2F_API int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, float* hi, float* lo, int B, int C, int H,
                                      int W, b2f_stream_t stream);
 B2F_API int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,

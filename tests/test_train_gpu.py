@@ -178,6 +178,11 @@ def test_network_backward_matches_autograd(past_flow, B, H, W):
     bias gradient of the 62 (Hard) / 92 (Soft) convolutions at 1e-4 (relative to the tensor's scale)."""
     from back2future_b200 import pwc
     from oracle import b2f_oracle as o, pwc_oracle as po, pwc_torch as pt
+    # deterministic forward (see test_train_batch_matches_the_oracle_step): the split-channel cost volumes of the small
+    # levels accumulate with float atomics, and an ulp of run-to-run difference can flip a floor() in a warp or a
+    # LeakyReLU sign, which moves one weight gradient by 10-25 % (seen: two runs in six)
+    from back2future_b200 import _lib as _l
+    request_restore.append(_l.load().b2f_debug_costvol_path(2))
     oopt = po.Opt(past_flow=past_flow)
     params = po.init_params(oopt, seed=31, scale=2.0)
     net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), params)
@@ -276,7 +281,7 @@ def _restore_costvol_path():
 
 
 @pytest.mark.parametrize("kind", ["hard", "soft"])
-def test_train_batch_matches_the_oracle_step(kind):
+def test_train_batch_matches_the_oracle_step(kind, tensor_cores=False):
     """train.lua:196-496 for one batch (B = 2, 64 x 64): the five weighted losses and every parameter gradient against
     the oracle composition; then an Adam step moves the parameters by optim.adam's formula."""
     from back2future_b200 import pwc, train
@@ -285,7 +290,7 @@ def test_train_batch_matches_the_oracle_step(kind):
     topt = train.TrainOpt.hard() if kind == "hard" else train.TrainOpt.soft()
     oopt = po.Opt(past_flow=past_flow)
     params = po.init_params(oopt, seed=41, scale=2.0)
-    net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), params)
+    net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), params, tensor_cores=tensor_cores, train_planar=tensor_cores)
     tr = train.Trainer(net, topt)
     rng = np.random.default_rng(44)
     x = _smooth((2, 9, 64, 64), rng)
@@ -325,6 +330,80 @@ def test_train_batch_matches_the_oracle_step(kind):
         gk = g[k].astype(np.float64)
         want = lr * gk / (np.abs(gk) + topt.epsilon / np.sqrt(1 - topt.beta2))
         assert np.allclose(d, want, rtol=2e-2, atol=lr * 2e-3), k
+
+
+@pytest.mark.parametrize("kind", ["hard", "soft"])
+def test_train_batch_with_the_tensor_core_forward(kind):
+    """The training step with the decoders' forward on tcgen05 (PWCNet(tensor_cores=True, train_planar=True): planar
+    activations as second outputs, (hi, lo) weights re-packed from the flat parameters at the start of every step)
+    against the same step on the FFMA path.  The three-pass TF32 forward differs from the FFMA forward by ~1e-5 per
+    level (up to 2e-4 after five levels of flow feedback).  A difference of that size can flip a floor() in a warp, a
+    LeakyReLU sign or a saturated softmax term, each of which moves some weight gradient by 10-30 % (the same
+    ill-conditioning the oracle test above documents for run-to-run ulps), so the GRADIENTS of the two paths are not
+    compared on independently computed activations: losses and activations are, and the backward plans are compared
+    on one identical forward state."""
+    from back2future_b200 import pwc, train
+    from oracle import b2f_oracle as o, pwc_oracle as po
+    past_flow = kind == "soft"
+    mk = train.TrainOpt.hard if kind == "hard" else train.TrainOpt.soft
+    oopt = po.Opt(past_flow=past_flow)
+    params = po.init_params(oopt, seed=41, scale=1.0)
+    rng = np.random.default_rng(44)
+    x = _smooth((2, 9, 64, 64), rng)
+    from back2future_b200 import _lib as _l
+    request_restore.append(_l.load().b2f_debug_costvol_path(2))
+    nets = {tc: pwc.PWCNet(pwc.Opt(past_flow=past_flow), params, tensor_cores=tc, train_planar=tc) for tc in (False, True)}
+    # (1) the configuration's own penalties: losses and every recorded activation
+    res = {}
+    for tc, net in nets.items():
+        tr = train.Trainer(net, mk())
+        res[tc] = tr.train_batch(_dev(x), graph=False, step=False)
+    for k in res[False]:
+        assert abs(res[True][k] - res[False][k]) <= 1e-4 * max(abs(res[False][k]), 1e-6), (k, res[True][k], res[False][k])
+    pa, pb = nets[False].plan(2, 64, 64), nets[True].plan(2, 64, 64)
+    for key in pa.dec:
+        for a, b in zip(pa.dec[key][0], pb.dec[key][0]):
+            assert o.rel_err(b.cpu().numpy(), a.cpu().numpy()) < 5e-4, key
+    # (2) the backward plan of the tensor-core net reads the buffers its forward wrote: copy the tensor-core net's whole
+    # forward state (every tensor of its plan that the FFMA plan also has) into the FFMA net's plan and run both
+    # backward plans on the same gradOutputs -- identical inputs, so no threshold can flip between the two
+    def tensors(obj, path, out):
+        if torch.is_tensor(obj):
+            out[path] = obj
+        elif isinstance(obj, dict):
+            for k, v in obj.items():
+                tensors(v, path + (k,), out)
+        elif isinstance(obj, (list, tuple)):
+            for i, v in enumerate(obj):
+                tensors(v, path + (i,), out)
+    ta, tb = {}, {}
+    for name in ("x", "J", "feats", "tmp", "warped", "occ", "skip_occ", "fs", "ufs", "skip_chain", "ds", "dec", "iw", "output"):
+        tensors(getattr(pa, name), (name,), ta)
+        tensors(getattr(pb, name), (name,), tb)
+    assert set(ta) == set(tb)
+    for k in ta:
+        ta[k].copy_(tb[k])
+    gos = [torch.randn_like(t) for t in pa.output]
+    grads = {}
+    for tc, net in nets.items():
+        net.backward(_dev(x), gos)
+        torch.cuda.synchronize()
+        grads[tc] = net.grad_params()
+    worst = max((o.rel_err(grads[True][k], grads[False][k]), k) for k in grads[False])
+    assert worst[0] < 2e-4, worst
+    # (3) an optimizer step on the tensor-core net: the NEXT forward must see the updated weights (operands re-packed
+    # inside the step)
+    net = nets[True]
+    tr = train.Trainer(net, mk())
+    tr.train_batch(_dev(x), graph=True, step=True)
+    tr.train_batch(_dev(x), graph=True, step=True)
+    after = net.state_params()
+    out_tc = [t.cpu().numpy() for t in net.forward(_dev(x), graph=False)]
+    ref_net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), after)
+    out_ff = [t.cpu().numpy() for t in ref_net.forward(_dev(x), graph=False)]
+    for a, b in zip(out_tc, out_ff):
+        assert o.rel_err(a, b) < 5e-4
+    assert any(not np.array_equal(after[k], params[k]) for k in params)
 
 
 @pytest.mark.gpu
