@@ -104,6 +104,11 @@ struct Args {
   int Cout, H, W, tiles_x, tiles_y;
   float slope;
   int store_split;        // TMA-store (hi, lo) channel-minor tensors
+  // input-gradient use (b2f_conv3x3_tc_backward_data): the activation derivative comes from `mask`, the planar forward
+  // output of the layer whose input gradient this is (factor 1 where mask > 0, `slope` elsewhere), not from the
+  // result's own sign
+  const float* mask;
+  int64_t mbs;
 };
 
 template <int N>
@@ -227,7 +232,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     for (int j = 0; j < 32; ++j) {
       const int n = 32 * g + j;
       float t = __uint_as_float(v[j]) + ((a.bias && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
-      t = t > 0.f ? t : t * a.slope;
+      if (a.mask) {
+        const float mk = (inside && n < a.Cout) ? __ldg(a.mask + (size_t)b * a.mbs + ((size_t)n * a.H + y) * a.W + x) : 1.f;
+        t = mk > 0.f ? t : t * a.slope;
+      } else {
+        t = t > 0.f ? t : t * a.slope;
+      }
       f[j] = n < a.Cout ? t : 0.f;
     }
     if (a.out_planar && inside) {
@@ -439,6 +449,48 @@ extern "C" int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, 
   tc::split_from_planar_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, xbs, hi, lo, C, Cp, hw);
   B2F_CHECK_LAUNCH("split_from_planar_kernel");
   return B2F_OK;
+}
+
+static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* out_hi, float* out_lo,
+                       const tc::Args& a, int B, int Cin, int Cout, cudaStream_t st, const char* who) {
+  const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
+  switch (Cout) {
+    case 32: return tc::launch_tc<32>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 64: return tc::launch_tc<64>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 96: return tc::launch_tc<96>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 128: return tc::launch_tc<128>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    default: return fail(B2F_EUNSUPPORTED, "%s: %d output channels is not one of the decoder widths (32, 64, 96, 128)", who, Cout);
+  }
+}
+
+// Input gradient of a stride-1 3x3 convolution on the tensor cores: the forward kernel on the transposed, mirrored
+// weights (b2f_conv3x3_tc_pack_from_packed, transpose = 1) over the channel-minor (hi, lo) OUTPUT gradient, with the
+// LeakyReLU derivative of the layer below taken from its planar forward output `act`.
+extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
+                                            const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
+                                            float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
+                                            int Cin, float leaky_slope, b2f_stream_t stream) {
+  if (!g_hi || !g_lo || !wt_hi || !wt_lo) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: NULL gradient / weights");
+  if ((gin_hi == nullptr) != (gin_lo == nullptr)) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: gin_hi and gin_lo go together");
+  if (!gin_hi && !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: no output");
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || B > 65535) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: bad size");
+  if (!aligned16(g_hi) || !aligned16(g_lo) || !aligned16(wt_hi) || !aligned16(wt_lo) || (gin_hi && (!aligned16(gin_hi) || !aligned16(gin_lo))))
+    return fail(B2F_EALIGN, "conv3x3_tc_backward_data: operands must be 16-byte aligned");
+  if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: cuTensorMapEncodeTiled not available");
+  if (B == 0) return B2F_OK;
+  tc::Args a{};
+  a.trace = tc::g_tc_trace;
+  a.bias = nullptr;
+  a.out_planar = gin_planar;
+  a.pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
+  a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
+  a.Cout = Cin; a.H = H; a.W = W;               // N = its input channels
+  a.slope = act ? leaky_slope : 1.f;
+  a.store_split = gin_hi != nullptr;
+  a.mask = act;
+  a.mbs = act_batch_stride ? act_batch_stride : (int64_t)Cin * H * W;
+  return tc_dispatch(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, Cin, reinterpret_cast<cudaStream_t>(stream),
+                     "conv3x3_tc_backward_data");
 }
 
 extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,

@@ -89,7 +89,7 @@ def _vp(t):
 
 
 class _Conv:
-    __slots__ = ("w", "b", "cin", "cout", "stride", "gw", "gb", "wt", "w_off", "b_off", "tc_h", "tc_l", "tc_cin")
+    __slots__ = ("w", "b", "cin", "cout", "stride", "gw", "gb", "wt", "w_off", "b_off", "tc_h", "tc_l", "tc_cin", "tct_h", "tct_l")
 
 
 def _round64(n):
@@ -189,7 +189,7 @@ class PWCNet:
                 cv.b = self.flat_params[off + nw:off + nw + cout]
                 cv.b.copy_(torch.from_numpy(b), non_blocking=False)        # cudaMemcpy H2D
                 cv.gw = cv.gb = cv.wt = None
-                cv.tc_h = cv.tc_l = None
+                cv.tc_h = cv.tc_l = cv.tct_h = cv.tct_l = None
                 if self.tensor_cores and kind in ("occ", "flow", "bflow") and cout in (32, 64, 96, 128):
                     # [9][Cout][Cin_p] hi / lo for the tensor-core path.  The coarsest level's flow decoder reads the
                     # first 162 channels of the occlusion decoder's wider joined input: zero weights for the rest.
@@ -516,6 +516,13 @@ class PWCNet:
         zero(self.flat_grads)                                      # model:zeroGradParameters(), train.lua:251
         for name, cv in self._convs.items():
             ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
+            kind, _lvl, idx = name.split(".")
+            if self.train_planar and kind in ("occ", "flow", "bflow") and idx in ("1", "2", "3", "4"):
+                if cv.tct_h is None:
+                    n_t = 9 * cv.cin * _round32(cv.cout)
+                    cv.tct_h = torch.empty(n_t, device=dev, dtype=torch.float32)
+                    cv.tct_l = torch.empty(n_t, device=dev, dtype=torch.float32)
+                ops.append((lib.b2f_conv3x3_tc_pack_from_packed, (P(cv.w), P(cv.tct_h), P(cv.tct_l), cv.cout, cv.cin, cv.cout, 1)))
         g_feats = {l: E(*plan.feats[l].shape) for l in plan.feats}
         for l in g_feats:
             zero(g_feats[l])
@@ -576,6 +583,8 @@ class PWCNet:
 
             def decoder_backward(kind, G, first):
                 chain, cin0 = plan.dec[(kind, l)]
+                if self.train_planar:
+                    return decoder_backward_tc(kind, G, first, chain, cin0)
                 for i in range(5, -1, -1):
                     name = "%s.l%d.%d" % (kind, l, i)
                     if i > 0:
@@ -590,6 +599,37 @@ class PWCNet:
                         G = gin
                     else:
                         dgrad(name, P(G), 0, None, 0, P(gJl), jbs, not first, B, cin, h, w)
+
+            def decoder_backward_tc(kind, G, first, chain, cin0):
+                """The same walk with the input gradients of layers 4..1 on tcgen05 (b2f_conv3x3_tc_backward_data: the
+                forward tensor-core kernel on transposed, mirrored (hi, lo) weights): the head's input gradient (FFMA, 32
+                channels) is split once into channel-minor (hi, lo), every tensor-core layer hands (hi, lo) to the next
+                and writes the planar copy the weight-gradient kernel reads; layer 0 (N = 196 .. 356 input channels: no
+                tensor-core shape) and all weight gradients stay on the FFMA kernels."""
+                name5 = "%s.l%d.5" % (kind, l)
+                wgrad(name5, P(chain[4]), 0, P(G), 0, B, DEC[4], h, w)
+                g4 = E(B, DEC[4], h, w)
+                dgrad(name5, P(G), 0, P(chain[4]), 0, P(g4), 0, False, B, DEC[4], h, w)
+                gh, gl = E(B, h, w, _round32(DEC[4])), E(B, h, w, _round32(DEC[4]))
+                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(g4), 0, P(gh), P(gl), B, DEC[4], h, w)))
+                plan.keep += [g4, gh, gl]
+                Gp = g4
+                for i in range(4, 0, -1):
+                    name = "%s.l%d.%d" % (kind, l, i)
+                    cv = self._convs[name]
+                    cin, cout = DEC[i - 1], DEC[i]
+                    wgrad(name, P(chain[i - 1]), 0, P(Gp), 0, B, cin, h, w)
+                    gin = E(B, cin, h, w)
+                    nh = E(B, h, w, _round32(cin)) if i > 1 else None
+                    nl = E(B, h, w, _round32(cin)) if i > 1 else None
+                    plan.keep += [t_ for t_ in (gin, nh, nl) if t_ is not None]
+                    ops.append((lib.b2f_conv3x3_tc_backward_data,
+                                (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), P(chain[i - 1]), 0, P(nh) if nh is not None else None,
+                                 P(nl) if nl is not None else None, P(gin), 0, B, cout, h, w, cin, C.c_float(0.2))))
+                    gh, gl, Gp = nh, nl, gin
+                name0 = "%s.l%d.0" % (kind, l)
+                wgrad(name0, P(Jl), jbs, P(Gp), 0, B, cin0, h, w)
+                dgrad(name0, P(Gp), 0, None, 0, P(gJl), jbs, not first, B, cin0, h, w)
 
             # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
             g_occ = E(B, 2, h, w)

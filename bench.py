@@ -632,14 +632,17 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
 
     for key, past_flow, topt in (("config2_hard", False, train.TrainOpt.hard()), ("config3_soft", True, train.TrainOpt.soft())):
         # forward: the decoders on tcgen05 (planar activations as second outputs for the backward plan, (hi, lo) weights
-        # re-packed from the flat parameters every step); backward: FFMA kernels
+        # re-packed from the flat parameters every step); backward: input gradients of decoder layers 1-4 on tcgen05,
+        # layer 0 / heads / feature pyramid and every weight gradient on the FFMA kernels
         net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True, tensor_cores=True, train_planar=True)
         res = {}
         for label, c in ((("with_allreduce", cm),) if world > 1 else ()) + (("local", None),):
             res[label], losses = timed(net, topt, c)
         step_ms = res.get("with_allreduce", res["local"])
         out[key] = {"ms_per_step": round(step_ms, 3), "samples_per_s": round(world * B / step_ms * 1e3, 1),
-                    "forward": "decoders on tcgen05 (three-pass TF32 split), feature pyramid + heads FFMA2",
+                    "tensor_cores": "decoder forward + input gradients of decoder layers 1-4 on tcgen05 (three-pass TF32 "
+                                    "split); feature pyramid, heads, first decoder layer's input gradient and all weight "
+                                    "gradients on the FFMA kernels",
                     "h2d_bytes_per_step": B * 9 * H * W * 4, "loss": round(losses["err"], 4),
                     "parameters": net.n_params(), "flat_gradient_floats": int(net.flat_params.numel())}
         if world > 1:
@@ -650,7 +653,7 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
         if world == 1:
             net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True)
             ms, _l = timed(net, topt, None)
-            out[key]["ms_per_step_ffma_forward"] = round(ms, 3)
+            out[key]["ms_per_step_ffma_only"] = round(ms, 3)
             del net
             torch.cuda.empty_cache()
     if cm is not None:

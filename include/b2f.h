@@ -266,6 +266,16 @@ B2F_API int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const f
                                    const float* bias, float* out_hi, float* out_lo, float* out_planar,
                                    int64_t out_planar_batch_stride, int B, int Cin, int H, int W, int Cout,
                                    float leaky_slope, b2f_stream_t stream);
+/* SpatialConvolution:updateGradInput of the same layer on the tensor cores (train.lua:480 model:backward): the forward
+ * kernel on the transposed, mirrored weights (b2f_conv3x3_tc_pack_from_packed with transpose = 1: N = Cin rows, K = Cout)
+ * over the channel-minor (hi, lo) gradient of the layer's OUTPUT; `act` = planar forward output of the layer BELOW
+ * (B, Cin, H, W): the result is multiplied by 1 where act > 0 and by leaky_slope elsewhere (NULL: no factor).  Outputs
+ * as b2f_conv3x3_tc_forward: (hi, lo) channel-minor for the next tensor-core input gradient and / or planar fp32 for
+ * the weight-gradient kernel.  Cin in {32, 64, 96, 128}.                                                              */
+B2F_API int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
+                                         const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
+                                         float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
+                                         int Cin, float leaky_slope, b2f_stream_t stream);
 
 /* ---- training: backward of the conv trunk + optimizer -------------------------------
  * Weight gradients live in the same PACKED layout as the weights ([Cin * 9][CoutP]), so that parameters, gradients

@@ -29,9 +29,10 @@ ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--H", type=int, default=320)
 ap.add_argument("--W", type=int, default=640)
 ap.add_argument("--past-flow", action="store_true")
+ap.add_argument("--tc", action="store_true", help="tensor-core forward + input gradients (train_planar)")
 a = ap.parse_args()
 lib = _lib.load()
-net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow))
+net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), tensor_cores=a.tc, train_planar=a.tc)
 x = torch.randn(a.B, 9, a.H, a.W, device="cuda")
 out = net.forward(x, graph=False)
 net.backward(x, [torch.randn_like(t) for t in out])
