@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
 CSRC      := back2future_b200/csrc
 OBJDIR    := build
-SRCS      := $(CSRC)/api.cu $(CSRC)/costvol.cu $(CSRC)/warp.cu $(CSRC)/criterions.cu $(CSRC)/conv.cu $(CSRC)/train.cu $(CSRC)/conv_tc.cu $(CSRC)/costvol_tc.cu
+SRCS      := $(CSRC)/api.cu $(CSRC)/costvol.cu $(CSRC)/warp.cu $(CSRC)/criterions.cu $(CSRC)/conv.cu $(CSRC)/train.cu $(CSRC)/conv_tc.cu $(CSRC)/costvol_tc.cu $(CSRC)/wgrad_tc.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := back2future_b200/libb2f_cuda.so
 COMMLIB   := back2future_b200/libb2f_comm.so

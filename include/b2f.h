@@ -276,6 +276,15 @@ B2F_API int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, c
                                          const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
                                          float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
                                          int Cin, float leaky_slope, b2f_stream_t stream);
+/* SpatialConvolution:accGradParameters of the same layer on the tensor cores: gw_packed += d loss / d weight from the
+ * channel-minor (hi, lo) INPUT activation (x_hi / x_lo, a (B, H, W, Cx rounded up to 32) tensor whose first Cin channels
+ * are this convolution's input -- the coarsest flow decoder reads the first 162 channels of a wider joined input) and
+ * the channel-minor (hi, lo) OUTPUT gradient: MN-major operands, the contraction runs over the pixels and a tap is a
+ * descriptor offset (wgrad_tc.cu).  gbias (may be NULL) += d loss / d bias, summed from the PLANAR output gradient
+ * g_planar (B, Cout, H, W; batch stride 0 = dense).  Cout in {32, 64, 96, 128}; any Cin.                              */
+B2F_API int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x_lo, int Cx, const float* g_hi, const float* g_lo,
+                                            const float* g_planar, int64_t g_planar_batch_stride, float* gw_packed,
+                                            float* gbias, int B, int Cin, int H, int W, int Cout, b2f_stream_t stream);
 
 /* ---- training: backward of the conv trunk + optimizer -------------------------------
  * Weight gradients live in the same PACKED layout as the weights ([Cin * 9][CoutP]), so that parameters, gradients

@@ -96,3 +96,52 @@ def test_conv3x3_tc_rejects_bad_arguments():
     assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, None, None, None, 0, 1, 32, 8, 8, 32, 0.2, _st()) != 0
     assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), _p(o), None, 0, 1, 32, 8, 8, 2, 0.2, _st()) != 0
     assert b"Cout" in lib.b2f_last_error()
+
+
+WGRAD_CASES = [
+    # B, Cx (channels of the activation tensor), Cin (of the convolution), H, W, Cout
+    (2, 128, 128, 14, 32, 128),
+    (1, 196, 196, 21, 40, 128),    # decoder conv 0 at level 3: two input-channel chunks (128 + 96 of 224), ragged tile edges
+    (1, 128, 128, 16, 32, 96),
+    (1, 96, 96, 9, 20, 64),        # M = 128 with one zero block
+    (1, 64, 64, 7, 16, 32),
+    (1, 354, 162, 7, 16, 128),     # coarsest flow decoder: the first 162 channels of a wider joined input
+    (3, 128, 128, 33, 50, 128),    # more tiles than fit one pass of the 3-stage ring, odd sizes
+]
+
+
+@pytest.mark.parametrize("B,Cx,Cin,H,W,Cout", WGRAD_CASES)
+def test_conv3x3_tc_backward_weights(B, Cx, Cin, H, W, Cout):
+    """SpatialConvolution:accGradParameters on the tensor cores (MN-major operands over the channel-minor (hi, lo)
+    tensors, wgrad_tc.cu) against a float64 correlation, accumulating into a gradient buffer that already holds
+    values."""
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((B, Cx, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    cxp, coutp32 = (Cx + 31) // 32 * 32, (Cout + 31) // 32 * 32
+    xd, gd = _dev(x), _dev(g)
+    xh, xl = torch.empty(B, H, W, cxp, device="cuda"), torch.empty(B, H, W, cxp, device="cuda")
+    gh, gl = torch.empty(B, H, W, coutp32, device="cuda"), torch.empty(B, H, W, coutp32, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(xd), 0, _p(xh), _p(xl), B, Cx, H, W, _st()))
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(gd), 0, _p(gh), _p(gl), B, Cout, H, W, _st()))
+    n = int(lib.b2f_conv3x3_packed_floats(Cin, Cout))
+    coutp = (Cout + 63) // 64 * 64
+    init = rng.standard_normal(n).astype(np.float32)
+    gw, gb = _dev(init), torch.full((Cout,), 0.5, device="cuda")
+    _lib.check(lib.b2f_conv3x3_tc_backward_weights(_p(xh), _p(xl), Cx, _p(gh), _p(gl), _p(gd), 0, _p(gw), _p(gb), B, Cin, H, W,
+                                                   Cout, _st()))
+    torch.cuda.synchronize()
+    xp = np.pad(x[:, :Cin].astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    want = np.zeros((Cin, 9, coutp))
+    g64 = g.astype(np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            want[:, ky * 3 + kx, :Cout] = np.einsum("bchw,bnhw->cn", xp[:, :, ky:ky + H, kx:kx + W], g64)
+    got = gw.cpu().numpy().reshape(Cin, 9, coutp).astype(np.float64) - init.reshape(Cin, 9, coutp)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 1e-4 * scale, np.abs(got - want).max() / scale
+    assert not got[:, :, Cout:].any()
+    wb = g64.sum(axis=(0, 2, 3)) + 0.5
+    assert np.abs(gb.cpu().numpy() - wb).max() < 1e-4 * np.abs(wb).max()
