@@ -341,7 +341,9 @@ class PWCNet:
                 planar output, the activations the backward plan reads (plan.dec, as the FFMA decoder records them)."""
                 xh, xl, cin = Jsplit[0], Jsplit[1], cj
                 chain = []
+                hl_in = []                         # (hi, lo, channels) of every tensor-core layer's INPUT
                 for i, cout in enumerate(DEC[:5]):
+                    hl_in.append((xh, xl, cin))
                     cv = self._convs["%s.l%d.%d" % (kind, l, i)]
                     assert cv.tc_cin == cin, (kind, l, i, cv.tc_cin, cin)
                     last = i == 4
@@ -361,6 +363,7 @@ class PWCNet:
                 conv("%s.l%d.5" % (kind, l), P(planar), 0, B, DEC[4], h, w, P(out), 0, slope=1.0, lane=lane)
                 if self.train_planar:
                     plan.dec[(kind, l)] = (chain, cin0)
+                    plan.dec_hl[(kind, l)] = hl_in
                 return out
 
             Jsplit = None
@@ -601,11 +604,14 @@ class PWCNet:
                         dgrad(name, P(G), 0, None, 0, P(gJl), jbs, not first, B, cin, h, w)
 
             def decoder_backward_tc(kind, G, first, chain, cin0):
-                """The same walk with the input gradients of layers 4..1 on tcgen05 (b2f_conv3x3_tc_backward_data: the
-                forward tensor-core kernel on transposed, mirrored (hi, lo) weights): the head's input gradient (FFMA, 32
-                channels) is split once into channel-minor (hi, lo), every tensor-core layer hands (hi, lo) to the next
-                and writes the planar copy the weight-gradient kernel reads; layer 0 (N = 196 .. 356 input channels: no
-                tensor-core shape) and all weight gradients stay on the FFMA kernels."""
+                """The same walk on tcgen05: the head's input gradient (FFMA, 32 channels) is split once into
+                channel-minor (hi, lo); the input gradients of layers 4..1 (b2f_conv3x3_tc_backward_data: the forward
+                tensor-core kernel on transposed, mirrored (hi, lo) weights) hand (hi, lo) to the next layer and write
+                the planar copy; the WEIGHT gradients of layers 4..0 (b2f_conv3x3_tc_backward_weights: MN-major operands,
+                contraction over pixels) read the (hi, lo) input activations the forward left behind and the (hi, lo)
+                output gradients.  Layer 0's input gradient (196 .. 356 channels: no tensor-core shape of that kernel)
+                and the 2-channel head stay on the FFMA kernels."""
+                hl_in = plan.dec_hl[(kind, l)]
                 name5 = "%s.l%d.5" % (kind, l)
                 wgrad(name5, P(chain[4]), 0, P(G), 0, B, DEC[4], h, w)
                 g4 = E(B, DEC[4], h, w)
@@ -614,21 +620,23 @@ class PWCNet:
                 ops.append((lib.b2f_nhwc_split_from_bdhw, (P(g4), 0, P(gh), P(gl), B, DEC[4], h, w)))
                 plan.keep += [g4, gh, gl]
                 Gp = g4
-                for i in range(4, 0, -1):
+                for i in range(4, -1, -1):
                     name = "%s.l%d.%d" % (kind, l, i)
                     cv = self._convs[name]
+                    xh, xl, cx = hl_in[i]
+                    ops.append((lib.b2f_conv3x3_tc_backward_weights,
+                                (P(xh), P(xl), cx, P(gh), P(gl), P(Gp), 0, P(cv.gw), P(cv.gb), B, cv.cin, h, w, cv.cout)))
+                    if i == 0:
+                        break
                     cin, cout = DEC[i - 1], DEC[i]
-                    wgrad(name, P(chain[i - 1]), 0, P(Gp), 0, B, cin, h, w)
                     gin = E(B, cin, h, w)
-                    nh = E(B, h, w, _round32(cin)) if i > 1 else None
-                    nl = E(B, h, w, _round32(cin)) if i > 1 else None
-                    plan.keep += [t_ for t_ in (gin, nh, nl) if t_ is not None]
+                    nh, nl = E(B, h, w, _round32(cin)), E(B, h, w, _round32(cin))
+                    plan.keep += [gin, nh, nl]
                     ops.append((lib.b2f_conv3x3_tc_backward_data,
-                                (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), P(chain[i - 1]), 0, P(nh) if nh is not None else None,
-                                 P(nl) if nl is not None else None, P(gin), 0, B, cout, h, w, cin, C.c_float(0.2))))
+                                (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), P(chain[i - 1]), 0, P(nh), P(nl), P(gin), 0, B, cout,
+                                 h, w, cin, C.c_float(0.2))))
                     gh, gl, Gp = nh, nl, gin
                 name0 = "%s.l%d.0" % (kind, l)
-                wgrad(name0, P(Jl), jbs, P(Gp), 0, B, cin0, h, w)
                 dgrad(name0, P(Gp), 0, None, 0, P(gJl), jbs, not first, B, cin0, h, w)
 
             # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
@@ -807,6 +815,7 @@ class _Plan:
         self.occ = {}
         self.fs = {}
         self.tmp, self.dec, self.skip_occ, self.skip_chain, self.iw = {}, {}, {}, {}, {}
+        self.dec_hl = {}
         self.bops = None
         self.bgraph = None
         self.graph = None

@@ -22,3 +22,21 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 10
 print("wgrad %d -> %d, B=%d, %dx%d: %.3f ms, %.1f TFLOP/s" % (Cin, Cout, B, H, W, ms, 2.0 * B * H * W * Cin * Cout * 9 / ms / 1e9))
+
+# the same layer on the tensor cores
+cxp = (Cin + 31) // 32 * 32
+xh, xl = torch.empty(B, H, W, cxp, device="cuda"), torch.empty(B, H, W, cxp, device="cuda")
+gh, gl = torch.empty(B, H, W, Cout, device="cuda"), torch.empty(B, H, W, Cout, device="cuda")
+_lib.check(lib.b2f_nhwc_split_from_bdhw(p(x), 0, p(xh), p(xl), B, Cin, H, W, None))
+_lib.check(lib.b2f_nhwc_split_from_bdhw(p(g), 0, p(gh), p(gl), B, Cout, H, W, None))
+run_tc = lambda: _lib.check(lib.b2f_conv3x3_tc_backward_weights(p(xh), p(xl), Cin, p(gh), p(gl), p(g), 0, p(gw), p(gb), B, Cin, H, W, Cout, None))
+for _ in range(3):
+    run_tc()
+torch.cuda.synchronize()
+a.record()
+for _ in range(10):
+    run_tc()
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 10
+print("wgrad_tc %d -> %d, B=%d, %dx%d: %.3f ms, %.1f TFLOP/s fp32-equivalent" % (Cin, Cout, B, H, W, ms, 2.0 * B * H * W * Cin * Cout * 9 / ms / 1e9))
