@@ -109,6 +109,9 @@ struct Args {
   // result's own sign
   const float* mask;
   int64_t mbs;
+  // output-channel slice of a wider convolution (the first decoder layer's input gradient has 196 .. 356 channels): the
+  // weight rows start at n0 (out_planar / bias / mask are passed already offset), and the planar result may be ADDED
+  int n0, accumulate;
 };
 
 // MASK: the input-gradient form (the activation derivative comes from a.mask); a compile-time switch -- as a run-time
@@ -164,8 +167,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       const int s = bs % NB, c = bs / 9, t = bs % 9;
       if (bs >= NB) mbar_wait(&b_empty[s], ((bs / NB) - 1) & 1);
       mbar_arrive_expect_tx(&b_full[s], 2 * cfg::B_BYTES);
-      tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, 0, t, 0, &b_full[s]);
-      tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, 0, t, 0, &b_full[s]);
+      tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, a.n0, t, 0, &b_full[s]);
+      tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, a.n0, t, 0, &b_full[s]);
     }
   } else if (warp == 2 && lane == 0) {
     // ---- TMA producer, input patches: its own thread, so that the patch of chunk c + 1 is requested the moment
@@ -244,9 +247,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     }
     if (a.out_planar && inside) {
       float* o = a.out_planar + (size_t)b * a.pbs + (size_t)y * a.W + x;
+      if (a.accumulate) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] = f[j];
+        for (int j = 0; j < 32; ++j)
+          if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] += f[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] = f[j];
+      }
     }
     if (a.store_split) {
       // two (hi, lo) staging buffers: group g reuses the buffer of group g - 2 once its stores have read it
@@ -352,7 +361,7 @@ __global__ void pack_tc_from_packed_kernel(const float* __restrict__ wp, float* 
 
 template <int N, bool MASK>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
-              int CinP, int CoutP, cudaStream_t st) {
+              int CinP, int CoutP, cudaStream_t st, int wrows_total = 0) {
   using cfg = Cfg<N>;
   Args a = a0;
   CUtensorMap txh, txl, twh, twl, toh, tol;
@@ -365,8 +374,9 @@ int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl
     if ((rc = make_tmap4(&txl, xl, dims, str, box, true))) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)CinP, (uint64_t)a.Cout, 9, 1};
-    const uint64_t str[3] = {(uint64_t)CinP, (uint64_t)CinP * a.Cout, (uint64_t)CinP * a.Cout * 9};
+    const uint64_t wrows = (uint64_t)(wrows_total > 0 ? wrows_total : a.Cout);
+    const uint64_t dims[4] = {(uint64_t)CinP, wrows, 9, 1};
+    const uint64_t str[3] = {(uint64_t)CinP, (uint64_t)CinP * wrows, (uint64_t)CinP * wrows * 9};
     const uint32_t box[4] = {32, (uint32_t)N, 1, 1};
     if ((rc = make_tmap4(&twh, wh, dims, str, box, true))) return rc;
     if ((rc = make_tmap4(&twl, wl, dims, str, box, true))) return rc;
@@ -455,13 +465,13 @@ extern "C" int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, 
 
 template <bool MASK>
 static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* out_hi, float* out_lo,
-                       const tc::Args& a, int B, int Cin, int Cout, cudaStream_t st, const char* who) {
+                       const tc::Args& a, int B, int Cin, int Cout, cudaStream_t st, const char* who, int wrows_total = 0) {
   const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
   switch (Cout) {
-    case 32: return tc::launch_tc<32, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
-    case 64: return tc::launch_tc<64, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
-    case 96: return tc::launch_tc<96, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
-    case 128: return tc::launch_tc<128, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st);
+    case 32: return tc::launch_tc<32, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
+    case 64: return tc::launch_tc<64, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
+    case 96: return tc::launch_tc<96, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
+    case 128: return tc::launch_tc<128, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
     default: return fail(B2F_EUNSUPPORTED, "%s: Cout = %d is not one of the decoder widths (32, 64, 96, 128)", who, Cout);
   }
 }
@@ -472,7 +482,7 @@ static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, 
 extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
                                             const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
                                             float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
-                                            int Cin, float leaky_slope, b2f_stream_t stream) {
+                                            int Cin, float leaky_slope, int accumulate, b2f_stream_t stream) {
   if (!g_hi || !g_lo || !wt_hi || !wt_lo) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: NULL gradient / weights");
   if ((gin_hi == nullptr) != (gin_lo == nullptr)) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: gin_hi and gin_lo go together");
   if (!gin_hi && !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: no output");
@@ -480,21 +490,36 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
   if (!aligned16(g_hi) || !aligned16(g_lo) || !aligned16(wt_hi) || !aligned16(wt_lo) || (gin_hi && (!aligned16(gin_hi) || !aligned16(gin_lo))))
     return fail(B2F_EALIGN, "conv3x3_tc_backward_data: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: cuTensorMapEncodeTiled not available");
+  const bool one = Cin == 32 || Cin == 64 || Cin == 96 || Cin == 128;
+  if (!one && (gin_hi || !gin_planar))
+    return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: Cin = %d runs as slices of <= 128 channels, planar output only", Cin);
+  if (accumulate && !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: accumulate needs the planar output");
   if (B == 0) return B2F_OK;
-  tc::Args a{};
-  a.trace = tc::g_tc_trace;
-  a.bias = nullptr;
-  a.out_planar = gin_planar;
-  a.pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
-  a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
-  a.Cout = Cin; a.H = H; a.W = W;               // N = its input channels
-  a.slope = act ? leaky_slope : 1.f;
-  a.store_split = gin_hi != nullptr;
-  a.mask = act;
-  a.mbs = act_batch_stride ? act_batch_stride : (int64_t)Cin * H * W;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return act ? tc_dispatch<true>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, Cin, st, "conv3x3_tc_backward_data")
-             : tc_dispatch<false>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, Cin, st, "conv3x3_tc_backward_data");
+  const int64_t pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
+  const int64_t mbs = act_batch_stride ? act_batch_stride : (int64_t)Cin * H * W;
+  // slices of the input channels: 128 at a time, the last one as the smallest decoder width that holds the rest
+  for (int n0 = 0; n0 < Cin; n0 += 128) {
+    const int rest = Cin - n0;
+    const int N = rest >= 128 ? 128 : (rest + 31) / 32 * 32;
+    tc::Args a{};
+    a.trace = tc::g_tc_trace;
+    a.bias = nullptr;
+    a.out_planar = gin_planar ? gin_planar + (size_t)n0 * H * W : nullptr;
+    a.pbs = pbs;
+    a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
+    a.Cout = std::min(N, rest); a.H = H; a.W = W; // valid channels of this slice (N = its width as a tensor-core shape)
+    a.slope = act ? leaky_slope : 1.f;
+    a.store_split = gin_hi != nullptr;
+    a.mask = act ? act + (size_t)n0 * H * W : nullptr;
+    a.mbs = mbs;
+    a.n0 = n0;
+    a.accumulate = accumulate;
+    const int rc = act ? tc_dispatch<true>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
+                       : tc_dispatch<false>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin);
+    if (rc) return rc;
+  }
+  return B2F_OK;
 }
 
 extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,

@@ -520,7 +520,7 @@ class PWCNet:
         for name, cv in self._convs.items():
             ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
             kind, _lvl, idx = name.split(".")
-            if self.train_planar and kind in ("occ", "flow", "bflow") and idx in ("1", "2", "3", "4"):
+            if self.train_planar and kind in ("occ", "flow", "bflow") and idx in ("0", "1", "2", "3", "4"):
                 if cv.tct_h is None:
                     n_t = 9 * cv.cin * _round32(cv.cout)
                     cv.tct_h = torch.empty(n_t, device=dev, dtype=torch.float32)
@@ -609,8 +609,8 @@ class PWCNet:
                 tensor-core kernel on transposed, mirrored (hi, lo) weights) hand (hi, lo) to the next layer and write
                 the planar copy; the WEIGHT gradients of layers 4..0 (b2f_conv3x3_tc_backward_weights: MN-major operands,
                 contraction over pixels) read the (hi, lo) input activations the forward left behind and the (hi, lo)
-                output gradients.  Layer 0's input gradient (196 .. 356 channels: no tensor-core shape of that kernel)
-                and the 2-channel head stay on the FFMA kernels."""
+                output gradients.  Layer 0's input gradient (162 .. 356 channels) runs as slices of <= 128 channels; only
+                the 2-channel head stays on the FFMA kernels."""
                 hl_in = plan.dec_hl[(kind, l)]
                 name5 = "%s.l%d.5" % (kind, l)
                 wgrad(name5, P(chain[4]), 0, P(G), 0, B, DEC[4], h, w)
@@ -634,10 +634,14 @@ class PWCNet:
                     plan.keep += [gin, nh, nl]
                     ops.append((lib.b2f_conv3x3_tc_backward_data,
                                 (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), P(chain[i - 1]), 0, P(nh), P(nl), P(gin), 0, B, cout,
-                                 h, w, cin, C.c_float(0.2))))
+                                 h, w, cin, C.c_float(0.2), 0)))
                     gh, gl, Gp = nh, nl, gin
-                name0 = "%s.l%d.0" % (kind, l)
-                dgrad(name0, P(Gp), 0, None, 0, P(gJl), jbs, not first, B, cin0, h, w)
+                # layer 0: 162 .. 356 input channels as slices of <= 128, straight into (or added to) the joined gradient
+                cv0 = self._convs["%s.l%d.0" % (kind, l)]
+                assert cv0.cin == cin0
+                ops.append((lib.b2f_conv3x3_tc_backward_data,
+                            (P(gh), P(gl), P(cv0.tct_h), P(cv0.tct_l), None, 0, None, None, P(gJl), jbs, B, cv0.cout, h, w,
+                             cin0, C.c_float(1.0), 0 if first else 1)))
 
             # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
             g_occ = E(B, 2, h, w)
