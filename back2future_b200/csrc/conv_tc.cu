@@ -535,16 +535,28 @@ extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, cons
     return fail(B2F_EALIGN, "conv3x3_tc_forward: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: cuTensorMapEncodeTiled not available");
   if (B == 0) return B2F_OK;
-  const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
-  tc::Args a{};
-  a.trace = tc::g_tc_trace;
-  a.bias = bias;
-  a.out_planar = out_planar;
-  a.pbs = out_planar_batch_stride ? out_planar_batch_stride : (int64_t)Cout * H * W;
-  a.nchunk = CinP / 32;
-  a.Cout = Cout; a.H = H; a.W = W;
-  a.slope = leaky_slope;
-  a.store_split = out_hi != nullptr;
-  return tc_dispatch<false>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, Cout, reinterpret_cast<cudaStream_t>(stream),
-                            "conv3x3_tc_forward");
+  const bool one = Cout <= 128;
+  if (!one && out_hi) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: Cout = %d runs as slices of <= 128 channels, planar output only", Cout);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int CinP = (Cin + 31) / 32 * 32;
+  const int64_t pbs = out_planar_batch_stride ? out_planar_batch_stride : (int64_t)Cout * H * W;
+  // output-channel slices: 128 at a time, the last one as the smallest decoder width that holds the rest (a 16-channel
+  // pyramid layer is one 32-wide slice with 16 valid channels)
+  for (int n0 = 0; n0 < Cout; n0 += 128) {
+    const int rest = Cout - n0;
+    const int N = rest >= 128 ? 128 : (rest + 31) / 32 * 32;
+    tc::Args a{};
+    a.trace = tc::g_tc_trace;
+    a.bias = bias ? bias + n0 : nullptr;
+    a.out_planar = out_planar ? out_planar + (size_t)n0 * H * W : nullptr;
+    a.pbs = pbs;
+    a.nchunk = CinP / 32;
+    a.Cout = std::min(N, rest); a.H = H; a.W = W;
+    a.slope = leaky_slope;
+    a.store_split = out_hi != nullptr;
+    a.n0 = n0;
+    const int rc = tc_dispatch<false>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, N, st, "conv3x3_tc_forward", Cout);
+    if (rc) return rc;
+  }
+  return B2F_OK;
 }

@@ -58,6 +58,7 @@ struct Args {
   int nxb_total;      // 32-channel blocks of the activation tensor (CinP / 32)
   int ngb;            // 32-channel blocks of the gradient (Cout / 32)
   int tiles_x, tiles_y, ntiles, nsplit;
+  int co0;            // first output channel of this launch's slice (Cout > 128 runs as slices)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -121,8 +122,8 @@ conv3x3_wgrad_tc(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
       }
       uint8_t* gs = st + 2 * MB * XBLK;
       for (int c = 0; c < a.ngb; ++c) {
-        tma_load_4d(gs + c * GBLK, &tm_gh, c * 32, x0, y0, b, &full[s]);
-        tma_load_4d(gs + MB * GBLK + c * GBLK, &tm_gl, c * 32, x0, y0, b, &full[s]);
+        tma_load_4d(gs + c * GBLK, &tm_gh, a.co0 + c * 32, x0, y0, b, &full[s]);
+        tma_load_4d(gs + MB * GBLK + c * GBLK, &tm_gl, a.co0 + c * 32, x0, y0, b, &full[s]);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -165,7 +166,7 @@ conv3x3_wgrad_tc(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
   const int ci = chunk * 128 + 32 * warp + lane;
   if (my_tiles > 0) {
     for (int kx = 0; kx < 3; ++kx) {
-      float* dst = a.gw + ((size_t)ci * 9 + (ky * 3 + kx)) * a.CoutP;
+      float* dst = a.gw + ((size_t)ci * 9 + (ky * 3 + kx)) * a.CoutP + a.co0;
       for (int n0 = 0; n0 < N; n0 += 8) {
         uint32_t v[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -175,7 +176,7 @@ conv3x3_wgrad_tc(const __grid_constant__ CUtensorMap tm_xh, const __grid_constan
         if (ci < a.Cin) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (n0 + j < a.Cout) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
+            if (a.co0 + n0 + j < a.Cout) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
         }
       }
     }
@@ -227,7 +228,6 @@ extern "C" int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x
                                                float* gbias, int B, int Cin, int H, int W, int Cout, b2f_stream_t stream) {
   if (!x_hi || !x_lo || !g_hi || !g_lo || !gw_packed) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: NULL operand");
   if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || Cx < Cin) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: bad size");
-  if (Cout % 32 != 0 || Cout > 128) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_weights: Cout = %d is not one of 32, 64, 96, 128", Cout);
   if (gbias && !g_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: the bias gradient needs the planar output gradient");
   if (!aligned16(x_hi) || !aligned16(x_lo) || !aligned16(g_hi) || !aligned16(g_lo)) return fail(B2F_EALIGN, "conv3x3_tc_backward_weights: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_weights: cuTensorMapEncodeTiled not available");
@@ -250,18 +250,6 @@ extern "C" int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x
     if ((rc = wtc::make_tmap4_atom32(&tgh, g_hi, dims, str, box))) return rc;
     if ((rc = wtc::make_tmap4_atom32(&tgl, g_lo, dims, str, box))) return rc;
   }
-  wtc::Args a{};
-  a.gw = gw_packed;
-  a.Cin = Cin; a.Cout = Cout; a.CoutP = (Cout + 63) / 64 * 64;
-  a.H = H; a.W = W; a.B = B;
-  a.nxb_total = (Cin + 31) / 32;          // blocks that hold channels of THIS convolution (the tensor may be wider)
-  a.ngb = Cout / 32;
-  a.tiles_x = (W + wtc::TW - 1) / wtc::TW;
-  a.tiles_y = (H + wtc::TH - 1) / wtc::TH;
-  a.ntiles = B * a.tiles_x * a.tiles_y;
-  const int nchunk = (a.nxb_total + wtc::MB - 1) / wtc::MB;
-  // one CTA per SM (it owns up to all 512 TMEM columns); at least 8 tiles per CTA so the 3-stage ring has something to overlap
-  a.nsplit = std::max(1, std::min(num_sms() / (3 * nchunk), std::max(1, a.ntiles / 8)));
   static thread_local int attr_dev = -1;
   int dev = 0;
   B2F_CUDA_TRY(cudaGetDevice(&dev));
@@ -269,9 +257,25 @@ extern "C" int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x
     B2F_CUDA_TRY(cudaFuncSetAttribute(wtc::conv3x3_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::SMEM_BYTES));
     attr_dev = dev;
   }
-  dim3 grid(3 * nchunk, a.nsplit);
-  wtc::conv3x3_wgrad_tc<<<grid, wtc::THREADS, wtc::SMEM_BYTES, st>>>(txh, txl, tgh, tgl, a);
-  B2F_CHECK_LAUNCH("conv3x3_wgrad_tc");
+  // output-channel slices of <= 128 (the accumulators of three taps are 3 N TMEM columns)
+  for (int co0 = 0; co0 < Cout; co0 += 128) {
+    wtc::Args a{};
+    a.gw = gw_packed;
+    a.Cin = Cin; a.Cout = Cout; a.CoutP = (Cout + 63) / 64 * 64;
+    a.H = H; a.W = W; a.B = B;
+    a.nxb_total = (Cin + 31) / 32;          // blocks that hold channels of THIS convolution (the tensor may be wider)
+    a.ngb = (std::min(128, Cout - co0) + 31) / 32;
+    a.co0 = co0;
+    a.tiles_x = (W + wtc::TW - 1) / wtc::TW;
+    a.tiles_y = (H + wtc::TH - 1) / wtc::TH;
+    a.ntiles = B * a.tiles_x * a.tiles_y;
+    const int nchunk = (a.nxb_total + wtc::MB - 1) / wtc::MB;
+    // one CTA per SM (it owns up to all 512 TMEM columns); at least 8 tiles per CTA so the 3-stage ring has something to overlap
+    a.nsplit = std::max(1, std::min(num_sms() / (3 * nchunk), std::max(1, a.ntiles / 8)));
+    dim3 grid(3 * nchunk, a.nsplit);
+    wtc::conv3x3_wgrad_tc<<<grid, wtc::THREADS, wtc::SMEM_BYTES, st>>>(txh, txl, tgh, tgl, a);
+    B2F_CHECK_LAUNCH("conv3x3_wgrad_tc");
+  }
   if (gbias) {
     const int64_t gbs = g_planar_batch_stride ? g_planar_batch_stride : (int64_t)Cout * H * W;
     wtc::bias_grad_kernel<<<dim3(Cout, B), 256, 0, st>>>(g_planar, gbs, gbias, (int64_t)H * W);

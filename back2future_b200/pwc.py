@@ -31,6 +31,7 @@ from . import _lib
 
 FEAT = (3, 16, 32, 64, 96, 128, 192)      # featMaps (pwc.lua:89, d = 16)
 DEC = (128, 128, 96, 64, 32, 2)           # decoder(nChannels) widths (pwc.lua:76-85)
+TC_FEAT_MIN = 64                          # feature-pyramid layers with at least this many channels run on tcgen05
 
 
 class Opt:
@@ -190,7 +191,8 @@ class PWCNet:
                 cv.b.copy_(torch.from_numpy(b), non_blocking=False)        # cudaMemcpy H2D
                 cv.gw = cv.gb = cv.wt = None
                 cv.tc_h = cv.tc_l = cv.tct_h = cv.tct_l = None
-                if self.tensor_cores and kind in ("occ", "flow", "bflow") and cout in (32, 64, 96, 128):
+                if self.tensor_cores and ((kind in ("occ", "flow", "bflow") and cout in (32, 64, 96, 128)) or
+                                          (kind == "feat" and idx == "1" and cout >= TC_FEAT_MIN)):
                     # [9][Cout][Cin_p] hi / lo for the tensor-core path.  The coarsest level's flow decoder reads the
                     # first 162 channels of the occlusion decoder's wider joined input: zero weights for the rest.
                     wtc = w
@@ -272,6 +274,13 @@ class PWCNet:
                 ops.append((1, lib.b2f_avgpool2x2_forward, (P(ds[k - 1]), P(ds[k]), 2 * B, 3, H >> (k - 1), W >> (k - 1))))
         plan.ds = ds
 
+        # -- training with the tensor-core forward: the (hi, lo) weights follow the flat parameters ---------
+        if self.train_planar:
+            for name, cv in self._convs.items():
+                if cv.tc_h is not None:
+                    ops.append((0, lib.b2f_conv3x3_tc_pack_from_packed,
+                                (P(cv.w), P(cv.tc_h), P(cv.tc_l), cv.cout, cv.cin, cv.tc_cin, 0)))
+
         # -- siamese feature pyramid on the 3B batch (slots: past, future, reference) -----------------------------
         feats = {}
         slot_of_frame = (0, 2, 1)     # frame index 0, 1, 2 (past, ref, future) -> slot
@@ -287,22 +296,30 @@ class PWCNet:
             else:
                 conv("feat.l%d.0" % l, P(prev), 0, 3 * B, c_in, 2 * h, 2 * w, P(tmp), 0)
             name = "feat.l%d.1" % l
-            conv(name, P(tmp), 0, 2 * B, c_out, h, w, P(feats[l]), 0)
-            if l >= l_st:     # the reference frame's features also go into the joined decoder input
-                conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0, sl(J[l], 0, 2 * nd), J[l].stride(0))
+            if self.tensor_cores and c_out >= TC_FEAT_MIN:
+                # the stride-1 half of the convUnit on tcgen05 (levels 4-7; at 16 / 32 channels the M = 128 tensor-core
+                # tiles are mostly padding and the FFMA2 kernel is as fast): one split of the stride-2 layer's output, one call for the
+                # three frames (192 channels: two output-channel slices; 16: one 32-wide slice), planar output
+                cv = self._convs[name]
+                th, tl = E(3 * B, h, w, _round32(c_out)), E(3 * B, h, w, _round32(c_out))
+                plan.keep += [th, tl]
+                plan.tmp_hl[l] = (th, tl)
+                ops.append((0, lib.b2f_nhwc_split_from_bdhw, (P(tmp), 0, P(th), P(tl), 3 * B, c_out, h, w)))
+                ops.append((0, lib.b2f_conv3x3_tc_forward, (P(th), P(tl), P(cv.tc_h), P(cv.tc_l), P(cv.b), None, None,
+                                                            P(feats[l]), 0, 3 * B, c_out, h, w, c_out, C.c_float(0.2))))
+                if l >= l_st:     # the reference frame's features also go into the joined decoder input
+                    ops.append((0, lib.b2f_copy2d_async, (sl(J[l], 0, 2 * nd), J[l].stride(0), sl(feats[l], 2 * B),
+                                                          c_out * h * w, c_out * h * w, B)))
             else:
-                conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0)
+                conv(name, P(tmp), 0, 2 * B, c_out, h, w, P(feats[l]), 0)
+                if l >= l_st:     # the reference frame's features also go into the joined decoder input
+                    conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0, sl(J[l], 0, 2 * nd), J[l].stride(0))
+                else:
+                    conv(name, sl(tmp, 2 * B), 0, B, c_out, h, w, sl(feats[l], 2 * B), 0)
             plan.keep.append(tmp)
             plan.tmp[l] = tmp
             prev = feats[l]
         plan.feats = feats
-
-        # -- training with the tensor-core forward: the (hi, lo) decoder weights follow the flat parameters ---------
-        if self.train_planar:
-            for name, cv in self._convs.items():
-                if cv.tc_h is not None:
-                    ops.append((0, lib.b2f_conv3x3_tc_pack_from_packed,
-                                (P(cv.w), P(cv.tc_h), P(cv.tc_l), cv.cout, cv.cin, cv.tc_cin, 0)))
 
         # -- levels, coarse to fine ---------------------------------------------------------------------------
         outs = {}
@@ -520,7 +537,8 @@ class PWCNet:
         for name, cv in self._convs.items():
             ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
             kind, _lvl, idx = name.split(".")
-            if self.train_planar and kind in ("occ", "flow", "bflow") and idx in ("0", "1", "2", "3", "4"):
+            if self.train_planar and ((kind in ("occ", "flow", "bflow") and idx in ("0", "1", "2", "3", "4")) or
+                                      (kind == "feat" and idx == "1" and cv.cout >= TC_FEAT_MIN)):
                 if cv.tct_h is None:
                     n_t = 9 * cv.cin * _round32(cv.cout)
                     cv.tct_h = torch.empty(n_t, device=dev, dtype=torch.float32)
@@ -677,10 +695,23 @@ class PWCNet:
             c_in, c_out = FEAT[l - 2], FEAT[l - 1]
             gf, f, tmp = g_feats[l], plan.feats[l], plan.tmp[l]
             ops.append((lib.b2f_leaky_relu_backward, (P(gf), gf.numel(), P(f), f.numel(), gf.numel(), 1, C.c_float(0.2))))
-            wgrad("feat.l%d.1" % l, P(tmp), 0, P(gf), 0, 3 * B, c_out, h, w)
-            g_tmp = E(*tmp.shape)
-            plan.keep.append(g_tmp)
-            dgrad("feat.l%d.1" % l, P(gf), 0, P(tmp), 0, P(g_tmp), 0, False, 3 * B, c_out, h, w)
+            if self.train_planar and c_out >= TC_FEAT_MIN:
+                cv1 = self._convs["feat.l%d.1" % l]
+                th, tl = plan.tmp_hl[l]
+                gfh, gfl = E(3 * B, h, w, _round32(c_out)), E(3 * B, h, w, _round32(c_out))
+                g_tmp = E(*tmp.shape)
+                plan.keep += [gfh, gfl, g_tmp]
+                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(gf), 0, P(gfh), P(gfl), 3 * B, c_out, h, w)))
+                ops.append((lib.b2f_conv3x3_tc_backward_weights,
+                            (P(th), P(tl), c_out, P(gfh), P(gfl), P(gf), 0, P(cv1.gw), P(cv1.gb), 3 * B, c_out, h, w, c_out)))
+                ops.append((lib.b2f_conv3x3_tc_backward_data,
+                            (P(gfh), P(gfl), P(cv1.tct_h), P(cv1.tct_l), P(tmp), 0, None, None, P(g_tmp), 0, 3 * B, c_out, h, w,
+                             c_out, C.c_float(0.2), 0)))
+            else:
+                wgrad("feat.l%d.1" % l, P(tmp), 0, P(gf), 0, 3 * B, c_out, h, w)
+                g_tmp = E(*tmp.shape)
+                plan.keep.append(g_tmp)
+                dgrad("feat.l%d.1" % l, P(gf), 0, P(tmp), 0, P(g_tmp), 0, False, 3 * B, c_out, h, w)
             name = "feat.l%d.0" % l
             if l == 2:
                 for fr, slot in enumerate((0, 2, 1)):
@@ -820,6 +851,7 @@ class _Plan:
         self.fs = {}
         self.tmp, self.dec, self.skip_occ, self.skip_chain, self.iw = {}, {}, {}, {}, {}
         self.dec_hl = {}
+        self.tmp_hl = {}
         self.bops = None
         self.bgraph = None
         self.graph = None

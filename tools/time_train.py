@@ -30,6 +30,7 @@ ap.add_argument("--H", type=int, default=320)
 ap.add_argument("--W", type=int, default=640)
 ap.add_argument("--past-flow", action="store_true")
 ap.add_argument("--tc", action="store_true", help="tensor-core forward + input gradients (train_planar)")
+ap.add_argument("--detail", action="store_true", help="list every FFMA convolution call of the backward plan")
 a = ap.parse_args()
 lib = _lib.load()
 net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), tensor_cores=a.tc, train_planar=a.tc)
@@ -38,9 +39,26 @@ out = net.forward(x, graph=False)
 net.backward(x, [torch.randn_like(t) for t in out])
 torch.cuda.synchronize()
 p = net.plan(a.B, a.H, a.W)
+name_of = {id(getattr(lib, n)): n for n in _lib.SIGNATURES}
+st0 = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 fwd = time_it(lambda: p.launch())
 bwd = time_it(lambda: p.launch_backward())
 print("forward %.3f ms, backward %.3f ms (eager)" % (fwd, bwd))
+if a.detail:
+    fagg = {}
+    for op in p.ops:
+        if op[0] == "fork":
+            continue
+        lane, fn, args = op
+        ms = time_it(lambda: fn(*args, st0), iters=3, warm=1)
+        k = name_of.get(id(fn), "?")
+        if k == "b2f_conv3x3_forward":
+            ints = [v for v in args if isinstance(v, int)]
+            print("   fwd %-40s %8.3f ms  ints %s" % (k, ms, ints[-7:]))
+        t, n = fagg.get(k, (0.0, 0))
+        fagg[k] = (t + ms, n + 1)
+    for k, (t, n) in sorted(fagg.items(), key=lambda kv: -kv[1][0]):
+        print("fwd %-42s %3d calls %8.3f ms" % (k, n, t))
 name = {id(getattr(lib, n)): n for n in _lib.SIGNATURES}
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 agg = {}
@@ -53,6 +71,9 @@ for fn, args in p.bops:
         k += " (stride %d)" % args[13]
     t, n = agg.get(k, (0.0, 0))
     agg[k] = (t + ms, n + 1)
+    if a.detail and k.startswith(("b2f_conv3x3_backward_weights", "b2f_conv3x3_backward_data")):
+        ints = [v for v in args if isinstance(v, int)]
+        print("   %-44s %8.3f ms  ints %s" % (k, ms, ints[-7:]))
 tot = sum(t for t, _ in agg.values())
 for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print("%-46s %3d calls %8.3f ms %5.1f%%" % (k, n, t, 100 * t / tot))
