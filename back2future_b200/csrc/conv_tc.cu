@@ -109,14 +109,19 @@ struct Args {
   // result's own sign
   const float* mask;
   int64_t mbs;
+  // the same derivative from the channel-minor HI half of that layer's output, (B, H, W, mcp): hi keeps the sign of every
+  // normal float, a thread's 32 channels are one 128-byte line instead of 32 strided words (MASK == 2)
+  const float* mask_hi;
+  int mcp;
   // output-channel slice of a wider convolution (the first decoder layer's input gradient has 196 .. 356 channels): the
   // weight rows start at n0 (out_planar / bias / mask are passed already offset), and the planar result may be ADDED
   int n0, accumulate;
 };
 
-// MASK: the input-gradient form (the activation derivative comes from a.mask); a compile-time switch -- as a run-time
-// branch inside the unrolled epilogue it cost the forward 10 % (0.307 -> 0.341 ms on the level-3 128 -> 128 layer)
-template <int N, bool MASK>
+// MASK: the input-gradient form (the activation derivative comes from a.mask (1, planar) or a.mask_hi (2, channel-minor));
+// a compile-time switch -- as a run-time branch inside the unrolled epilogue it cost the forward 10 % (0.307 -> 0.341 ms
+// on the level-3 128 -> 128 layer)
+template <int N, int MASK>
 __global__ void __launch_bounds__(THREADS, (AS == 1 ? 2 : 1))
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
@@ -231,13 +236,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
 #pragma unroll 1
   for (int g = 0; g < cfg::NG; ++g) {
     uint32_t v[32];
+    float mk2[MASK == 2 ? 32 : 1];
+    if (MASK == 2) {      // requested before the accumulator read so that the two latencies overlap
+      const float4* mp = reinterpret_cast<const float4*>(a.mask_hi + (((size_t)b * a.H + (inside ? y : 0)) * a.W + (inside ? x : 0)) * a.mcp +
+                                                         a.n0 + 32 * g);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t4 = inside ? __ldg(mp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+        mk2[4 * q] = t4.x; mk2[4 * q + 1] = t4.y; mk2[4 * q + 2] = t4.z; mk2[4 * q + 3] = t4.w;
+      }
+    }
     tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(32 * g), v);
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int n = 32 * g + j;
       float t = __uint_as_float(v[j]) + ((a.bias && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
-      if (MASK) {
+      if (MASK == 2) {
+        t = mk2[j] > 0.f ? t : t * a.slope;
+      } else if (MASK == 1) {
         const float mk = (inside && n < a.Cout) ? __ldg(a.mask + (size_t)b * a.mbs + ((size_t)n * a.H + y) * a.W + x) : 1.f;
         t = mk > 0.f ? t : t * a.slope;
       } else {
@@ -248,9 +265,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     if (a.out_planar && inside) {
       float* o = a.out_planar + (size_t)b * a.pbs + (size_t)y * a.W + x;
       if (a.accumulate) {
+        // one writer per element and call: a reduction without a return value (RED) instead of load + add + store,
+        // so that the thread does not wait for 32 strided loads
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] += f[j];
+          if (32 * g + j < a.Cout) atomicAdd(o + (size_t)(32 * g + j) * a.H * a.W, f[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -359,7 +378,7 @@ __global__ void pack_tc_from_packed_kernel(const float* __restrict__ wp, float* 
   }
 }
 
-template <int N, bool MASK>
+template <int N, int MASK>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
               int CinP, int CoutP, cudaStream_t st, int wrows_total = 0) {
   using cfg = Cfg<N>;
@@ -463,7 +482,7 @@ extern "C" int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, 
   return B2F_OK;
 }
 
-template <bool MASK>
+template <int MASK>
 static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* out_hi, float* out_lo,
                        const tc::Args& a, int B, int Cin, int Cout, cudaStream_t st, const char* who, int wrows_total = 0) {
   const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
@@ -480,7 +499,7 @@ static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, 
 // weights (b2f_conv3x3_tc_pack_from_packed, transpose = 1) over the channel-minor (hi, lo) OUTPUT gradient, with the
 // LeakyReLU derivative of the layer below taken from its planar forward output `act`.
 extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
-                                            const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
+                                            const float* act, int64_t act_batch_stride, const float* act_hi, float* gin_hi, float* gin_lo,
                                             float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
                                             int Cin, float leaky_slope, int accumulate, b2f_stream_t stream) {
   if (!g_hi || !g_lo || !wt_hi || !wt_lo) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: NULL gradient / weights");
@@ -494,6 +513,8 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
   if (!one && (gin_hi || !gin_planar))
     return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: Cin = %d runs as slices of <= 128 channels, planar output only", Cin);
   if (accumulate && !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: accumulate needs the planar output");
+  if (act && act_hi) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: act (planar) and act_hi (channel-minor) are alternatives");
+  if (act_hi && !aligned16(act_hi)) return fail(B2F_EALIGN, "conv3x3_tc_backward_data: act_hi must be 16-byte aligned");
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
@@ -509,14 +530,17 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
     a.pbs = pbs;
     a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
     a.Cout = std::min(N, rest); a.H = H; a.W = W; // valid channels of this slice (N = its width as a tensor-core shape)
-    a.slope = act ? leaky_slope : 1.f;
+    a.slope = (act || act_hi) ? leaky_slope : 1.f;
     a.store_split = gin_hi != nullptr;
     a.mask = act ? act + (size_t)n0 * H * W : nullptr;
     a.mbs = mbs;
+    a.mask_hi = act_hi;
+    a.mcp = (Cin + 31) / 32 * 32;
     a.n0 = n0;
     a.accumulate = accumulate;
-    const int rc = act ? tc_dispatch<true>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
-                       : tc_dispatch<false>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin);
+    const int rc = act_hi ? tc_dispatch<2>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
+                   : act  ? tc_dispatch<1>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
+                          : tc_dispatch<0>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin);
     if (rc) return rc;
   }
   return B2F_OK;
@@ -555,7 +579,7 @@ extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, cons
     a.slope = leaky_slope;
     a.store_split = out_hi != nullptr;
     a.n0 = n0;
-    const int rc = tc_dispatch<false>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, N, st, "conv3x3_tc_forward", Cout);
+    const int rc = tc_dispatch<0>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, N, st, "conv3x3_tc_forward", Cout);
     if (rc) return rc;
   }
   return B2F_OK;

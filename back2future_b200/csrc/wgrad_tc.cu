@@ -204,6 +204,28 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   }
 }
 
+// The same sum from the channel-minor (hi, lo) output gradient, (pixels, Cp): a warp reads one 128-byte line of 32
+// channels per pixel, eight pixels per block and trip
+__global__ void __launch_bounds__(256) bias_grad_nhwc_kernel(const float* __restrict__ gh, const float* __restrict__ gl,
+                                                            float* __restrict__ gb, int64_t npix, int Cp, int Cout) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = 32 * blockIdx.x + lane;
+  float s = 0.f;
+  for (int64_t p = (int64_t)blockIdx.y * 8 + w; p < npix; p += (int64_t)gridDim.y * 8) {
+    const size_t o = (size_t)p * Cp + c;
+    s += __ldg(gh + o) + __ldg(gl + o);
+  }
+  __shared__ float part[8][32];
+  part[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < Cout) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    atomicAdd(gb + c, t);
+  }
+}
+
 int make_tmap4_atom32(CUtensorMap* tm, const float* base, const uint64_t dims[4], const uint64_t strides_elems[3], const uint32_t box[4]) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(B2F_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
@@ -228,7 +250,6 @@ extern "C" int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x
                                                float* gbias, int B, int Cin, int H, int W, int Cout, b2f_stream_t stream) {
   if (!x_hi || !x_lo || !g_hi || !g_lo || !gw_packed) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: NULL operand");
   if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || Cx < Cin) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: bad size");
-  if (gbias && !g_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_weights: the bias gradient needs the planar output gradient");
   if (!aligned16(x_hi) || !aligned16(x_lo) || !aligned16(g_hi) || !aligned16(g_lo)) return fail(B2F_EALIGN, "conv3x3_tc_backward_weights: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_weights: cuTensorMapEncodeTiled not available");
   if (B == 0) return B2F_OK;
@@ -276,7 +297,12 @@ extern "C" int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x
     wtc::conv3x3_wgrad_tc<<<grid, wtc::THREADS, wtc::SMEM_BYTES, st>>>(txh, txl, tgh, tgl, a);
     B2F_CHECK_LAUNCH("conv3x3_wgrad_tc");
   }
-  if (gbias) {
+  if (gbias && !g_planar) {
+    const int64_t npix = (int64_t)B * H * W;
+    const int ny = (int)std::max<int64_t>(1, std::min<int64_t>((npix + 63) / 64, 4 * num_sms()));
+    wtc::bias_grad_nhwc_kernel<<<dim3(CoutP32 / 32, ny), 256, 0, st>>>(g_hi, g_lo, gbias, npix, CoutP32, Cout);
+    B2F_CHECK_LAUNCH("bias_grad_nhwc_kernel");
+  } else if (gbias) {
     const int64_t gbs = g_planar_batch_stride ? g_planar_batch_stride : (int64_t)Cout * H * W;
     wtc::bias_grad_kernel<<<dim3(Cout, B), 256, 0, st>>>(g_planar, gbs, gbias, (int64_t)H * W);
     B2F_CHECK_LAUNCH("bias_grad_kernel");

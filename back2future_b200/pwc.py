@@ -643,23 +643,25 @@ class PWCNet:
                     cv = self._convs[name]
                     xh, xl, cx = hl_in[i]
                     ops.append((lib.b2f_conv3x3_tc_backward_weights,
-                                (P(xh), P(xl), cx, P(gh), P(gl), P(Gp), 0, P(cv.gw), P(cv.gb), B, cv.cin, h, w, cv.cout)))
+                                (P(xh), P(xl), cx, P(gh), P(gl), P(Gp) if Gp is not None else None, 0, P(cv.gw), P(cv.gb), B,
+                                 cv.cin, h, w, cv.cout)))
                     if i == 0:
                         break
                     cin, cout = DEC[i - 1], DEC[i]
-                    gin = E(B, cin, h, w)
                     nh, nl = E(B, h, w, _round32(cin)), E(B, h, w, _round32(cin))
-                    plan.keep += [gin, nh, nl]
+                    plan.keep += [nh, nl]
+                    # the LeakyReLU derivative from the HI half of layer i's channel-minor input (= layer i - 1's output);
+                    # no planar copy of the gradient: the next weight-gradient call sums the bias gradient from (hi, lo)
                     ops.append((lib.b2f_conv3x3_tc_backward_data,
-                                (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), P(chain[i - 1]), 0, P(nh), P(nl), P(gin), 0, B, cout,
+                                (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), None, 0, P(xh), P(nh), P(nl), None, 0, B, cout,
                                  h, w, cin, C.c_float(0.2), 0)))
-                    gh, gl, Gp = nh, nl, gin
+                    gh, gl, Gp = nh, nl, None
                 # layer 0: 162 .. 356 input channels as slices of <= 128, straight into (or added to) the joined gradient
                 cv0 = self._convs["%s.l%d.0" % (kind, l)]
                 assert cv0.cin == cin0
                 ops.append((lib.b2f_conv3x3_tc_backward_data,
-                            (P(gh), P(gl), P(cv0.tct_h), P(cv0.tct_l), None, 0, None, None, P(gJl), jbs, B, cv0.cout, h, w,
-                             cin0, C.c_float(1.0), 0 if first else 1)))
+                            (P(gh), P(gl), P(cv0.tct_h), P(cv0.tct_l), None, 0, None, None, None, P(gJl), jbs, B, cv0.cout, h,
+                             w, cin0, C.c_float(1.0), 0 if first else 1)))
 
             # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
             g_occ = E(B, 2, h, w)
@@ -705,8 +707,8 @@ class PWCNet:
                 ops.append((lib.b2f_conv3x3_tc_backward_weights,
                             (P(th), P(tl), c_out, P(gfh), P(gfl), P(gf), 0, P(cv1.gw), P(cv1.gb), 3 * B, c_out, h, w, c_out)))
                 ops.append((lib.b2f_conv3x3_tc_backward_data,
-                            (P(gfh), P(gfl), P(cv1.tct_h), P(cv1.tct_l), P(tmp), 0, None, None, P(g_tmp), 0, 3 * B, c_out, h, w,
-                             c_out, C.c_float(0.2), 0)))
+                            (P(gfh), P(gfl), P(cv1.tct_h), P(cv1.tct_l), None, 0, P(th), None, None, P(g_tmp), 0, 3 * B, c_out,
+                             h, w, c_out, C.c_float(0.2), 0)))
             else:
                 wgrad("feat.l%d.1" % l, P(tmp), 0, P(gf), 0, 3 * B, c_out, h, w)
                 g_tmp = E(*tmp.shape)

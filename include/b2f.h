@@ -269,21 +269,26 @@ B2F_API int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const f
 /* SpatialConvolution:updateGradInput of the same layer on the tensor cores (train.lua:480 model:backward): the forward
  * kernel on the transposed, mirrored weights (b2f_conv3x3_tc_pack_from_packed with transpose = 1: N = Cin rows, K = Cout)
  * over the channel-minor (hi, lo) gradient of the layer's OUTPUT; `act` = planar forward output of the layer BELOW
- * (B, Cin, H, W): the result is multiplied by 1 where act > 0 and by leaky_slope elsewhere (NULL: no factor).  Outputs
+ * (B, Cin, H, W): the result is multiplied by 1 where act > 0 and by leaky_slope elsewhere (NULL: no factor).  `act_hi`
+ * is the alternative to `act` (at most one of the two): the HI half of the same activation's channel-minor split,
+ * (B, H, W, Cin rounded up to 32) -- hi = x & 0xFFFFE000 has the sign of every normal float, and a pixel's channels
+ * are one 128-byte line per 32 instead of 32 strided words.  Outputs
  * as b2f_conv3x3_tc_forward: (hi, lo) channel-minor for the next tensor-core input gradient and / or planar fp32 for
  * the weight-gradient kernel.  Cin in {32, 64, 96, 128}; any other Cin (the first decoder layer: 162 .. 356) runs as
  * slices of <= 128 input channels with the planar output only.  accumulate != 0: the planar result is ADDED to
  * gin_planar (nngraph's gradient accumulation at the joined decoder input).                                            */
 B2F_API int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
-                                         const float* act, int64_t act_batch_stride, float* gin_hi, float* gin_lo,
-                                         float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int H, int W,
+                                         const float* act, int64_t act_batch_stride, const float* act_hi, float* gin_hi,
+                                         float* gin_lo, float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout,
+                                         int H, int W,
                                          int Cin, float leaky_slope, int accumulate, b2f_stream_t stream);
 /* SpatialConvolution:accGradParameters of the same layer on the tensor cores: gw_packed += d loss / d weight from the
  * channel-minor (hi, lo) INPUT activation (x_hi / x_lo, a (B, H, W, Cx rounded up to 32) tensor whose first Cin channels
  * are this convolution's input -- the coarsest flow decoder reads the first 162 channels of a wider joined input) and
  * the channel-minor (hi, lo) OUTPUT gradient: MN-major operands, the contraction runs over the pixels and a tap is a
  * descriptor offset (wgrad_tc.cu).  gbias (may be NULL) += d loss / d bias, summed from the PLANAR output gradient
- * g_planar (B, Cout, H, W; batch stride 0 = dense).  Cout in {32, 64, 96, 128}; any Cin.                              */
+ * g_planar (B, Cout, H, W; batch stride 0 = dense) or, when g_planar is NULL, from g_hi + g_lo.  Any Cin, any Cout
+ * (output-channel slices of <= 128).                                                                                   */
 B2F_API int b2f_conv3x3_tc_backward_weights(const float* x_hi, const float* x_lo, int Cx, const float* g_hi, const float* g_lo,
                                             const float* g_planar, int64_t g_planar_batch_stride, float* gw_packed,
                                             float* gbias, int B, int Cin, int H, int W, int Cout, b2f_stream_t stream);

@@ -148,3 +148,98 @@ def test_conv3x3_tc_backward_weights(B, Cx, Cin, H, W, Cout):
     assert not got[:, :, Cout:].any()
     wb = g64.sum(axis=(0, 2, 3)) + 0.5
     assert np.abs(gb.cpu().numpy() - wb).max() < 1e-4 * np.abs(wb).max()
+
+
+def test_conv3x3_tc_backward_weights_bias_from_split_gradient():
+    """g_planar == NULL: the bias gradient is summed from the channel-minor (hi, lo) output gradient."""
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    B, Cin, H, W, Cout = 2, 64, 13, 24, 96
+    x = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    xd, gd = _dev(x), _dev(g)
+    xh, xl = torch.empty(B, H, W, Cin, device="cuda"), torch.empty(B, H, W, Cin, device="cuda")
+    gh, gl = torch.empty(B, H, W, Cout, device="cuda"), torch.empty(B, H, W, Cout, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(xd), 0, _p(xh), _p(xl), B, Cin, H, W, _st()))
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(gd), 0, _p(gh), _p(gl), B, Cout, H, W, _st()))
+    gw = torch.zeros(int(lib.b2f_conv3x3_packed_floats(Cin, Cout)), device="cuda")
+    gb = torch.full((Cout,), -0.25, device="cuda")
+    _lib.check(lib.b2f_conv3x3_tc_backward_weights(_p(xh), _p(xl), Cin, _p(gh), _p(gl), None, 0, _p(gw), _p(gb), B, Cin, H, W,
+                                                   Cout, _st()))
+    torch.cuda.synchronize()
+    wb = g.astype(np.float64).sum(axis=(0, 2, 3)) - 0.25
+    assert np.abs(gb.cpu().numpy() - wb).max() < 1e-4 * np.abs(wb).max()
+
+
+DGRAD_CASES = [
+    # B, Cout (K), H, W, Cin (N), mask
+    (2, 128, 14, 32, 128, "hi"),
+    (1, 128, 9, 20, 96, "planar"),
+    (1, 64, 7, 16, 32, "hi"),
+    (1, 96, 16, 33, 64, "none"),
+    (1, 128, 10, 20, 196, "slices"),      # first decoder layer: slices of <= 128, planar, second call accumulates
+    (3, 192, 5, 10, 192, "slices_hi"),    # coarsest pyramid layer: slices with the channel-minor mask
+]
+
+
+@pytest.mark.parametrize("B,Cout,H,W,Cin,mask", DGRAD_CASES)
+def test_conv3x3_tc_backward_data(B, Cout, H, W, Cin, mask):
+    """SpatialConvolution:updateGradInput on the tensor cores against the float64 transpose of the oracle's
+    convolution: gin[ci, y, x] = sum_{co, ky, kx} g[co, y + 1 - ky, x + 1 - kx] w[co, ci, ky, kx], times the
+    LeakyReLU derivative of the layer below taken from its planar output or from the HI half of its split."""
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    g = rng.standard_normal((B, Cout, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * 0.05).astype(np.float32)
+    act = rng.standard_normal((B, Cin, H, W)).astype(np.float32)
+    act[rng.random(act.shape) < 0.05] = 0.0                 # exact zeros take the slope branch (act > 0 is false)
+    coutp, cinp = (Cout + 31) // 32 * 32, (Cin + 31) // 32 * 32
+    gd, ad = _dev(g), _dev(act)
+    gh, gl = torch.empty(B, H, W, coutp, device="cuda"), torch.empty(B, H, W, coutp, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(gd), 0, _p(gh), _p(gl), B, Cout, H, W, _st()))
+    ah, al = torch.empty(B, H, W, cinp, device="cuda"), torch.empty(B, H, W, cinp, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(ad), 0, _p(ah), _p(al), B, Cin, H, W, _st()))
+    wp = torch.empty(int(lib.b2f_conv3x3_packed_floats(Cin, Cout)), device="cuda")
+    _lib.check(lib.b2f_conv3x3_pack_weights(_p(_dev(w)), _p(wp), Cout, Cin, 0, _st()))
+    nt = 9 * Cin * coutp
+    th, tl = torch.empty(nt, device="cuda"), torch.empty(nt, device="cuda")
+    _lib.check(lib.b2f_conv3x3_tc_pack_from_packed(_p(wp), _p(th), _p(tl), Cout, Cin, Cout, 1, _st()))
+    # float64 reference
+    gp = np.pad(g.astype(np.float64), ((0, 0), (0, 0), (1, 1), (1, 1)))
+    want = np.zeros((B, Cin, H, W))
+    w64 = w.astype(np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            want += np.einsum("bnhw,nc->bchw", gp[:, :, 2 - ky:2 - ky + H, 2 - kx:2 - kx + W], w64[:, :, ky, kx])
+    slope = 0.2
+    masked = mask in ("hi", "planar", "slices_hi")
+    if masked:
+        want = np.where(act > 0, want, slope * want)
+    sliced = mask.startswith("slices")
+    one = Cin in (32, 64, 96, 128)
+    oh = torch.full((B, H, W, cinp), 9.0, device="cuda") if one else None
+    ol = torch.full((B, H, W, cinp), 9.0, device="cuda") if one else None
+    base = rng.standard_normal((B, Cin + 1, H, W)).astype(np.float32)
+    op = _dev(base) if (sliced or mask == "planar") else None
+    acc = 1 if sliced else 0
+    _lib.check(lib.b2f_conv3x3_tc_backward_data(
+        _p(gh), _p(gl), _p(th), _p(tl), _p(ad) if mask == "planar" else None, 0, _p(ah) if mask in ("hi", "slices_hi") else None,
+        _p(oh), _p(ol), _p(op, H * W) if op is not None else None, (Cin + 1) * H * W if op is not None else 0, B, Cout, H, W,
+        Cin, slope, acc, _st()))
+    torch.cuda.synchronize()
+    scale = np.abs(want).max()
+    if oh is not None:
+        got = (oh.double() + ol.double()).cpu().numpy()
+        assert np.abs(got[..., :Cin].transpose(0, 3, 1, 2) - want).max() < TOL * scale
+        assert not got[..., Cin:].any()
+    if op is not None:
+        got = op.cpu().numpy().astype(np.float64)
+        assert np.array_equal(got[:, 0], base[:, 0].astype(np.float64))            # the channel in front is untouched
+        ref = want + (base[:, 1:].astype(np.float64) if acc else 0.0)
+        assert np.abs(got[:, 1:] - ref).max() < TOL * max(scale, np.abs(ref).max())
+    # alternatives are exclusive
+    rc = lib.b2f_conv3x3_tc_backward_data(_p(gh), _p(gl), _p(th), _p(tl), _p(ad), 0, _p(ah), _p(oh), _p(ol),
+                                          _p(op, H * W) if op is not None else None, 0, B, Cout, H, W, Cin, slope, 0, _st())
+    assert rc != 0

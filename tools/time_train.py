@@ -71,7 +71,7 @@ for fn, args in p.bops:
         k += " (stride %d)" % args[13]
     t, n = agg.get(k, (0.0, 0))
     agg[k] = (t + ms, n + 1)
-    if a.detail and k.startswith(("b2f_conv3x3_backward_weights", "b2f_conv3x3_backward_data")):
+    if a.detail and k.startswith(("b2f_conv3x3_backward_weights", "b2f_conv3x3_backward_data", "b2f_conv3x3_tc_")):
         ints = [v for v in args if isinstance(v, int)]
         print("   %-44s %8.3f ms  ints %s" % (k, ms, ints[-7:]))
 tot = sum(t for t, _ in agg.values())
