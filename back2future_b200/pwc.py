@@ -108,11 +108,12 @@ class PWCNet:
 
     def __init__(self, opt=None, params=None, device="cuda:0", seed=2, image_warps=True, tensor_cores=False,
                  train_planar=False):
-        """tensor_cores=True: the decoders' five wide convolutions run on tcgen05 (b2f_conv3x3_tc_forward, three-pass
-        TF32 split, fp32-level accuracy) over channel-minor (hi, lo) activations.  The backward plan reads PLANAR
-        activations: with train_planar=True every tensor-core layer also writes its planar output (its second
-        destination) and the forward plan starts by re-packing the decoders' (hi, lo) weights from the flat parameter
-        buffer (Adam updates it every step) -- the training configuration of the tensor-core forward."""
+        """tensor_cores=True: the decoders (five wide convolutions and the 2-channel head) and the stride-1 pyramid layers
+        with >= TC_FEAT_MIN channels run on tcgen05 (b2f_conv3x3_tc_forward, three-pass TF32 split, fp32-level accuracy)
+        over channel-minor (hi, lo) activations.  train_planar=True is the training configuration of that path (the
+        name is from the time it also kept planar copies): the forward plan starts by re-packing the (hi, lo) weights
+        from the flat parameter buffer (Adam updates it every step) and records every layer's (hi, lo) input
+        (plan.dec_hl), which is all the tensor-core backward plan reads."""
         if not torch.cuda.is_available():
             raise RuntimeError("PWCNet: no CUDA device; the B200 path has no CPU fallback")
         self.opt = opt or Opt()
@@ -191,7 +192,7 @@ class PWCNet:
                 cv.b.copy_(torch.from_numpy(b), non_blocking=False)        # cudaMemcpy H2D
                 cv.gw = cv.gb = cv.wt = None
                 cv.tc_h = cv.tc_l = cv.tct_h = cv.tct_l = None
-                if self.tensor_cores and ((kind in ("occ", "flow", "bflow") and cout in (32, 64, 96, 128)) or
+                if self.tensor_cores and (kind in ("occ", "flow", "bflow") or
                                           (kind == "feat" and idx == "1" and cout >= TC_FEAT_MIN)):
                     # [9][Cout][Cin_p] hi / lo for the tensor-core path.  The coarsest level's flow decoder reads the
                     # first 162 channels of the occlusion decoder's wider joined input: zero weights for the rest.
@@ -353,33 +354,31 @@ class PWCNet:
                 return out
 
             def decoder_tc(kind, lane, cin0):
-                """Five tensor-core layers over channel-minor (hi, lo) pairs; the fifth writes planar fp32 for the
-                2-channel head (FFMA kernel: N = 2 is no tensor-core shape).  train_planar: every layer also writes its
-                planar output, the activations the backward plan reads (plan.dec, as the FFMA decoder records them)."""
+                """Six tensor-core layers over channel-minor (hi, lo) pairs: five wide ones that hand (hi, lo) to the
+                next, and the 2-channel head as one 32-wide output slice with two valid channels (the TMA zero-fills
+                the weight rows beyond Cout) that writes planar fp32.  No planar copy of the hidden activations: the
+                backward plan reads the (hi, lo) inputs of every layer (plan.dec_hl)."""
                 xh, xl, cin = Jsplit[0], Jsplit[1], cj
-                chain = []
-                hl_in = []                         # (hi, lo, channels) of every tensor-core layer's INPUT
+                hl_in = []                         # (hi, lo, channels) of every layer's INPUT
                 for i, cout in enumerate(DEC[:5]):
                     hl_in.append((xh, xl, cin))
                     cv = self._convs["%s.l%d.%d" % (kind, l, i)]
                     assert cv.tc_cin == cin, (kind, l, i, cv.tc_cin, cin)
-                    last = i == 4
-                    oh = None if last else E(B, h, w, _round32(cout))
-                    ol = None if last else E(B, h, w, _round32(cout))
-                    planar = E(B, cout, h, w) if (last or self.train_planar) else None
-                    plan.keep += [t_ for t_ in (oh, ol, planar) if t_ is not None]
-                    chain.append(planar)
+                    oh, ol = E(B, h, w, _round32(cout)), E(B, h, w, _round32(cout))
+                    plan.keep += [oh, ol]
                     ops.append((lane, lib.b2f_conv3x3_tc_forward,
-                                (P(xh), P(xl), P(cv.tc_h), P(cv.tc_l), P(cv.b), P(oh) if oh is not None else None,
-                                 P(ol) if ol is not None else None, P(planar) if planar is not None else None, 0, B, cin,
-                                 h, w, cout, C.c_float(0.2))))
+                                (P(xh), P(xl), P(cv.tc_h), P(cv.tc_l), P(cv.b), P(oh), P(ol), None, 0, B, cin, h, w, cout,
+                                 C.c_float(0.2))))
                     xh, xl, cin = oh, ol, cout
+                hl_in.append((xh, xl, cin))
                 out = E(B, 2, h, w)
                 plan.keep.append(out)
-                chain.append(out)
-                conv("%s.l%d.5" % (kind, l), P(planar), 0, B, DEC[4], h, w, P(out), 0, slope=1.0, lane=lane)
+                cv = self._convs["%s.l%d.5" % (kind, l)]
+                ops.append((lane, lib.b2f_conv3x3_tc_forward,
+                            (P(xh), P(xl), P(cv.tc_h), P(cv.tc_l), P(cv.b), None, None, P(out), 0, B, cin, h, w, 2,
+                             C.c_float(1.0))))
                 if self.train_planar:
-                    plan.dec[(kind, l)] = (chain, cin0)
+                    plan.dec[(kind, l)] = ([None] * 5 + [out], cin0)
                     plan.dec_hl[(kind, l)] = hl_in
                 return out
 
@@ -537,7 +536,7 @@ class PWCNet:
         for name, cv in self._convs.items():
             ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
             kind, _lvl, idx = name.split(".")
-            if self.train_planar and ((kind in ("occ", "flow", "bflow") and idx in ("0", "1", "2", "3", "4")) or
+            if self.train_planar and (kind in ("occ", "flow", "bflow") or
                                       (kind == "feat" and idx == "1" and cv.cout >= TC_FEAT_MIN)):
                 if cv.tct_h is None:
                     n_t = 9 * cv.cin * _round32(cv.cout)
@@ -622,23 +621,19 @@ class PWCNet:
                         dgrad(name, P(G), 0, None, 0, P(gJl), jbs, not first, B, cin, h, w)
 
             def decoder_backward_tc(kind, G, first, chain, cin0):
-                """The same walk on tcgen05: the head's input gradient (FFMA, 32 channels) is split once into
-                channel-minor (hi, lo); the input gradients of layers 4..1 (b2f_conv3x3_tc_backward_data: the forward
-                tensor-core kernel on transposed, mirrored (hi, lo) weights) hand (hi, lo) to the next layer and write
-                the planar copy; the WEIGHT gradients of layers 4..0 (b2f_conv3x3_tc_backward_weights: MN-major operands,
-                contraction over pixels) read the (hi, lo) input activations the forward left behind and the (hi, lo)
-                output gradients.  Layer 0's input gradient (162 .. 356 channels) runs as slices of <= 128 channels; only
-                the 2-channel head stays on the FFMA kernels."""
+                """The same walk on tcgen05: the 2-channel output gradient is split once into channel-minor (hi, lo);
+                the input gradients of layers 5..1 (b2f_conv3x3_tc_backward_data: the forward tensor-core kernel on
+                transposed, mirrored (hi, lo) weights, LeakyReLU derivative from the hi half of the layer's input) hand
+                (hi, lo) to the next layer; the WEIGHT gradients of layers 5..0 (b2f_conv3x3_tc_backward_weights:
+                MN-major operands, contraction over pixels) read the (hi, lo) input activations the forward left
+                behind and the (hi, lo) output gradients, the bias gradients are summed from (hi, lo) too.  Layer 0's
+                input gradient (162 .. 356 channels) runs as slices of <= 128 channels into the joined gradient."""
                 hl_in = plan.dec_hl[(kind, l)]
-                name5 = "%s.l%d.5" % (kind, l)
-                wgrad(name5, P(chain[4]), 0, P(G), 0, B, DEC[4], h, w)
-                g4 = E(B, DEC[4], h, w)
-                dgrad(name5, P(G), 0, P(chain[4]), 0, P(g4), 0, False, B, DEC[4], h, w)
-                gh, gl = E(B, h, w, _round32(DEC[4])), E(B, h, w, _round32(DEC[4]))
-                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(g4), 0, P(gh), P(gl), B, DEC[4], h, w)))
-                plan.keep += [g4, gh, gl]
-                Gp = g4
-                for i in range(4, -1, -1):
+                gh, gl = E(B, h, w, 32), E(B, h, w, 32)
+                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(G), 0, P(gh), P(gl), B, 2, h, w)))
+                plan.keep += [gh, gl]
+                Gp = G
+                for i in range(5, -1, -1):
                     name = "%s.l%d.%d" % (kind, l, i)
                     cv = self._convs[name]
                     xh, xl, cx = hl_in[i]
@@ -647,7 +642,7 @@ class PWCNet:
                                  cv.cin, h, w, cv.cout)))
                     if i == 0:
                         break
-                    cin, cout = DEC[i - 1], DEC[i]
+                    cin, cout = DEC[i - 1], cv.cout
                     nh, nl = E(B, h, w, _round32(cin)), E(B, h, w, _round32(cin))
                     plan.keep += [nh, nl]
                     # the LeakyReLU derivative from the HI half of layer i's channel-minor input (= layer i - 1's output);
