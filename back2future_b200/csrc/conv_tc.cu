@@ -49,7 +49,7 @@ constexpr int AS = B2F_TC_AS;                       // input-patch stages
 // tools/tc_trace.py) runs under the other tile's MMAs; (2, 4) is the one-CTA-per-SM deep-pipeline form.
 constexpr int THREADS = 128;
 
-template <int N>
+template <int N, bool S2 = false>
 struct Cfg {
   static constexpr int B_BYTES = N * 128;           // one of (hi, lo), one (chunk, tap)
   static constexpr int B_SLOT = 2 * B_BYTES;
@@ -58,7 +58,8 @@ struct Cfg {
   static constexpr int NG = (N + 31) / 32;          // 32-channel output groups
   static constexpr int STAGING = 2 * 2 * (TH * TW * 128);   // two (hi, lo) group buffers, reused round-robin
   static constexpr int SMEM_BYTES = (SMEM_MAIN > STAGING ? SMEM_MAIN : STAGING) + 256 + 1024;
-  static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static constexpr int NACC = S2 ? 4 * N : N;       // stride-2 input gradient: one accumulator per output parity class
+  static constexpr int TMEM_COLS = NACC <= 32 ? 32 : (NACC <= 64 ? 64 : (NACC <= 128 ? 128 : (NACC <= 256 ? 256 : 512)));
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(N % 16 == 0 && N >= 16 && N <= 256, "tcgen05.mma M = 128 needs N % 16 == 0");
 };
@@ -116,17 +117,26 @@ struct Args {
   // output-channel slice of a wider convolution (the first decoder layer's input gradient has 196 .. 356 channels): the
   // weight rows start at n0 (out_planar / bias / mask are passed already offset), and the planar result may be ADDED
   int n0, accumulate;
+  // S2 (input gradient of a STRIDE-2 convolution): H, W are the low-resolution (output-gradient) size the tiles walk,
+  // H2 x W2 the input-gradient plane the four parity classes are written to
+  int H2, W2;
 };
 
 // MASK: the input-gradient form (the activation derivative comes from a.mask (1, planar) or a.mask_hi (2, channel-minor));
 // a compile-time switch -- as a run-time branch inside the unrolled epilogue it cost the forward 10 % (0.307 -> 0.341 ms
 // on the level-3 128 -> 128 layer)
-template <int N, int MASK>
+// S2: the input gradient of a stride-2 convolution without the 4x zero-inserted detour.  gin[2y + py, 2x + px] only
+// receives the taps with ky = py + 1 (mod 2), kx = px + 1 (mod 2), read at g[y + (ky == 0), x + (kx == 0)]: the nine taps
+// of the transposed weights are still nine descriptor offsets into ONE low-resolution patch of the output gradient, but
+// they accumulate into FOUR TMEM accumulators (1 + 2 + 2 + 4 taps), one per parity class of the output pixel, and the
+// epilogue writes each class to its own pixels of the (H2, W2) plane.
+template <int N, int MASK, bool S2 = false>
 __global__ void __launch_bounds__(THREADS, (AS == 1 ? 2 : 1))
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                   const __grid_constant__ CUtensorMap tm_oh, const __grid_constant__ CUtensorMap tm_ol, const Args a) {
-  using cfg = Cfg<N>;
+  using cfg = Cfg<N, S2>;
+  static_assert(!S2 || MASK == 0, "the stride-2 input gradient has no activation mask");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_buf = smem;                                  // [2 stages][hi, lo][A_SLOT]
@@ -192,6 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int bs = 0;
     uint32_t acc = 0;
+    uint32_t seen = 0;       // S2: parity classes whose accumulator has been written
     for (int c = 0; c < a.nchunk; ++c) {
       const int as = c % AS;
       mbar_wait(&a_full[as], (c / AS) & 1);
@@ -202,14 +213,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
         mbar_wait(&b_full[s], (bs / NB) & 1);
         if (bs == 0) TC_STAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t shift = (uint32_t)((t / 3) * PW + (t % 3)) * 128u;
+        uint32_t shift = (uint32_t)((t / 3) * PW + (t % 3)) * 128u;
+        uint32_t dcol = 0;
+        if (S2) {
+          // stage t holds the mirrored tap: ky = 2 - t / 3, kx = 2 - t % 3
+          const int ky = 2 - t / 3, kx = 2 - t % 3;
+          const int cls = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);
+          shift = (uint32_t)((1 + (ky == 0)) * PW + 1 + (kx == 0)) * 128u;
+          dcol = (uint32_t)(cls * N);
+          acc = (seen >> cls) & 1u;
+          seen |= 1u << cls;
+        }
         const uint32_t bh = smem_u32(b_buf + s * cfg::B_SLOT), bl = bh + cfg::B_BYTES;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {            // hi * hi, lo * hi, hi * lo
           const uint32_t pa = (p == 1 ? al : ah) + shift, pb = (p == 2 ? bl : bh);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            mma_tf32(tmem, smem_desc(pa + 32u * k), smem_desc(pb + 32u * k), idesc, acc);
+            mma_tf32(tmem + dcol, smem_desc(pa + 32u * k), smem_desc(pb + 32u * k), idesc, acc);
             acc = 1;
           }
         }
@@ -233,8 +254,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   const bool inside = valid && y < a.H && x < a.W;
   const int prow = ry * TW + rx;                          // row of the staged (dense 7 x 16) tile
   const uint32_t stage0 = smem_u32(smem);
+  if (S2) {
+    // four parity classes x NG groups, planar only: class (py, px) of tile pixel (y, x) is pixel (2y + py, 2x + px)
 #pragma unroll 1
-  for (int g = 0; g < cfg::NG; ++g) {
+    for (int q = 0; q < 4 * cfg::NG; ++q) {
+      const int cls = q / cfg::NG, g = q % cfg::NG;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(cls * N + 32 * g), v);
+      const int Y = 2 * y + (cls >> 1), X = 2 * x + (cls & 1);
+      if (valid && Y < a.H2 && X < a.W2) {
+        float* o = a.out_planar + (size_t)b * a.pbs + (size_t)Y * a.W2 + X;
+        const size_t cs = (size_t)a.H2 * a.W2;
+        if (a.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (32 * g + j < a.Cout) atomicAdd(o + (size_t)(32 * g + j) * cs, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * cs] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+#pragma unroll 1
+  for (int g = 0; g < (S2 ? 0 : cfg::NG); ++g) {
     uint32_t v[32];
     float mk2[MASK == 2 ? 32 : 1];
     if (MASK == 2) {      // requested before the accumulator read so that the two latencies overlap
@@ -378,10 +422,10 @@ __global__ void pack_tc_from_packed_kernel(const float* __restrict__ wp, float* 
   }
 }
 
-template <int N, int MASK>
+template <int N, int MASK, bool S2 = false>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
               int CinP, int CoutP, cudaStream_t st, int wrows_total = 0) {
-  using cfg = Cfg<N>;
+  using cfg = Cfg<N, S2>;
   Args a = a0;
   CUtensorMap txh, txl, twh, twl, toh, tol;
   int rc;
@@ -410,7 +454,7 @@ int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl
     toh = txh;
     tol = txl;
   }
-  auto kern = conv3x3_tc_kernel<N, MASK>;
+  auto kern = conv3x3_tc_kernel<N, MASK, S2>;
   static thread_local int attr_dev = -1;
   int dev = 0;
   B2F_CUDA_TRY(cudaGetDevice(&dev));
@@ -544,6 +588,38 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
     if (rc) return rc;
   }
   return B2F_OK;
+}
+
+// Input gradient of a STRIDE-2 3x3 convolution (the down-sampling layers of the feature pyramid) on the tensor cores:
+// four parity-class accumulators over one low-resolution patch of the output gradient (kernel comment, S2).
+extern "C" int b2f_conv3x3_tc_backward_data_s2(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
+                                               float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int Ho,
+                                               int Wo, int Cin, int H, int W, int accumulate, b2f_stream_t stream) {
+  if (!g_hi || !g_lo || !wt_hi || !wt_lo || !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data_s2: NULL operand");
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || B > 65535) return fail(B2F_EINVAL, "conv3x3_tc_backward_data_s2: bad size");
+  if (Ho != (H - 1) / 2 + 1 || Wo != (W - 1) / 2 + 1)
+    return fail(B2F_EINVAL, "conv3x3_tc_backward_data_s2: %d x %d is not the stride-2 output size of %d x %d", Ho, Wo, H, W);
+  if (Cin > 128) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data_s2: Cin = %d > 128", Cin);
+  if (!aligned16(g_hi) || !aligned16(g_lo) || !aligned16(wt_hi) || !aligned16(wt_lo) || !aligned4(gin_planar))
+    return fail(B2F_EALIGN, "conv3x3_tc_backward_data_s2: misaligned operand");
+  if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data_s2: cuTensorMapEncodeTiled not available");
+  if (B == 0) return B2F_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int N = (Cin + 31) / 32 * 32, KP = (Cout + 31) / 32 * 32;
+  tc::Args a{};
+  a.trace = tc::g_tc_trace;
+  a.out_planar = gin_planar;
+  a.pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
+  a.nchunk = KP / 32;
+  a.Cout = Cin; a.H = Ho; a.W = Wo; a.H2 = H; a.W2 = W;
+  a.slope = 1.f;
+  a.accumulate = accumulate;
+  switch (N) {
+    case 32: return tc::launch_tc<32, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
+    case 64: return tc::launch_tc<64, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
+    case 96: return tc::launch_tc<96, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
+    default: return tc::launch_tc<128, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
+  }
 }
 
 extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,

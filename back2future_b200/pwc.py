@@ -537,7 +537,8 @@ class PWCNet:
             ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
             kind, _lvl, idx = name.split(".")
             if self.train_planar and (kind in ("occ", "flow", "bflow") or
-                                      (kind == "feat" and idx == "1" and cv.cout >= TC_FEAT_MIN)):
+                                      (kind == "feat" and idx == "1" and cv.cout >= TC_FEAT_MIN) or
+                                      (kind == "feat" and idx == "0" and cv.cin > 3)):
                 if cv.tct_h is None:
                     n_t = 9 * cv.cin * _round32(cv.cout)
                     cv.tct_h = torch.empty(n_t, device=dev, dtype=torch.float32)
@@ -691,6 +692,7 @@ class PWCNet:
             h, w = hw(l)
             c_in, c_out = FEAT[l - 2], FEAT[l - 1]
             gf, f, tmp = g_feats[l], plan.feats[l], plan.tmp[l]
+            g_tmp_hl = None
             ops.append((lib.b2f_leaky_relu_backward, (P(gf), gf.numel(), P(f), f.numel(), gf.numel(), 1, C.c_float(0.2))))
             if self.train_planar and c_out >= TC_FEAT_MIN:
                 cv1 = self._convs["feat.l%d.1" % l]
@@ -701,9 +703,13 @@ class PWCNet:
                 ops.append((lib.b2f_nhwc_split_from_bdhw, (P(gf), 0, P(gfh), P(gfl), 3 * B, c_out, h, w)))
                 ops.append((lib.b2f_conv3x3_tc_backward_weights,
                             (P(th), P(tl), c_out, P(gfh), P(gfl), P(gf), 0, P(cv1.gw), P(cv1.gb), 3 * B, c_out, h, w, c_out)))
+                if c_out in (64, 96, 128):      # one slice: the (hi, lo) form for the stride-2 input gradient below comes for free
+                    gth, gtl = E(3 * B, h, w, c_out), E(3 * B, h, w, c_out)
+                    plan.keep += [gth, gtl]
+                    g_tmp_hl = (gth, gtl)
                 ops.append((lib.b2f_conv3x3_tc_backward_data,
-                            (P(gfh), P(gfl), P(cv1.tct_h), P(cv1.tct_l), None, 0, P(th), None, None, P(g_tmp), 0, 3 * B, c_out,
-                             h, w, c_out, C.c_float(0.2), 0)))
+                            (P(gfh), P(gfl), P(cv1.tct_h), P(cv1.tct_l), None, 0, P(th), P(g_tmp_hl[0]) if g_tmp_hl else None,
+                             P(g_tmp_hl[1]) if g_tmp_hl else None, P(g_tmp), 0, 3 * B, c_out, h, w, c_out, C.c_float(0.2), 0)))
             else:
                 wgrad("feat.l%d.1" % l, P(tmp), 0, P(gf), 0, 3 * B, c_out, h, w)
                 g_tmp = E(*tmp.shape)
@@ -715,7 +721,17 @@ class PWCNet:
                     wgrad(name, sl(plan.x, 0, 3 * fr), 9 * H * W, sl(g_tmp, slot * B), 0, B, 3, H, W)
             else:
                 wgrad(name, P(plan.feats[l - 1]), 0, P(g_tmp), 0, 3 * B, c_in, 2 * h, 2 * w)
-                if w % 2 == 0:
+                if self.train_planar:
+                    # stride-2 input gradient on tcgen05: four parity-class accumulators over the low-resolution gradient
+                    cv0 = self._convs[name]
+                    if g_tmp_hl is None:
+                        g_tmp_hl = (E(3 * B, h, w, _round32(c_out)), E(3 * B, h, w, _round32(c_out)))
+                        plan.keep += list(g_tmp_hl)
+                        ops.append((lib.b2f_nhwc_split_from_bdhw, (P(g_tmp), 0, P(g_tmp_hl[0]), P(g_tmp_hl[1]), 3 * B, c_out, h, w)))
+                    ops.append((lib.b2f_conv3x3_tc_backward_data_s2,
+                                (P(g_tmp_hl[0]), P(g_tmp_hl[1]), P(cv0.tct_h), P(cv0.tct_l), P(g_feats[l - 1]), 0, 3 * B, c_out, h,
+                                 w, c_in, 2 * h, 2 * w, 1)))
+                elif w % 2 == 0:
                     # stride 2: dilate the output gradient and run the stride-1 (TMA / FFMA2) input-gradient kernel
                     z = E(3 * B, c_out, 2 * h, 2 * w)
                     plan.keep.append(z)

@@ -282,6 +282,15 @@ B2F_API int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, c
                                          float* gin_lo, float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout,
                                          int H, int W,
                                          int Cin, float leaky_slope, int accumulate, b2f_stream_t stream);
+/* SpatialConvolution:updateGradInput of a STRIDE-2 3x3 convolution (the down-sampling half of pwc.lua:58-65's convUnit)
+ * on the tensor cores: g_hi / g_lo = channel-minor (B, Ho, Wo, Cout rounded up to 32) split of the output gradient, wt_hi
+ * / wt_lo as for b2f_conv3x3_tc_backward_data; gin_planar (B, Cin, H, W) with Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1.
+ * gin[2y + py, 2x + px] only receives the taps with ky = py + 1, kx = px + 1 (mod 2): four accumulators (one per parity
+ * class of the output pixel) over ONE low-resolution patch, a quarter of the multiply-adds of the zero-inserted form.
+ * Cin <= 128.  accumulate != 0: added to gin_planar.                                                                */
+B2F_API int b2f_conv3x3_tc_backward_data_s2(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
+                                            float* gin_planar, int64_t gin_planar_batch_stride, int B, int Cout, int Ho,
+                                            int Wo, int Cin, int H, int W, int accumulate, b2f_stream_t stream);
 /* SpatialConvolution:accGradParameters of the same layer on the tensor cores: gw_packed += d loss / d weight from the
  * channel-minor (hi, lo) INPUT activation (x_hi / x_lo, a (B, H, W, Cx rounded up to 32) tensor whose first Cin channels
  * are this convolution's input -- the coarsest flow decoder reads the first 162 channels of a wider joined input) and

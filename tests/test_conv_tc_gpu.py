@@ -243,3 +243,52 @@ def test_conv3x3_tc_backward_data(B, Cout, H, W, Cin, mask):
     rc = lib.b2f_conv3x3_tc_backward_data(_p(gh), _p(gl), _p(th), _p(tl), _p(ad), 0, _p(ah), _p(oh), _p(ol),
                                           _p(op, H * W) if op is not None else None, 0, B, Cout, H, W, Cin, slope, 0, _st())
     assert rc != 0
+
+
+S2_CASES = [
+    # B, Cout (K), H, W (input-gradient plane), Cin (N), accumulate
+    (2, 64, 16, 32, 32, 0),
+    (1, 96, 10, 20, 64, 1),
+    (1, 32, 9, 15, 16, 1),       # odd sizes, 16 valid channels of a 32-wide slice
+    (1, 128, 14, 40, 96, 0),
+    (2, 192, 10, 20, 128, 1),    # four 128-column accumulators: all 512 TMEM columns
+]
+
+
+@pytest.mark.parametrize("B,Cout,H,W,Cin,acc", S2_CASES)
+def test_conv3x3_tc_backward_data_stride2(B, Cout, H, W, Cin, acc):
+    """Input gradient of a stride-2 convolution on the tensor cores (four parity-class accumulators) against the
+    float64 scatter gin[ci, 2 yo + ky - 1, 2 xo + kx - 1] += g[co, yo, xo] w[co, ci, ky, kx]."""
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(13)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    g = rng.standard_normal((B, Cout, Ho, Wo)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * 0.05).astype(np.float32)
+    coutp = (Cout + 31) // 32 * 32
+    gd = _dev(g)
+    gh, gl = torch.empty(B, Ho, Wo, coutp, device="cuda"), torch.empty(B, Ho, Wo, coutp, device="cuda")
+    _lib.check(lib.b2f_nhwc_split_from_bdhw(_p(gd), 0, _p(gh), _p(gl), B, Cout, Ho, Wo, _st()))
+    wp = torch.empty(int(lib.b2f_conv3x3_packed_floats(Cin, Cout)), device="cuda")
+    _lib.check(lib.b2f_conv3x3_pack_weights(_p(_dev(w)), _p(wp), Cout, Cin, 0, _st()))
+    nt = 9 * Cin * coutp
+    th, tl = torch.empty(nt, device="cuda"), torch.empty(nt, device="cuda")
+    _lib.check(lib.b2f_conv3x3_tc_pack_from_packed(_p(wp), _p(th), _p(tl), Cout, Cin, Cout, 1, _st()))
+    want = np.zeros((B, Cin, H + 2, W + 2))
+    g64, w64 = g.astype(np.float64), w.astype(np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            # padded coordinates: Y + 1 = 2 yo + ky
+            want[:, :, ky:ky + 2 * Ho:2, kx:kx + 2 * Wo:2] += np.einsum("bnhw,nc->bchw", g64, w64[:, :, ky, kx])
+    want = want[:, :, 1:H + 1, 1:W + 1]
+    base = rng.standard_normal((B, Cin + 1, H, W)).astype(np.float32)
+    op = _dev(base)
+    _lib.check(lib.b2f_conv3x3_tc_backward_data_s2(_p(gh), _p(gl), _p(th), _p(tl), _p(op, H * W), (Cin + 1) * H * W, B, Cout, Ho,
+                                                   Wo, Cin, H, W, acc, _st()))
+    torch.cuda.synchronize()
+    got = op.cpu().numpy().astype(np.float64)
+    assert np.array_equal(got[:, 0], base[:, 0].astype(np.float64))
+    ref = want + (base[:, 1:].astype(np.float64) if acc else 0.0)
+    assert np.abs(got[:, 1:] - ref).max() < TOL * max(np.abs(want).max(), np.abs(ref).max())
+    assert lib.b2f_conv3x3_tc_backward_data_s2(_p(gh), _p(gl), _p(th), _p(tl), _p(op), 0, B, Cout, Ho + 1, Wo, Cin, H, W, 0,
+                                               _st()) != 0
