@@ -74,6 +74,7 @@ SIGNATURES = {
     "b2f_conv3x3_tc_backward_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "b2f_conv3x3_tc_pack_from_packed_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b2f_conv3x3_tc_backward_data_s2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b2f_conv3x3_tc_backward_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
@@ -161,6 +162,20 @@ def check(status):
         lib = load()
         msg = lib.b2f_last_error().decode("utf-8", "replace") or lib.b2f_status_string(status).decode()
         raise B2FError(status, msg)
+
+
+class PackJob(C.Structure):
+    """b2f_pack_job (include/b2f.h)."""
+    _fields_ = [("w_packed", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("Cout", C.c_int32),
+                ("Cin", C.c_int32), ("K", C.c_int32), ("transpose", C.c_int32)]
+
+
+def pack_jobs(jobs):
+    """Host bytes of a b2f_pack_job array; jobs = [(w_packed_ptr, hi_ptr, lo_ptr, Cout, Cin, K, transpose), ...]."""
+    arr = (PackJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        arr[i] = PackJob(*j)
+    return bytes(arr)
 
 
 def ptr_array(ptrs):

@@ -422,6 +422,31 @@ __global__ void pack_tc_from_packed_kernel(const float* __restrict__ wp, float* 
   }
 }
 
+// blockIdx.y = job (b2f_pack_job in device memory), blockIdx.x strides over the job's elements
+struct PackJob {
+  const float* wp;
+  float* hi;
+  float* lo;
+  int32_t Cout, Cin, K, transpose;
+};
+__global__ void pack_tc_from_packed_batch_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const int Kp = (j.K + 31) / 32 * 32, N = j.transpose ? j.Cin : j.Cout, CoutP = (j.Cout + 63) / 64 * 64;
+  const int total = 9 * N * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Kp, n = (i / Kp) % N, t = i / (Kp * N);
+    float v = 0.f;
+    if (!j.transpose) {
+      if (k < j.Cin && n < j.Cout) v = j.wp[((size_t)k * 9 + t) * CoutP + n];
+    } else {
+      if (k < j.Cout && n < j.Cin) v = j.wp[((size_t)n * 9 + (8 - t)) * CoutP + k];
+    }
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    j.hi[i] = h;
+    j.lo[i] = v - h;
+  }
+}
+
 template <int N, int MASK, bool S2 = false>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
               int CinP, int CoutP, cudaStream_t st, int wrows_total = 0) {
@@ -509,6 +534,17 @@ extern "C" int b2f_conv3x3_tc_pack_from_packed(const float* w_packed, float* w_h
   tc::pack_tc_from_packed_kernel<<<std::max(1, std::min((total + 255) / 256, num_sms() * 8)), 256, 0,
                                    reinterpret_cast<cudaStream_t>(stream)>>>(w_packed, w_hi, w_lo, Cout, Cin, CoutP, N, Kp, transpose);
   B2F_CHECK_LAUNCH("pack_tc_from_packed_kernel");
+  return B2F_OK;
+}
+
+static_assert(sizeof(b2f_pack_job) == sizeof(tc::PackJob), "b2f_pack_job layout");
+extern "C" int b2f_conv3x3_tc_pack_from_packed_batch(const b2f_pack_job* jobs_device, int njobs, b2f_stream_t stream) {
+  if (njobs < 0 || (njobs > 0 && !jobs_device)) return fail(B2F_EINVAL, "conv3x3_tc_pack_from_packed_batch: bad argument");
+  if (njobs > 65535) return fail(B2F_EINVAL, "conv3x3_tc_pack_from_packed_batch: more than 65535 jobs");
+  if (njobs == 0) return B2F_OK;
+  tc::pack_tc_from_packed_batch_kernel<<<dim3(16, njobs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const tc::PackJob*>(jobs_device));
+  B2F_CHECK_LAUNCH("pack_tc_from_packed_batch_kernel");
   return B2F_OK;
 }
 

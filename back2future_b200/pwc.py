@@ -277,10 +277,11 @@ class PWCNet:
 
         # -- training with the tensor-core forward: the (hi, lo) weights follow the flat parameters ---------
         if self.train_planar:
-            for name, cv in self._convs.items():
-                if cv.tc_h is not None:
-                    ops.append((0, lib.b2f_conv3x3_tc_pack_from_packed,
-                                (P(cv.w), P(cv.tc_h), P(cv.tc_l), cv.cout, cv.cin, cv.tc_cin, 0)))
+            jobs = [(cv.w.data_ptr(), cv.tc_h.data_ptr(), cv.tc_l.data_ptr(), cv.cout, cv.cin, cv.tc_cin, 0)
+                    for cv in self._convs.values() if cv.tc_h is not None]
+            table = torch.frombuffer(bytearray(_lib.pack_jobs(jobs)), dtype=torch.uint8).to(dev)
+            plan.keep.append(table)
+            ops.append((0, lib.b2f_conv3x3_tc_pack_from_packed_batch, (P(table), len(jobs))))       # one launch for all
 
         # -- siamese feature pyramid on the 3B batch (slots: past, future, reference) -----------------------------
         feats = {}
@@ -533,17 +534,25 @@ class PWCNet:
         plan.gout = [E(*t.shape) for t in plan.output]
         per = len(plan.output) // (levels - l_st + 1)
         zero(self.flat_grads)                                      # model:zeroGradParameters(), train.lua:251
+        jobs = []
         for name, cv in self._convs.items():
-            ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
             kind, _lvl, idx = name.split(".")
             if self.train_planar and (kind in ("occ", "flow", "bflow") or
                                       (kind == "feat" and idx == "1" and cv.cout >= TC_FEAT_MIN) or
                                       (kind == "feat" and idx == "0" and cv.cin > 3)):
+                # input gradient on tcgen05: transposed, mirrored (hi, lo) operand; all of them in ONE launch below
                 if cv.tct_h is None:
                     n_t = 9 * cv.cin * _round32(cv.cout)
                     cv.tct_h = torch.empty(n_t, device=dev, dtype=torch.float32)
                     cv.tct_l = torch.empty(n_t, device=dev, dtype=torch.float32)
-                ops.append((lib.b2f_conv3x3_tc_pack_from_packed, (P(cv.w), P(cv.tct_h), P(cv.tct_l), cv.cout, cv.cin, cv.cout, 1)))
+                jobs.append((cv.w.data_ptr(), cv.tct_h.data_ptr(), cv.tct_l.data_ptr(), cv.cout, cv.cin, cv.cout, 1))
+            elif not (kind == "feat" and idx == "0" and cv.cin == 3):
+                # input gradient on the FFMA kernel (the first convolution's input is the image: no input gradient)
+                ops.append((lib.b2f_conv3x3_transpose_packed, (P(cv.w), P(cv.wt), cv.cout, cv.cin)))
+        if jobs:
+            table = torch.frombuffer(bytearray(_lib.pack_jobs(jobs)), dtype=torch.uint8).to(dev)
+            plan.keep.append(table)
+            ops.append((lib.b2f_conv3x3_tc_pack_from_packed_batch, (P(table), len(jobs))))
         g_feats = {l: E(*plan.feats[l].shape) for l in plan.feats}
         for l in g_feats:
             zero(g_feats[l])
