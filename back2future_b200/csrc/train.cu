@@ -21,13 +21,20 @@ namespace {
 // tile of gout (64 planes) and the matching input patch (8 planes, + halo) are staged in shared memory with cp.async,
 // two stages deep; per 4 pixels a thread reads its two gout float4 (conflict-free: the plane pitch is 4 mod 32 words)
 // and, per tap row, 6 (stride 1) or 9 (stride 2) input values that are the same for the whole warp (broadcast) for
-// 72 FMAs.  The partial sums leave with atomicAdd (co is the lane index: 128-byte coalesced reductions).
+// 72 FMAs.  The partial sums leave with atomicAdd (co is the lane index: 128-byte coalesced reductions).  The input
+// values of a row are read as one word + one or two aligned float4 (+ one word): 3 shared-memory loads instead of 6 / 9.
+// Layers with at most 32 output channels (where the wide form idles half or more of its lanes) use the NARROW form:
+// CTA = (16 input channels, 32 output channels), thread (co, ci) and (co, ci + 8).
 namespace wg {
-constexpr int KC = 8, NC = 64, TH = 4, TW = 32, THREADS = 256;
+constexpr int TH = 4, TW = 32, THREADS = 256;
 constexpr int GP = TW + 4;                 // gout row pitch (words)
 constexpr int GPLANE = TH * GP + 4;        // plane pitch: 148 = 4 mod 32
-template <int S>
+// NARROW = false: CTA = 8 input x 64 output channels, thread (co, co + 32) x ci;
+// NARROW = true (Cout <= 32: the pyramid's 16- and 32-channel layers, where half or three quarters of the wide form's
+//               lanes idle): CTA = 16 input x 32 output channels, thread co x (ci, ci + 8).
+template <int S, bool NARROW>
 struct Cfg {
+  static constexpr int KC = NARROW ? 16 : 8, NC = NARROW ? 32 : 64;
   static constexpr int XR = (TH - 1) * S + 3;          // input rows of a tile
   static constexpr int XW = (TW - 1) * S + 3;          // input columns
   static constexpr int XP = (XW + 3) / 4 * 4 + 4;      // row pitch, first column at word 3 so that column 1 is 16-byte aligned
@@ -35,6 +42,9 @@ struct Cfg {
   static constexpr int X_ELEMS = KC * XR * XP;
   static constexpr int STAGE = G_ELEMS + X_ELEMS;
   static constexpr int SMEM_BYTES = 2 * STAGE * 4;
+  static constexpr int NV = (XW - 1) / 4;              // whole 16-byte chunks of an input row after its first column
+  static constexpr int RW = 1 + NV + ((XW - 1) % 4);   // copies per input row in the vector form (1 + 8 + 1 / 1 + 16)
+  static_assert((XW - 1) % 4 <= 1, "one trailing column at most");
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -51,12 +61,15 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int S, bool VEC>
+// VEC: 16-byte staging copies of gout AND of the input rows (Wo % 4 == 0, W % 4 == 0, 16-byte aligned bases and batch
+// strides): a row is its first column (the left halo), NV whole chunks and, for stride 1, one trailing column.
+template <int S, bool VEC, bool NARROW>
 __global__ void __launch_bounds__(THREADS, 2)
 conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict__ gout, int64_t gbs,
               float* __restrict__ gw, float* __restrict__ gb, int B, int Cin, int H, int W, int Cout, int CoutP, int Ho,
               int Wo, int nco, int nsplit) {
-  using cfg = Cfg<S>;
+  using cfg = Cfg<S, NARROW>;
+  constexpr int KC = cfg::KC, NC = cfg::NC;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int co_l = tid & 31, ci_l = tid >> 5;
@@ -66,6 +79,7 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
   const int ntiles = B * tiles_y * tiles_x;
   const int t_lo = (int)((int64_t)ntiles * blockIdx.y / nsplit), t_hi = (int)((int64_t)ntiles * (blockIdx.y + 1) / nsplit);
 
+  // acc[h]: WIDE h = output-channel half (co, co + 32); NARROW h = input-channel half (ci, ci + 8)
   float acc[2][9];
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -80,7 +94,7 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
     const int x0 = tx * TW, y0 = ty * TH;
     const float* gbase = gout + (size_t)b * gbs;
     if (VEC) {
-      // 64 planes x 4 rows x 8 float4
+      // NC planes x 4 rows x 8 float4
       for (int i = tid; i < NC * TH * (TW / 4); i += THREADS) {
         const int q = i & 7, r = (i >> 3) & 3, c = i >> 5;
         const int yy = y0 + r, xx = x0 + 4 * q, n = n0 + c;
@@ -97,11 +111,30 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
     }
     const float* xbase = x + (size_t)b * xbs;
     const int xi0 = x0 * S - 1, yi0 = y0 * S - 1;
-    for (int i = tid; i < KC * cfg::XR * cfg::XW; i += THREADS) {
-      const int q = i % cfg::XW, r = (i / cfg::XW) % cfg::XR, c = i / (cfg::XW * cfg::XR);
-      const int yy = yi0 + r, xx = xi0 + q, ci = c0 + c;
-      const bool ok = ci < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W;
-      cp_async4(xs + (c * cfg::XR + r) * cfg::XP + 3 + q, ok ? xbase + ((size_t)ci * H + yy) * W + xx : x, ok);
+    if (VEC) {
+      for (int i = tid; i < KC * cfg::XR * cfg::RW; i += THREADS) {
+        const int it = i % cfg::RW, r = (i / cfg::RW) % cfg::XR, c = i / (cfg::RW * cfg::XR);
+        const int yy = yi0 + r, ci = c0 + c;
+        const bool rok = ci < Cin && yy >= 0 && yy < H;
+        float* drow = xs + (c * cfg::XR + r) * cfg::XP + 3;
+        const float* srow = xbase + ((size_t)ci * H + yy) * W;
+        if (it >= 1 && it <= cfg::NV) {
+          const int q = 1 + 4 * (it - 1), xx = xi0 + q;        // xx = x0 * S + 4 (it - 1): a multiple of 4
+          const bool ok = rok && xx < W;                       // W % 4 == 0
+          cp_async16(drow + q, ok ? srow + xx : x, ok);
+        } else {
+          const int q = it == 0 ? 0 : cfg::XW - 1, xx = xi0 + q;
+          const bool ok = rok && xx >= 0 && xx < W;
+          cp_async4(drow + q, ok ? srow + xx : x, ok);
+        }
+      }
+    } else {
+      for (int i = tid; i < KC * cfg::XR * cfg::XW; i += THREADS) {
+        const int q = i % cfg::XW, r = (i / cfg::XW) % cfg::XR, c = i / (cfg::XW * cfg::XR);
+        const int yy = yi0 + r, xx = xi0 + q, ci = c0 + c;
+        const bool ok = ci < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        cp_async4(xs + (c * cfg::XR + r) * cfg::XP + 3 + q, ok ? xbase + ((size_t)ci * H + yy) * W + xx : x, ok);
+      }
     }
     cp_commit();
   };
@@ -119,48 +152,64 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
     const float* gs = smem + s * cfg::STAGE;
     const float* xs = gs + cfg::G_ELEMS + ci_l * cfg::XR * cfg::XP + 3;
     const float* g0 = gs + co_l * GPLANE;
-    const float* g1 = g0 + 32 * GPLANE;
 #pragma unroll
     for (int r = 0; r < TH; ++r) {
 #pragma unroll 2
       for (int q = 0; q < TW / 4; ++q) {
         const float4 a = *reinterpret_cast<const float4*>(g0 + r * GP + 4 * q);
-        const float4 c = *reinterpret_cast<const float4*>(g1 + r * GP + 4 * q);
+        float4 c = a;
+        if (!NARROW) c = *reinterpret_cast<const float4*>(g0 + 32 * GPLANE + r * GP + 4 * q);
         const float ga[4] = {a.x, a.y, a.z, a.w}, gc[4] = {c.x, c.y, c.z, c.w};
         if (ci_l == 0) {
           bsum[0] += (a.x + a.y) + (a.z + a.w);
-          bsum[1] += (c.x + c.y) + (c.z + c.w);
+          if (!NARROW) bsum[1] += (c.x + c.y) + (c.z + c.w);
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const float* xr = xs + (r * S + ky) * cfg::XP + 4 * q * S;
-          constexpr int NX = 3 * S + 3;      // 6 / 9 input values of this row
-          float xv[NX];
+          constexpr int NX = 3 * S + 3;      // 6 / 9 input values of this row: one word, then one or two aligned float4, [one word]
 #pragma unroll
-          for (int i = 0; i < NX; ++i) xv[i] = xr[i];
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              acc[0][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[0][ky * 3 + kx]);
-              acc[1][ky * 3 + kx] = fmaf(gc[p], xv[p * S + kx], acc[1][ky * 3 + kx]);
+          for (int hx = 0; hx < (NARROW ? 2 : 1); ++hx) {
+            const float* xr = xs + hx * 8 * cfg::XR * cfg::XP + (r * S + ky) * cfg::XP + 4 * q * S;
+            float xv[NX];
+            xv[0] = xr[0];
+            {
+              const float4 v = *reinterpret_cast<const float4*>(xr + 1);
+              xv[1] = v.x; xv[2] = v.y; xv[3] = v.z; xv[4] = v.w;
             }
+            if (S == 2) {
+              const float4 v = *reinterpret_cast<const float4*>(xr + 5);
+              xv[5] = v.x; xv[6] = v.y; xv[7] = v.z; xv[NX - 1] = v.w;
+            } else {
+              xv[NX - 1] = xr[NX - 1];
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int p = 0; p < 4; ++p) {
+                if (NARROW) {
+                  acc[hx][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[hx][ky * 3 + kx]);
+                } else {
+                  acc[0][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[0][ky * 3 + kx]);
+                  acc[1][ky * 3 + kx] = fmaf(gc[p], xv[p * S + kx], acc[1][ky * 3 + kx]);
+                }
+              }
+          }
         }
       }
     }
     __syncthreads();
   }
 
-  const int ci = c0 + ci_l;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int n = n0 + co_l + 32 * h;
+    const int n = n0 + co_l + (NARROW ? 0 : 32 * h);
+    const int ci = c0 + ci_l + (NARROW ? 8 * h : 0);
     if (n >= Cout) continue;
     if (ci < Cin) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) atomicAdd(gw + (size_t)(ci * 9 + t) * CoutP + n, acc[h][t]);
     }
-    if (gb && ci_l == 0 && c0 == 0) atomicAdd(gb + n, bsum[h]);
+    if (gb && ci_l == 0 && c0 == 0 && (!NARROW || h == 0)) atomicAdd(gb + n, bsum[h]);
   }
 }
 }  // namespace wg
@@ -325,32 +374,39 @@ extern "C" int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stri
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int CoutP = (Cout + 63) / 64 * 64;
-  const int nci = (Cin + wg::KC - 1) / wg::KC, nco = (Cout + wg::NC - 1) / wg::NC;
+  const bool narrow = Cout <= 32 && Cin > 8;
+  const int KC = narrow ? 16 : 8, NC = narrow ? 32 : 64;
+  const int nci = (Cin + KC - 1) / KC, nco = (Cout + NC - 1) / NC;
   const int ntiles = B * ((Ho + wg::TH - 1) / wg::TH) * ((Wo + wg::TW - 1) / wg::TW);
   // enough CTAs for ~3 waves of 2 per SM, at least 4 tiles per CTA so the two-stage pipeline has something to overlap
   int nsplit = (num_sms() * 6 + nci * nco - 1) / (nci * nco);
   nsplit = std::max(1, std::min(nsplit, std::max(1, ntiles / 4)));
   if (nsplit > 65535) nsplit = 65535;
-  const bool vec = (Wo % 4) == 0 && aligned16(gout) && gbs % 4 == 0;
+  const bool vec = (Wo % 4) == 0 && aligned16(gout) && gbs % 4 == 0 && (W % 4) == 0 && aligned16(x) && xbs % 4 == 0;
   dim3 grid(nci * nco, nsplit);
-#define B2F_WG(S, V)                                                                                                  \
+#define B2F_WG(S, V, NRW)                                                                                             \
   do {                                                                                                                \
-    auto kern = wg::conv3x3_wgrad<S, V>;                                                                              \
+    auto kern = wg::conv3x3_wgrad<S, V, NRW>;                                                                         \
     static thread_local int attr_dev = -1;                                                                            \
     int dev = 0;                                                                                                      \
     B2F_CUDA_TRY(cudaGetDevice(&dev));                                                                                \
     if (attr_dev != dev) {                                                                                            \
-      B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::Cfg<S>::SMEM_BYTES));  \
+      B2F_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::Cfg<S, NRW>::SMEM_BYTES)); \
       attr_dev = dev;                                                                                                 \
     }                                                                                                                 \
-    kern<<<grid, wg::THREADS, wg::Cfg<S>::SMEM_BYTES, st>>>(x, xbs, gout, gbs, gw_packed, gbias, B, Cin, H, W, Cout,   \
-                                                            CoutP, Ho, Wo, nco, nsplit);                              \
+    kern<<<grid, wg::THREADS, wg::Cfg<S, NRW>::SMEM_BYTES, st>>>(x, xbs, gout, gbs, gw_packed, gbias, B, Cin, H, W, Cout, \
+                                                                  CoutP, Ho, Wo, nco, nsplit);                        \
+  } while (0)
+#define B2F_WG2(S, V)                                                                                                 \
+  do {                                                                                                                \
+    if (narrow) B2F_WG(S, V, true); else B2F_WG(S, V, false);                                                         \
   } while (0)
   if (stride == 1) {
-    if (vec) B2F_WG(1, true); else B2F_WG(1, false);
+    if (vec) B2F_WG2(1, true); else B2F_WG2(1, false);
   } else {
-    if (vec) B2F_WG(2, true); else B2F_WG(2, false);
+    if (vec) B2F_WG2(2, true); else B2F_WG2(2, false);
   }
+#undef B2F_WG2
 #undef B2F_WG
   B2F_CHECK_LAUNCH("conv3x3_wgrad");
   return B2F_OK;

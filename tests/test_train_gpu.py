@@ -46,6 +46,10 @@ CASES = [
     (1, 5, 10, 38, 7, 1),       # widths the TMA path cannot take
     (1, 6, 5, 19, 4, 2),
     (2, 354, 7, 16, 128, 1),
+    (2, 16, 20, 48, 32, 2),     # narrow weight-gradient form (Cout <= 32: 16 input x 32 output channels per CTA), stride 2
+    (1, 24, 12, 32, 16, 1),     # narrow, ragged input-channel block, half the lanes without an output channel
+    (1, 16, 10, 38, 16, 1),     # narrow, scalar staging (width not a multiple of 4)
+    (1, 40, 9, 64, 70, 2),      # wide form, vector staging of a stride-2 input row (two 16-byte chunks per 4 pixels)
 ]
 
 
