@@ -29,12 +29,14 @@ namespace wg {
 constexpr int TH = 4, TW = 32, THREADS = 256;
 constexpr int GP = TW + 4;                 // gout row pitch (words)
 constexpr int GPLANE = TH * GP + 4;        // plane pitch: 148 = 4 mod 32
-// NARROW = false: CTA = 8 input x 64 output channels, thread (co, co + 32) x ci;
-// NARROW = true (Cout <= 32: the pyramid's 16- and 32-channel layers, where half or three quarters of the wide form's
-//               lanes idle): CTA = 16 input x 32 output channels, thread co x (ci, ci + 8).
-template <int S, bool NARROW>
+// MODE 0 (wide):   CTA = 8 input x 64 output channels, thread (co, co + 32) x ci;
+// MODE 1 (narrow, Cout <= 32: the pyramid's 16- and 32-channel layers, where half or three quarters of the wide form's
+//                 lanes idle): CTA = 16 input x 32 output channels, thread co x (ci, ci + 8);
+// MODE 2 (tiny, Cin <= 4 and Cout <= 16: the first convolution, 3 image channels -> 16): CTA = 4 input x 16 output
+//                 channels x the 4 rows of the pixel tile, thread (co, ci, row).
+template <int S, int MODE>
 struct Cfg {
-  static constexpr int KC = NARROW ? 16 : 8, NC = NARROW ? 32 : 64;
+  static constexpr int KC = MODE == 2 ? 4 : (MODE == 1 ? 16 : 8), NC = MODE == 2 ? 16 : (MODE == 1 ? 32 : 64);
   static constexpr int XR = (TH - 1) * S + 3;          // input rows of a tile
   static constexpr int XW = (TW - 1) * S + 3;          // input columns
   static constexpr int XP = (XW + 3) / 4 * 4 + 4;      // row pitch, first column at word 3 so that column 1 is 16-byte aligned
@@ -63,16 +65,18 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 
 // VEC: 16-byte staging copies of gout AND of the input rows (Wo % 4 == 0, W % 4 == 0, 16-byte aligned bases and batch
 // strides): a row is its first column (the left halo), NV whole chunks and, for stride 1, one trailing column.
-template <int S, bool VEC, bool NARROW>
+template <int S, bool VEC, int MODE>
 __global__ void __launch_bounds__(THREADS, 2)
 conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict__ gout, int64_t gbs,
               float* __restrict__ gw, float* __restrict__ gb, int B, int Cin, int H, int W, int Cout, int CoutP, int Ho,
               int Wo, int nco, int nsplit) {
-  using cfg = Cfg<S, NARROW>;
+  using cfg = Cfg<S, MODE>;
   constexpr int KC = cfg::KC, NC = cfg::NC;
+  constexpr bool NARROW = MODE == 1, TINY = MODE == 2;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
-  const int co_l = tid & 31, ci_l = tid >> 5;
+  const int co_l = TINY ? (tid & 15) : (tid & 31), ci_l = TINY ? ((tid >> 4) & 3) : (tid >> 5);
+  const int ps = tid >> 6;                 // TINY: the tile row of this thread
   const int cblk = blockIdx.x;
   const int c0 = (cblk / nco) * KC, n0 = (cblk % nco) * NC;
   const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
@@ -153,16 +157,17 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
     const float* xs = gs + cfg::G_ELEMS + ci_l * cfg::XR * cfg::XP + 3;
     const float* g0 = gs + co_l * GPLANE;
 #pragma unroll
-    for (int r = 0; r < TH; ++r) {
+    for (int rr = 0; rr < (TINY ? 1 : TH); ++rr) {
+      const int r = TINY ? ps : rr;
 #pragma unroll 2
       for (int q = 0; q < TW / 4; ++q) {
         const float4 a = *reinterpret_cast<const float4*>(g0 + r * GP + 4 * q);
         float4 c = a;
-        if (!NARROW) c = *reinterpret_cast<const float4*>(g0 + 32 * GPLANE + r * GP + 4 * q);
+        if (MODE == 0) c = *reinterpret_cast<const float4*>(g0 + 32 * GPLANE + r * GP + 4 * q);
         const float ga[4] = {a.x, a.y, a.z, a.w}, gc[4] = {c.x, c.y, c.z, c.w};
         if (ci_l == 0) {
           bsum[0] += (a.x + a.y) + (a.z + a.w);
-          if (!NARROW) bsum[1] += (c.x + c.y) + (c.z + c.w);
+          if (MODE == 0) bsum[1] += (c.x + c.y) + (c.z + c.w);
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -186,7 +191,7 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
               for (int p = 0; p < 4; ++p) {
-                if (NARROW) {
+                if (MODE != 0) {
                   acc[hx][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[hx][ky * 3 + kx]);
                 } else {
                   acc[0][ky * 3 + kx] = fmaf(ga[p], xv[p * S + kx], acc[0][ky * 3 + kx]);
@@ -201,17 +206,18 @@ conv3x3_wgrad(const float* __restrict__ x, int64_t xbs, const float* __restrict_
   }
 
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int n = n0 + co_l + (NARROW ? 0 : 32 * h);
+  for (int h = 0; h < (TINY ? 1 : 2); ++h) {
+    const int n = n0 + co_l + (MODE == 0 ? 32 * h : 0);
     const int ci = c0 + ci_l + (NARROW ? 8 * h : 0);
     if (n >= Cout) continue;
     if (ci < Cin) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) atomicAdd(gw + (size_t)(ci * 9 + t) * CoutP + n, acc[h][t]);
     }
-    if (gb && ci_l == 0 && c0 == 0 && (!NARROW || h == 0)) atomicAdd(gb + n, bsum[h]);
+    if (gb && ci_l == 0 && c0 == 0 && (MODE == 0 || h == 0)) atomicAdd(gb + n, bsum[h]);
   }
 }
+
 }  // namespace wg
 
 // ---- small backward ops --------------------------------------------------------------------------------------------
@@ -374,8 +380,8 @@ extern "C" int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stri
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int CoutP = (Cout + 63) / 64 * 64;
-  const bool narrow = Cout <= 32 && Cin > 8;
-  const int KC = narrow ? 16 : 8, NC = narrow ? 32 : 64;
+  const int mode = (Cin <= 4 && Cout <= 16) ? 2 : ((Cout <= 32 && Cin > 8) ? 1 : 0);
+  const int KC = mode == 2 ? 4 : (mode == 1 ? 16 : 8), NC = mode == 2 ? 16 : (mode == 1 ? 32 : 64);
   const int nci = (Cin + KC - 1) / KC, nco = (Cout + NC - 1) / NC;
   const int ntiles = B * ((Ho + wg::TH - 1) / wg::TH) * ((Wo + wg::TW - 1) / wg::TW);
   // enough CTAs for ~3 waves of 2 per SM, at least 4 tiles per CTA so the two-stage pipeline has something to overlap
@@ -399,7 +405,7 @@ extern "C" int b2f_conv3x3_backward_weights(const float* x, int64_t x_batch_stri
   } while (0)
 #define B2F_WG2(S, V)                                                                                                 \
   do {                                                                                                                \
-    if (narrow) B2F_WG(S, V, true); else B2F_WG(S, V, false);                                                         \
+    if (mode == 2) B2F_WG(S, V, 2); else if (mode == 1) B2F_WG(S, V, 1); else B2F_WG(S, V, 0);                         \
   } while (0)
   if (stride == 1) {
     if (vec) B2F_WG2(1, true); else B2F_WG2(1, false);

@@ -49,6 +49,7 @@ CASES = [
     (2, 16, 20, 48, 32, 2),     # narrow weight-gradient form (Cout <= 32: 16 input x 32 output channels per CTA), stride 2
     (1, 24, 12, 32, 16, 1),     # narrow, ragged input-channel block, half the lanes without an output channel
     (1, 16, 10, 38, 16, 1),     # narrow, scalar staging (width not a multiple of 4)
+    (2, 2, 11, 37, 7, 2),       # first-layer form (Cin <= 3, Cout <= 16, stride 2) on odd sizes
     (1, 40, 9, 64, 70, 2),      # wide form, vector staging of a stride-2 input row (two 16-byte chunks per 4 pixels)
 ]
 
