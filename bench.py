@@ -465,8 +465,8 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
         return ms
 
     out["decoders"] = ("tcgen05 implicit GEMM, three-pass TF32 split over channel-minor (hi, lo) activations "
-                       "(b2f_conv3x3_tc_forward); so are the stride-1 pyramid layers with >= 64 channels; the other "
-                       "pyramid layers and the 2-channel heads on the FFMA2 kernel")
+                       "(b2f_conv3x3_tc_forward), the 2-channel heads included; so are the stride-1 pyramid layers with "
+                       ">= 64 channels; the other pyramid layers on the FFMA2 kernel")
     net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True, tensor_cores=True)
     p = net.plan(B, H_FULL, W_FULL)
     p.x.copy_(torch.randn(p.x.shape, device=dev))
@@ -632,19 +632,19 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
         return ms, losses
 
     for key, past_flow, topt in (("config2_hard", False, train.TrainOpt.hard()), ("config3_soft", True, train.TrainOpt.soft())):
-        # forward: the decoders and the stride-1 pyramid layers with >= 64 channels on tcgen05 (planar activations as
-        # second outputs for the backward plan, (hi, lo) weights re-packed from the flat parameters every step);
-        # backward: their input gradients (b2f_conv3x3_tc_backward_data) and weight gradients
-        # (b2f_conv3x3_tc_backward_weights) on tcgen05 too; heads and the other pyramid layers on the FFMA kernels
+        # forward: the decoders (heads included) and the stride-1 pyramid layers with >= 64 channels on tcgen05 ((hi, lo)
+        # weights re-packed from the flat parameters every step, one launch); backward: their input gradients
+        # (b2f_conv3x3_tc_backward_data), weight gradients (b2f_conv3x3_tc_backward_weights) and the input gradients
+        # of the stride-2 pyramid layers (b2f_conv3x3_tc_backward_data_s2) on tcgen05 too; the rest on the FFMA kernels
         net = pwc.PWCNet(pwc.Opt(past_flow=past_flow), device=dev, image_warps=True, tensor_cores=True, train_planar=True)
         res = {}
         for label, c in ((("with_allreduce", cm),) if world > 1 else ()) + (("local", None),):
             res[label], losses = timed(net, topt, c)
         step_ms = res.get("with_allreduce", res["local"])
         out[key] = {"ms_per_step": round(step_ms, 3), "samples_per_s": round(world * B / step_ms * 1e3, 1),
-                    "tensor_cores": "decoders and stride-1 pyramid layers with >= 64 channels on tcgen05 in forward, input "
-                                    "gradient and weight gradient (three-pass TF32 split); heads and the other pyramid "
-                                    "layers on the FFMA kernels",
+                    "tensor_cores": "decoders (heads included) and stride-1 pyramid layers with >= 64 channels on tcgen05 in "
+                                    "forward, input gradient and weight gradient, stride-2 pyramid layers in the input "
+                                    "gradient (three-pass TF32 split); the other pyramid work on the FFMA kernels",
                     "h2d_bytes_per_step": B * 9 * H * W * 4, "loss": round(losses["err"], 4),
                     "parameters": net.n_params(), "flat_gradient_floats": int(net.flat_params.numel())}
         if world > 1:
