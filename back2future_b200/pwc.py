@@ -31,6 +31,7 @@ from . import _lib
 
 FEAT = (3, 16, 32, 64, 96, 128, 192)      # featMaps (pwc.lua:89, d = 16)
 DEC = (128, 128, 96, 64, 32, 2)           # decoder(nChannels) widths (pwc.lua:76-85)
+SIDE_LANE_WGRAD = True                    # weight gradients on a side stream (tools/time_train.py --no-side measures without)
 TC_FEAT_MIN = 64                          # feature-pyramid layers with at least this many channels run on tcgen05
 
 
@@ -514,7 +515,7 @@ class PWCNet:
             cv = self._convs[name]
             assert cv.cin == cin
             ops.append((lib.b2f_conv3x3_backward_weights, (xin, xbs, gout, gbs, P(cv.gw), P(cv.gb), nb, cin, h, w, cv.cout,
-                                                           cv.stride)))
+                                                           cv.stride), 1))
 
         def dgrad(name, gout, gbs, act, abs_, gin, ibs, acc, nb, cin, h, w, slope=0.2, stride=None):
             cv = self._convs[name]
@@ -649,7 +650,7 @@ class PWCNet:
                     xh, xl, cx = hl_in[i]
                     ops.append((lib.b2f_conv3x3_tc_backward_weights,
                                 (P(xh), P(xl), cx, P(gh), P(gl), P(Gp) if Gp is not None else None, 0, P(cv.gw), P(cv.gb), B,
-                                 cv.cin, h, w, cv.cout)))
+                                 cv.cin, h, w, cv.cout), 1))
                     if i == 0:
                         break
                     cin, cout = DEC[i - 1], cv.cout
@@ -711,7 +712,7 @@ class PWCNet:
                 plan.keep += [gfh, gfl, g_tmp]
                 ops.append((lib.b2f_nhwc_split_from_bdhw, (P(gf), 0, P(gfh), P(gfl), 3 * B, c_out, h, w)))
                 ops.append((lib.b2f_conv3x3_tc_backward_weights,
-                            (P(th), P(tl), c_out, P(gfh), P(gfl), P(gf), 0, P(cv1.gw), P(cv1.gb), 3 * B, c_out, h, w, c_out)))
+                            (P(th), P(tl), c_out, P(gfh), P(gfl), P(gf), 0, P(cv1.gw), P(cv1.gb), 3 * B, c_out, h, w, c_out), 1))
                 if c_out in (64, 96, 128):      # one slice: the (hi, lo) form for the stride-2 input gradient below comes for free
                     gth, gtl = E(3 * B, h, w, c_out), E(3 * B, h, w, c_out)
                     plan.keep += [gth, gtl]
@@ -878,6 +879,7 @@ class _Plan:
         self.bgraph = None
         self.graph = None
         self._lanes = None
+        self._wlane = None
         self.n_launches = 0
 
     def launch(self):
@@ -909,8 +911,26 @@ class _Plan:
         self.n_launches = n
 
     def launch_backward(self, lo=0, hi=None):
-        """Issue bops[lo:hi] on the current stream."""
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        """Issue bops[lo:hi]: (fn, args) on the current stream; (fn, args, 1) -- the weight gradients, leaves of the
+        backward graph that only the all-reduce / Adam read -- on a side stream behind an event recorded at that point
+        of the current stream, joined at the end of the slice.  Every buffer such a call reads is written once per
+        step, so nothing later on the main stream can overwrite it; at the coarse levels, where no kernel fills the
+        machine, the weight gradients run under the input-gradient chain."""
+        cur = torch.cuda.current_stream()
+        st = C.c_void_p(cur.cuda_stream)
+        if self._wlane is None:
+            self._wlane = torch.cuda.Stream()
+        side, used = self._wlane, False
+        sst = C.c_void_p(side.cuda_stream)
         check = _lib.check
-        for fn, args in self.bops[lo:hi]:
-            check(fn(*args, st))
+        for op in self.bops[lo:hi]:
+            if len(op) == 3 and SIDE_LANE_WGRAD:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                check(op[0](*op[1], sst))
+                used = True
+            else:
+                check(op[0](*op[1], st))
+        if used:
+            cur.wait_stream(side)

@@ -30,9 +30,12 @@ ap.add_argument("--H", type=int, default=320)
 ap.add_argument("--W", type=int, default=640)
 ap.add_argument("--past-flow", action="store_true")
 ap.add_argument("--tc", action="store_true", help="tensor-core forward + input gradients (train_planar)")
+ap.add_argument("--no-side", action="store_true", help="weight gradients on the main stream")
 ap.add_argument("--detail", action="store_true", help="list every FFMA convolution call of the backward plan")
 a = ap.parse_args()
 lib = _lib.load()
+if a.no_side:
+    pwc.SIDE_LANE_WGRAD = False
 net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), tensor_cores=a.tc, train_planar=a.tc)
 x = torch.randn(a.B, 9, a.H, a.W, device="cuda")
 out = net.forward(x, graph=False)
@@ -62,7 +65,8 @@ if a.detail:
 name = {id(getattr(lib, n)): n for n in _lib.SIGNATURES}
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 agg = {}
-for fn, args in p.bops:
+for op in p.bops:
+    fn, args = op[0], op[1]
     ms = time_it(lambda: fn(*args, st), iters=3, warm=1)
     k = name.get(id(fn), "?")
     if k == "b2f_conv3x3_backward_weights":
