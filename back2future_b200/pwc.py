@@ -31,7 +31,7 @@ from . import _lib
 
 FEAT = (3, 16, 32, 64, 96, 128, 192)      # featMaps (pwc.lua:89, d = 16)
 DEC = (128, 128, 96, 64, 32, 2)           # decoder(nChannels) widths (pwc.lua:76-85)
-SIDE_LANE_WGRAD = True                    # weight gradients on a side stream (tools/time_train.py --no-side measures without)
+SIDE_LANES = True                         # backward plan on several streams (tools/time_train.py --no-side measures without)
 TC_FEAT_MIN = 64                          # feature-pyramid layers with at least this many channels run on tcgen05
 
 
@@ -612,10 +612,10 @@ class PWCNet:
             Jl, gJl = plan.J[l], gJ[l]
             jbs = Jl.stride(0)
 
-            def decoder_backward(kind, G, first):
+            def decoder_backward(kind, G, first, lane=0):
                 chain, cin0 = plan.dec[(kind, l)]
                 if self.train_planar:
-                    return decoder_backward_tc(kind, G, first, chain, cin0)
+                    return decoder_backward_tc(kind, G, first, chain, cin0, lane)
                 for i in range(5, -1, -1):
                     name = "%s.l%d.%d" % (kind, l, i)
                     if i > 0:
@@ -631,7 +631,7 @@ class PWCNet:
                     else:
                         dgrad(name, P(G), 0, None, 0, P(gJl), jbs, not first, B, cin, h, w)
 
-            def decoder_backward_tc(kind, G, first, chain, cin0):
+            def decoder_backward_tc(kind, G, first, chain, cin0, lane):
                 """The same walk on tcgen05: the 2-channel output gradient is split once into channel-minor (hi, lo);
                 the input gradients of layers 5..1 (b2f_conv3x3_tc_backward_data: the forward tensor-core kernel on
                 transposed, mirrored (hi, lo) weights, LeakyReLU derivative from the hi half of the layer's input) hand
@@ -641,7 +641,8 @@ class PWCNet:
                 input gradient (162 .. 356 channels) runs as slices of <= 128 channels into the joined gradient."""
                 hl_in = plan.dec_hl[(kind, l)]
                 gh, gl = E(B, h, w, 32), E(B, h, w, 32)
-                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(G), 0, P(gh), P(gl), B, 2, h, w)))
+                # `lane` != 0: this chain runs beside the main stream's; it starts behind what produced G there
+                ops.append((lib.b2f_nhwc_split_from_bdhw, (P(G), 0, P(gh), P(gl), B, 2, h, w), lane, (0,)))
                 plan.keep += [gh, gl]
                 Gp = G
                 for i in range(5, -1, -1):
@@ -650,7 +651,7 @@ class PWCNet:
                     xh, xl, cx = hl_in[i]
                     ops.append((lib.b2f_conv3x3_tc_backward_weights,
                                 (P(xh), P(xl), cx, P(gh), P(gl), P(Gp) if Gp is not None else None, 0, P(cv.gw), P(cv.gb), B,
-                                 cv.cin, h, w, cv.cout), 1))
+                                 cv.cin, h, w, cv.cout), 1, (lane,)))
                     if i == 0:
                         break
                     cin, cout = DEC[i - 1], cv.cout
@@ -660,14 +661,18 @@ class PWCNet:
                     # no planar copy of the gradient: the next weight-gradient call sums the bias gradient from (hi, lo)
                     ops.append((lib.b2f_conv3x3_tc_backward_data,
                                 (P(gh), P(gl), P(cv.tct_h), P(cv.tct_l), None, 0, P(xh), P(nh), P(nl), None, 0, B, cout,
-                                 h, w, cin, C.c_float(0.2), 0)))
+                                 h, w, cin, C.c_float(0.2), 0), lane))
                     gh, gl, Gp = nh, nl, None
                 # layer 0: 162 .. 356 input channels as slices of <= 128, straight into (or added to) the joined gradient
                 cv0 = self._convs["%s.l%d.0" % (kind, l)]
                 assert cv0.cin == cin0
-                ops.append((lib.b2f_conv3x3_tc_backward_data,
-                            (P(gh), P(gl), P(cv0.tct_h), P(cv0.tct_l), None, 0, None, None, None, P(gJl), jbs, B, cv0.cout, h,
-                             w, cin0, C.c_float(1.0), 0 if first else 1)))
+                last = (lib.b2f_conv3x3_tc_backward_data,
+                        (P(gh), P(gl), P(cv0.tct_h), P(cv0.tct_l), None, 0, None, None, None, P(gJl), jbs, B, cv0.cout, h,
+                         w, cin0, C.c_float(1.0), 0 if first else 1))
+                if lane == 0:
+                    ops.append(last)
+                    return None
+                return last         # the caller places it behind the occlusion decoder's write of the joined gradient
 
             # occlusion path: nearest^T, softmax^T, decoder (first: it reads every channel of J[l])
             g_occ = E(B, 2, h, w)
@@ -675,12 +680,22 @@ class PWCNet:
             g_logit = E(B, 2, h, w)
             ops.append((lib.b2f_softmax_channels_backward, (P(plan.occ[l]), P(g_occ), P(g_logit), B, 2, h, w)))
             plan.keep += [g_occ, g_logit]
-            decoder_backward("occ", g_logit, True)
-            for fi, kind in enumerate(("flow", "bflow")[:nflow]):
-                g_fs = E(B, 2, h, w)
-                plan.keep.append(g_fs)
-                ops.append((lib.b2f_upsample_bilinear2x_backward, (P(g_u[fi]), P(g_fs), B, 2, h, w, C.c_float(1.0), 0)))
-                decoder_backward(kind, g_fs, False)
+            g_fs = [E(B, 2, h, w) for _ in range(nflow)]
+            plan.keep += g_fs
+            for fi in range(nflow):
+                ops.append((lib.b2f_upsample_bilinear2x_backward, (P(g_u[fi]), P(g_fs[fi]), B, 2, h, w, C.c_float(1.0), 0)))
+            if self.train_planar:
+                # flow decoders' chains on lanes 2 / 3 beside the occlusion decoder's on the main stream; their last
+                # calls ADD into the joined gradient: behind the occlusion decoder's write, and one after the other
+                # (two concurrent reductions into the same words would make the sum's rounding order a race)
+                lasts = [decoder_backward(kind, g_fs[fi], False, lane=2 + fi) for fi, kind in enumerate(("flow", "bflow")[:nflow])]
+                decoder_backward("occ", g_logit, True)
+                for fi, last in enumerate(lasts):
+                    ops.append((last[0], last[1], 2 + fi, (0,) + tuple(range(2, 2 + fi))))
+            else:
+                decoder_backward("occ", g_logit, True)
+                for fi, kind in enumerate(("flow", "bflow")[:nflow]):
+                    decoder_backward(kind, g_fs[fi], False)
             # cost volumes: gradRef of both directions + the joined input's feature slice -> reference features
             ref = sl(plan.feats[l], 2 * B)
             tmp_ref, tmp_frm = E(B, Cl, h, w), E(B, Cl, h, w)
@@ -690,7 +705,8 @@ class PWCNet:
                 frame = sl(plan.feats[l], slot * B) if l == levels else sl(plan.warped[l], slot * B)
                 gfrm = P(tmp_frm) if l == levels else sl(g_warped[l], slot * B)
                 ops.append((lib.b2f_costvol_backward, (_lib.ptr_array([ref.value, frame.value]), 2, B, Cl, h, w, win, fwd,
-                                                       sl(gJl, 0, c0), jbs, _lib.ptr_array([tmp_ref.data_ptr(), gfrm.value]))))
+                                                       sl(gJl, 0, c0), jbs, _lib.ptr_array([tmp_ref.data_ptr(), gfrm.value])),
+                            0, (2, 3)))
                 axpy(sl(g_feats[l], 2 * B), 0, P(tmp_ref), 0, B * n_item, 1)
                 if l == levels:
                     axpy(sl(g_feats[l], slot * B), 0, P(tmp_frm), 0, B * n_item, 1)
@@ -879,7 +895,7 @@ class _Plan:
         self.bgraph = None
         self.graph = None
         self._lanes = None
-        self._wlane = None
+        self._blanes = None
         self.n_launches = 0
 
     def launch(self):
@@ -911,26 +927,34 @@ class _Plan:
         self.n_launches = n
 
     def launch_backward(self, lo=0, hi=None):
-        """Issue bops[lo:hi]: (fn, args) on the current stream; (fn, args, 1) -- the weight gradients, leaves of the
-        backward graph that only the all-reduce / Adam read -- on a side stream behind an event recorded at that point
-        of the current stream, joined at the end of the slice.  Every buffer such a call reads is written once per
-        step, so nothing later on the main stream can overwrite it; at the coarse levels, where no kernel fills the
-        machine, the weight gradients run under the input-gradient chain."""
+        """Issue bops[lo:hi].  An entry is (fn, args[, lane[, deps]]): lane 0 is the current stream; lane 1 carries the
+        weight gradients (leaves of the backward graph that only the all-reduce / Adam read); lanes 2, 3 the input-
+        gradient chains of the flow decoders, which are independent of the occlusion decoder's until both add into the
+        joined gradient.  `deps` = lanes whose work issued so far the call must wait for (an event recorded at that
+        point; default: lane 0 for a weight gradient, nothing otherwise -- a lane is ordered in itself).  All lanes
+        are joined into the current stream at the end of the slice.  Every buffer a side-lane call reads is written
+        once per step, so nothing later on another lane can overwrite it; at the coarse levels, where no kernel fills
+        the machine, the chains and the weight gradients run under each other."""
         cur = torch.cuda.current_stream()
-        st = C.c_void_p(cur.cuda_stream)
-        if self._wlane is None:
-            self._wlane = torch.cuda.Stream()
-        side, used = self._wlane, False
-        sst = C.c_void_p(side.cuda_stream)
+        if self._blanes is None:
+            self._blanes = {k: torch.cuda.Stream() for k in (1, 2, 3)}
+        streams = {0: cur}
+        streams.update(self._blanes)
+        handles = {k: C.c_void_p(v.cuda_stream) for k, v in streams.items()}
+        used = set()
         check = _lib.check
         for op in self.bops[lo:hi]:
-            if len(op) == 3 and SIDE_LANE_WGRAD:
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                side.wait_event(ev)
-                check(op[0](*op[1], sst))
-                used = True
-            else:
-                check(op[0](*op[1], st))
-        if used:
-            cur.wait_stream(side)
+            lane = op[2] if len(op) > 2 else 0
+            deps = op[3] if len(op) > 3 else ((0,) if lane == 1 else ())
+            if not SIDE_LANES:
+                lane, deps = 0, ()
+            for d in deps:
+                if d != lane and (d == 0 or d in used):
+                    ev = torch.cuda.Event()
+                    ev.record(streams[d])
+                    streams[lane].wait_event(ev)
+            check(op[0](*op[1], handles[lane]))
+            if lane:
+                used.add(lane)
+        for lane in used:
+            cur.wait_stream(streams[lane])

@@ -35,7 +35,7 @@ ap.add_argument("--detail", action="store_true", help="list every FFMA convoluti
 a = ap.parse_args()
 lib = _lib.load()
 if a.no_side:
-    pwc.SIDE_LANE_WGRAD = False
+    pwc.SIDE_LANES = False
 net = pwc.PWCNet(pwc.Opt(past_flow=a.past_flow), tensor_cores=a.tc, train_planar=a.tc)
 x = torch.randn(a.B, 9, a.H, a.W, device="cuda")
 out = net.forward(x, graph=False)
