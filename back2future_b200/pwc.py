@@ -896,6 +896,7 @@ class _Plan:
         self.graph = None
         self._lanes = None
         self._blanes = None
+        self._bused = set()
         self.n_launches = 0
 
     def launch(self):
@@ -926,13 +927,14 @@ class _Plan:
             cur.wait_stream(lanes[lane])
         self.n_launches = n
 
-    def launch_backward(self, lo=0, hi=None):
+    def launch_backward(self, lo=0, hi=None, join=True):
         """Issue bops[lo:hi].  An entry is (fn, args[, lane[, deps]]): lane 0 is the current stream; lane 1 carries the
         weight gradients (leaves of the backward graph that only the all-reduce / Adam read); lanes 2, 3 the input-
         gradient chains of the flow decoders, which are independent of the occlusion decoder's until both add into the
         joined gradient.  `deps` = lanes whose work issued so far the call must wait for (an event recorded at that
         point; default: lane 0 for a weight gradient, nothing otherwise -- a lane is ordered in itself).  All lanes
-        are joined into the current stream at the end of the slice.  Every buffer a side-lane call reads is written
+        are joined into the current stream at the end of the slice unless join=False (the data-parallel step issues
+        the plan bucket by bucket and lets only the COMMUNICATION stream wait for the lanes: `backward_streams()`).  Every buffer a side-lane call reads is written
         once per step, so nothing later on another lane can overwrite it; at the coarse levels, where no kernel fills
         the machine, the chains and the weight gradients run under each other."""
         cur = torch.cuda.current_stream()
@@ -941,7 +943,9 @@ class _Plan:
         streams = {0: cur}
         streams.update(self._blanes)
         handles = {k: C.c_void_p(v.cuda_stream) for k, v in streams.items()}
-        used = set()
+        if lo == 0:
+            self._bused = set()
+        used = self._bused
         check = _lib.check
         for op in self.bops[lo:hi]:
             lane = op[2] if len(op) > 2 else 0
@@ -956,5 +960,11 @@ class _Plan:
             check(op[0](*op[1], handles[lane]))
             if lane:
                 used.add(lane)
-        for lane in used:
-            cur.wait_stream(streams[lane])
+        if join:
+            for lane in used:
+                cur.wait_stream(streams[lane])
+            used.clear()
+
+    def backward_streams(self):
+        """The side streams that carry un-joined work of the backward plan (after launch_backward(..., join=False))."""
+        return [self._blanes[k] for k in sorted(self._bused)] if self._blanes else []

@@ -210,12 +210,14 @@ class Trainer:
         if self.comm is None or self.comm.world == 1:
             return [(lambda: (head(), p.launch_backward()), None)]
         segs, lo = [], 0
+        nb = len(p.bucket_marks)
         for k, (idx, rng) in enumerate(p.bucket_marks):
             a, b = lo, idx
+            last = k == nb - 1       # only the last slice joins the plan's side streams into the main one
             if k == 0:
-                segs.append((lambda a=a, b=b: (head(), p.launch_backward(a, b)), rng))
+                segs.append((lambda a=a, b=b, last=last: (head(), p.launch_backward(a, b, join=last)), rng))
             else:
-                segs.append((lambda a=a, b=b: p.launch_backward(a, b), rng))
+                segs.append((lambda a=a, b=b, last=last: p.launch_backward(a, b, join=last), rng))
             lo = idx
         assert lo == len(p.bops)
         return segs
@@ -261,9 +263,12 @@ class Trainer:
                     for fn, rng in segs:
                         fn()
                         if multi and rng is not None:
-                            ev = torch.cuda.Event()
-                            ev.record(cap)
-                            self._comm_stream.wait_event(ev)
+                            # the bucket is final once the main stream AND the plan's side streams (weight gradients,
+                            # flow-decoder chains) have reached this point; only the communication stream waits
+                            for s_ in [cap] + st.plan.backward_streams():
+                                ev = torch.cuda.Event()
+                                ev.record(s_)
+                                self._comm_stream.wait_event(ev)
                             self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
                     if multi:
                         cap.wait_stream(self._comm_stream)
@@ -274,9 +279,10 @@ class Trainer:
                 for fn, rng in segs:
                     fn()
                     if multi and rng is not None:
-                        ev = torch.cuda.Event()
-                        ev.record(cur)
-                        self._comm_stream.wait_event(ev)
+                        for s_ in [cur] + st.plan.backward_streams():
+                            ev = torch.cuda.Event()
+                            ev.record(s_)
+                            self._comm_stream.wait_event(ev)
                         self.comm.allreduce_sum(net.flat_grads, rng[0], rng[1], stream=self._comm_stream)
                 if multi:
                     cur.wait_stream(self._comm_stream)

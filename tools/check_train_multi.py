@@ -33,7 +33,15 @@ dist.all_gather(ref, gg)
 same = max(rel(r, ref[0]) for r in ref)
 print("rank %d: loss graph %.6f eager %.6f | grads graph vs eager %.2e | params %.2e | grads across ranks %.2e"
       % (rank, lg, le, rel(gg, ge), rel(pg, pe), same), flush=True)
-ok = rel(gg, ge) < 1e-4 and rel(pg, pe) < 1e-4 and same == 0.0
+# Parameters after two Adam steps: the update of an element is lr * m / (sqrt(v) + eps), i.e. ~ +-lr whatever the size
+# of its gradient, so an element whose gradient is at the level of the run-to-run rounding noise (atomic order: 1e-7
+# of the largest gradient) can move by 2 lr the other way.  Bound: no element differs by more than 2 lr per step, and
+# all but a vanishing fraction agree to 1e-4.
+lr = train.TrainOpt.hard().LR
+dp = (pg - pe).abs()
+frac = (dp > 1e-4 * pe.abs().max()).float().mean().item()
+print("rank %d: params max abs diff %.2e (bound %.2e), fraction beyond 1e-4: %.2e" % (rank, dp.max().item(), 4.04 * lr, frac), flush=True)
+ok = rel(gg, ge) < 1e-4 and dp.max().item() <= 4.04 * lr and frac < 1e-3 and same == 0.0
 dist.barrier()
 cm.destroy()
 dist.destroy_process_group()
