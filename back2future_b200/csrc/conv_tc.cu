@@ -152,6 +152,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x, b = blockIdx.y;
   const int x0 = tx * TW, y0 = ty * TH;
+  // blockIdx.z = slice of N output columns of a wider convolution (the first decoder layer's input gradient has 196 ..
+  // 356 channels; at the coarse levels, where a launch has fewer tiles than the machine has SMs, every layer is cut into
+  // 32- or 64-column slices so that the serial MMA chain of a CTA is shorter and there are more CTAs)
+  const int nz = blockIdx.z * N;
 
   if (threadIdx.x == 0) {
     TC_STAMP(0);
@@ -182,8 +186,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       const int s = bs % NB, c = bs / 9, t = bs % 9;
       if (bs >= NB) mbar_wait(&b_empty[s], ((bs / NB) - 1) & 1);
       mbar_arrive_expect_tx(&b_full[s], 2 * cfg::B_BYTES);
-      tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, a.n0, t, 0, &b_full[s]);
-      tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, a.n0, t, 0, &b_full[s]);
+      tma_load_4d(b_buf + s * cfg::B_SLOT, &tm_wh, c * 32, a.n0 + nz, t, 0, &b_full[s]);
+      tma_load_4d(b_buf + s * cfg::B_SLOT + cfg::B_BYTES, &tm_wl, c * 32, a.n0 + nz, t, 0, &b_full[s]);
     }
   } else if (warp == 2 && lane == 0) {
     // ---- TMA producer, input patches: its own thread, so that the patch of chunk c + 1 is requested the moment
@@ -268,11 +272,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
         if (a.accumulate) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (32 * g + j < a.Cout) atomicAdd(o + (size_t)(32 * g + j) * cs, __uint_as_float(v[j]));
+            if (nz + 32 * g + j < a.Cout) atomicAdd(o + (size_t)(nz + 32 * g + j) * cs, __uint_as_float(v[j]));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * cs] = __uint_as_float(v[j]);
+            if (nz + 32 * g + j < a.Cout) o[(size_t)(nz + 32 * g + j) * cs] = __uint_as_float(v[j]);
         }
       }
     }
@@ -283,7 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     float mk2[MASK == 2 ? 32 : 1];
     if (MASK == 2) {      // requested before the accumulator read so that the two latencies overlap
       const float4* mp = reinterpret_cast<const float4*>(a.mask_hi + (((size_t)b * a.H + (inside ? y : 0)) * a.W + (inside ? x : 0)) * a.mcp +
-                                                         a.n0 + 32 * g);
+                                                         a.n0 + nz + 32 * g);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 t4 = inside ? __ldg(mp + q) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -294,7 +298,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int n = 32 * g + j;
+      const int n = nz + 32 * g + j;
       float t = __uint_as_float(v[j]) + ((a.bias && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
       if (MASK == 2) {
         t = mk2[j] > 0.f ? t : t * a.slope;
@@ -313,11 +317,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
         // so that the thread does not wait for 32 strided loads
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (32 * g + j < a.Cout) atomicAdd(o + (size_t)(32 * g + j) * a.H * a.W, f[j]);
+          if (nz + 32 * g + j < a.Cout) atomicAdd(o + (size_t)(nz + 32 * g + j) * a.H * a.W, f[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (32 * g + j < a.Cout) o[(size_t)(32 * g + j) * a.H * a.W] = f[j];
+          if (nz + 32 * g + j < a.Cout) o[(size_t)(nz + 32 * g + j) * a.H * a.W] = f[j];
       }
     }
     if (a.store_split) {
@@ -346,8 +350,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_consta
       fence_proxy_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) {
-        tma_store_4d_addr(rh0, &tm_oh, 32 * g, x0, y0, b);
-        tma_store_4d_addr(rh0 + TH * TW * 128, &tm_ol, 32 * g, x0, y0, b);
+        tma_store_4d_addr(rh0, &tm_oh, nz + 32 * g, x0, y0, b);
+        tma_store_4d_addr(rh0 + TH * TW * 128, &tm_ol, nz + 32 * g, x0, y0, b);
         tma_store_commit();
       }
     }
@@ -449,7 +453,7 @@ __global__ void pack_tc_from_packed_batch_kernel(const PackJob* __restrict__ job
 
 template <int N, int MASK, bool S2 = false>
 int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl, float* oh, float* ol, const Args& a0, int B,
-              int CinP, int CoutP, cudaStream_t st, int wrows_total = 0) {
+              int CinP, int CoutP, cudaStream_t st, int wrows_total = 0, int nslices = 1) {
   using cfg = Cfg<N, S2>;
   Args a = a0;
   CUtensorMap txh, txl, twh, twl, toh, tol;
@@ -489,7 +493,7 @@ int launch_tc(const float* xh, const float* xl, const float* wh, const float* wl
   }
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
-  dim3 grid(a.tiles_x * a.tiles_y, B);
+  dim3 grid(a.tiles_x * a.tiles_y, B, nslices);
   kern<<<grid, THREADS, cfg::SMEM_BYTES, st>>>(txh, txl, twh, twl, toh, tol, a);
   B2F_CHECK_LAUNCH("conv3x3_tc_kernel");
   return B2F_OK;
@@ -562,16 +566,35 @@ extern "C" int b2f_nhwc_split_from_bdhw(const float* x, int64_t x_batch_stride, 
   return B2F_OK;
 }
 
+// Slice width (the kernel's N) and number of slices for `width` output columns over `ctas` = tiles x images CTAs per
+// slice.  A machine-filling launch takes the widest slices (fewest re-reads of the input patch): <= 128 columns in one,
+// more in ceil(width / 128) balanced ones.  A launch with fewer CTAs than SMs is latency-bound on the serial MMA chain
+// of its CTAs (a 128 -> 128 layer takes 36 us at 5 x 10, 10 x 20 and 20 x 40 alike): 32-column slices.
+static void tc_slices(int width, int ctas, int* ns, int* nslices) {
+  const int w32 = (width + 31) / 32 * 32;
+  int n;
+  if (w32 <= 32) n = 32;
+  else if (ctas < 100) n = 32;      // (64-column slices at 240 CTAs measured 25 % SLOWER than one 128-column slice)
+  else {
+    const int z = (w32 + 127) / 128;
+    n = ((w32 + z - 1) / z + 31) / 32 * 32;
+  }
+  if (n > w32) n = w32;
+  *ns = n;
+  *nslices = (w32 + n - 1) / n;
+}
+
 template <int MASK>
 static int tc_dispatch(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, float* out_hi, float* out_lo,
-                       const tc::Args& a, int B, int Cin, int Cout, cudaStream_t st, const char* who, int wrows_total = 0) {
-  const int CinP = (Cin + 31) / 32 * 32, CoutP = (Cout + 31) / 32 * 32;
-  switch (Cout) {
-    case 32: return tc::launch_tc<32, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
-    case 64: return tc::launch_tc<64, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
-    case 96: return tc::launch_tc<96, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
-    case 128: return tc::launch_tc<128, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total);
-    default: return fail(B2F_EUNSUPPORTED, "%s: Cout = %d is not one of the decoder widths (32, 64, 96, 128)", who, Cout);
+                       const tc::Args& a, int B, int Cin, int N, int nslices, int width, cudaStream_t st, const char* who,
+                       int wrows_total) {
+  const int CinP = (Cin + 31) / 32 * 32, CoutP = (width + 31) / 32 * 32;
+  switch (N) {
+    case 32: return tc::launch_tc<32, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total, nslices);
+    case 64: return tc::launch_tc<64, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total, nslices);
+    case 96: return tc::launch_tc<96, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total, nslices);
+    case 128: return tc::launch_tc<128, MASK>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, CinP, CoutP, st, wrows_total, nslices);
+    default: return fail(B2F_EUNSUPPORTED, "%s: slice width %d", who, N);
   }
 }
 
@@ -589,9 +612,6 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
   if (!aligned16(g_hi) || !aligned16(g_lo) || !aligned16(wt_hi) || !aligned16(wt_lo) || (gin_hi && (!aligned16(gin_hi) || !aligned16(gin_lo))))
     return fail(B2F_EALIGN, "conv3x3_tc_backward_data: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: cuTensorMapEncodeTiled not available");
-  const bool one = Cin == 32 || Cin == 64 || Cin == 96 || Cin == 128;
-  if (!one && (gin_hi || !gin_planar))
-    return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data: Cin = %d runs as slices of <= 128 channels, planar output only", Cin);
   if (accumulate && !gin_planar) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: accumulate needs the planar output");
   if (act && act_hi) return fail(B2F_EINVAL, "conv3x3_tc_backward_data: act (planar) and act_hi (channel-minor) are alternatives");
   if (act_hi && !aligned16(act_hi)) return fail(B2F_EALIGN, "conv3x3_tc_backward_data: act_hi must be 16-byte aligned");
@@ -599,31 +619,26 @@ extern "C" int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t pbs = gin_planar_batch_stride ? gin_planar_batch_stride : (int64_t)Cin * H * W;
   const int64_t mbs = act_batch_stride ? act_batch_stride : (int64_t)Cin * H * W;
-  // slices of the input channels: 128 at a time, the last one as the smallest decoder width that holds the rest
-  for (int n0 = 0; n0 < Cin; n0 += 128) {
-    const int rest = Cin - n0;
-    const int N = rest >= 128 ? 128 : (rest + 31) / 32 * 32;
-    tc::Args a{};
-    a.trace = tc::g_tc_trace;
-    a.bias = nullptr;
-    a.out_planar = gin_planar ? gin_planar + (size_t)n0 * H * W : nullptr;
-    a.pbs = pbs;
-    a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
-    a.Cout = std::min(N, rest); a.H = H; a.W = W; // valid channels of this slice (N = its width as a tensor-core shape)
-    a.slope = (act || act_hi) ? leaky_slope : 1.f;
-    a.store_split = gin_hi != nullptr;
-    a.mask = act ? act + (size_t)n0 * H * W : nullptr;
-    a.mbs = mbs;
-    a.mask_hi = act_hi;
-    a.mcp = (Cin + 31) / 32 * 32;
-    a.n0 = n0;
-    a.accumulate = accumulate;
-    const int rc = act_hi ? tc_dispatch<2>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
-                   : act  ? tc_dispatch<1>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin)
-                          : tc_dispatch<0>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, st, "conv3x3_tc_backward_data", Cin);
-    if (rc) return rc;
-  }
-  return B2F_OK;
+  int N, nslices;
+  tc_slices(Cin, ((W + tc::TW - 1) / tc::TW) * ((H + tc::TH - 1) / tc::TH) * B, &N, &nslices);
+  tc::Args a{};
+  a.trace = tc::g_tc_trace;
+  a.bias = nullptr;
+  a.out_planar = gin_planar;
+  a.pbs = pbs;
+  a.nchunk = ((Cout + 31) / 32 * 32) / 32;      // K = the forward layer's output channels
+  a.Cout = Cin; a.H = H; a.W = W;               // valid output columns of the launch
+  a.slope = (act || act_hi) ? leaky_slope : 1.f;
+  a.store_split = gin_hi != nullptr;
+  a.mask = act;
+  a.mbs = mbs;
+  a.mask_hi = act_hi;
+  a.mcp = (Cin + 31) / 32 * 32;
+  a.n0 = 0;
+  a.accumulate = accumulate;
+  return act_hi ? tc_dispatch<2>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, nslices, Cin, st, "conv3x3_tc_backward_data", Cin)
+         : act  ? tc_dispatch<1>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, nslices, Cin, st, "conv3x3_tc_backward_data", Cin)
+                : tc_dispatch<0>(g_hi, g_lo, wt_hi, wt_lo, gin_hi, gin_lo, a, B, Cout, N, nslices, Cin, st, "conv3x3_tc_backward_data", Cin);
 }
 
 // Input gradient of a STRIDE-2 3x3 convolution (the down-sampling layers of the feature pyramid) on the tensor cores:
@@ -641,7 +656,9 @@ extern "C" int b2f_conv3x3_tc_backward_data_s2(const float* g_hi, const float* g
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_backward_data_s2: cuTensorMapEncodeTiled not available");
   if (B == 0) return B2F_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int N = (Cin + 31) / 32 * 32, KP = (Cout + 31) / 32 * 32;
+  const int KP = (Cout + 31) / 32 * 32;
+  int N, nslices;
+  tc_slices(Cin, ((Wo + tc::TW - 1) / tc::TW) * ((Ho + tc::TH - 1) / tc::TH) * B, &N, &nslices);
   tc::Args a{};
   a.trace = tc::g_tc_trace;
   a.out_planar = gin_planar;
@@ -650,11 +667,12 @@ extern "C" int b2f_conv3x3_tc_backward_data_s2(const float* g_hi, const float* g
   a.Cout = Cin; a.H = Ho; a.W = Wo; a.H2 = H; a.W2 = W;
   a.slope = 1.f;
   a.accumulate = accumulate;
+  const int NP = (Cin + 31) / 32 * 32;
   switch (N) {
-    case 32: return tc::launch_tc<32, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
-    case 64: return tc::launch_tc<64, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
-    case 96: return tc::launch_tc<96, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
-    default: return tc::launch_tc<128, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, N, st, Cin);
+    case 32: return tc::launch_tc<32, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, NP, st, Cin, nslices);
+    case 64: return tc::launch_tc<64, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, NP, st, Cin, nslices);
+    case 96: return tc::launch_tc<96, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, NP, st, Cin, nslices);
+    default: return tc::launch_tc<128, 0, true>(g_hi, g_lo, wt_hi, wt_lo, nullptr, nullptr, a, B, KP, NP, st, Cin, nslices);
   }
 }
 
@@ -671,28 +689,22 @@ extern "C" int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, cons
     return fail(B2F_EALIGN, "conv3x3_tc_forward: operands must be 16-byte aligned");
   if (get_encode_fn() == nullptr) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: cuTensorMapEncodeTiled not available");
   if (B == 0) return B2F_OK;
-  const bool one = Cout <= 128;
-  if (!one && out_hi) return fail(B2F_EUNSUPPORTED, "conv3x3_tc_forward: Cout = %d runs as slices of <= 128 channels, planar output only", Cout);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int CinP = (Cin + 31) / 32 * 32;
+  (void)CinP;
   const int64_t pbs = out_planar_batch_stride ? out_planar_batch_stride : (int64_t)Cout * H * W;
-  // output-channel slices: 128 at a time, the last one as the smallest decoder width that holds the rest (a 16-channel
-  // pyramid layer is one 32-wide slice with 16 valid channels)
-  for (int n0 = 0; n0 < Cout; n0 += 128) {
-    const int rest = Cout - n0;
-    const int N = rest >= 128 ? 128 : (rest + 31) / 32 * 32;
-    tc::Args a{};
-    a.trace = tc::g_tc_trace;
-    a.bias = bias ? bias + n0 : nullptr;
-    a.out_planar = out_planar ? out_planar + (size_t)n0 * H * W : nullptr;
-    a.pbs = pbs;
-    a.nchunk = CinP / 32;
-    a.Cout = std::min(N, rest); a.H = H; a.W = W;
-    a.slope = leaky_slope;
-    a.store_split = out_hi != nullptr;
-    a.n0 = n0;
-    const int rc = tc_dispatch<0>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, N, st, "conv3x3_tc_forward", Cout);
-    if (rc) return rc;
-  }
-  return B2F_OK;
+  // output-channel slices in ONE launch (blockIdx.z): tc_slices
+  int N, nslices;
+  tc_slices(Cout, ((W + tc::TW - 1) / tc::TW) * ((H + tc::TH - 1) / tc::TH) * B, &N, &nslices);
+  tc::Args a{};
+  a.trace = tc::g_tc_trace;
+  a.bias = bias;
+  a.out_planar = out_planar;
+  a.pbs = pbs;
+  a.nchunk = ((Cin + 31) / 32 * 32) / 32;
+  a.Cout = Cout; a.H = H; a.W = W;
+  a.slope = leaky_slope;
+  a.store_split = out_hi != nullptr;
+  a.n0 = 0;
+  return tc_dispatch<0>(x_hi, x_lo, w_hi, w_lo, out_hi, out_lo, a, B, Cin, N, nslices, Cout, st, "conv3x3_tc_forward", Cout);
 }

@@ -247,7 +247,9 @@ B2F_API int b2f_softmax_channels_forward(const float* x, float* out, int B, int 
  * tensors; b2f_nhwc_split_from_bdhw converts a planar (B, C, H, W) tensor (batch-strided: the decoder's joined input).
  * Weights: [9 taps][Cout][Cin_p] hi / lo, b2f_conv3x3_tc_packed_floats(Cin, Cout) floats each.
  * Outputs: out_hi / out_lo (both or neither; (B, H, W, Cout rounded up to 32)) for the next tensor-core layer and / or
- * out_planar (B, Cout, H, W) fp32 with its batch stride (0 = dense) for every other consumer.  Cout in {32, 64, 96, 128}. */
+ * out_planar (B, Cout, H, W) fp32 with its batch stride (0 = dense) for every other consumer.  Any Cout: the
+ * output columns run as slices of 32 .. 128 of ONE launch (wide layers; and coarse levels, where narrow slices shorten the
+ * serial MMA chain of a launch that cannot fill the machine).                                                          */
 B2F_API int64_t b2f_conv3x3_tc_packed_floats(int Cin, int Cout);
 /* Measurement hook (thread-local): while a device buffer of 16 x (number of CTAs) uint64 is registered, every CTA of
  * b2f_conv3x3_tc_forward stores clock64 stamps of its phases there (tools/tc_trace.py); NULL switches it off.        */
@@ -284,8 +286,8 @@ B2F_API int b2f_conv3x3_tc_forward(const float* x_hi, const float* x_lo, const f
  * (B, H, W, Cin rounded up to 32) -- hi = x & 0xFFFFE000 has the sign of every normal float, and a pixel's channels
  * are one 128-byte line per 32 instead of 32 strided words.  Outputs
  * as b2f_conv3x3_tc_forward: (hi, lo) channel-minor for the next tensor-core input gradient and / or planar fp32 for
- * the weight-gradient kernel.  Cin in {32, 64, 96, 128}; any other Cin (the first decoder layer: 162 .. 356) runs as
- * slices of <= 128 input channels with the planar output only.  accumulate != 0: the planar result is ADDED to
+ * the weight-gradient kernel.  Any Cin (the first decoder layer: 162 .. 356): slices of one launch, as in the
+ * forward.  accumulate != 0: the planar result is ADDED to
  * gin_planar (nngraph's gradient accumulation at the joined decoder input).                                            */
 B2F_API int b2f_conv3x3_tc_backward_data(const float* g_hi, const float* g_lo, const float* wt_hi, const float* wt_lo,
                                          const float* act, int64_t act_batch_stride, const float* act_hi, float* gin_hi,

@@ -58,6 +58,9 @@ CASES = [
     (1, 96, 9, 20, 64),
     (1, 64, 7, 16, 32),
     (1, 354, 7, 16, 128),      # coarsest level
+    (2, 64, 10, 20, 192),      # more than 128 output channels: slices of one launch (blockIdx.z), (hi, lo) outputs too
+    (8, 128, 20, 40, 128),     # 72 tiles: 32-column slices
+    (8, 96, 40, 80, 96),       # 240 tiles: one slice again
     (1, 32, 30, 50, 64),       # ragged in both directions
 ]
 
@@ -94,9 +97,8 @@ def test_conv3x3_tc_rejects_bad_arguments():
     o = torch.zeros(1, 8, 8, 32, device="cuda")
     assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), None, None, 0, 1, 32, 8, 8, 32, 0.2, _st()) != 0
     assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, None, None, None, 0, 1, 32, 8, 8, 32, 0.2, _st()) != 0
-    # more than 128 output channels run as slices with the planar output only
-    assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), _p(o), None, 0, 1, 32, 8, 8, 192, 0.2, _st()) != 0
-    assert b"Cout" in lib.b2f_last_error()
+    assert lib.b2f_conv3x3_tc_forward(_p(t), _p(t), _p(w), _p(w), None, _p(o), _p(o), None, 0, 1, 32, 0, 8, 32, 0.2, _st()) != 0
+    assert b"bad size" in lib.b2f_last_error()
     # the weight gradient's activation tensor must hold at least the convolution's input channels
     assert lib.b2f_conv3x3_tc_backward_weights(_p(t), _p(t), 16, _p(o), _p(o), None, 0, _p(w), None, 1, 32, 8, 8, 32, _st()) != 0
 
