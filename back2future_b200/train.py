@@ -87,6 +87,8 @@ class Trainer:
         self.lib = net.lib
         self._steps = {}
         self._comm_stream = torch.cuda.Stream(net.device) if comm is not None and comm.world > 1 else None
+        self._copy_stream = None
+        self._staged, self._stage_buf = {}, {}
         self.batchNumber = 0
 
     # ---- the step's criterion calls -----------------------------------------------------------------------
@@ -228,10 +230,17 @@ class Trainer:
             fn()
 
     # ---- trainBatch ---------------------------------------------------------------------------------------
-    def train_batch(self, inputs, graph=True, step=True):
+    def train_batch(self, inputs, graph=True, step=True, prefetch=None):
         """One optimisation step on `inputs` (B, 9, H, W) (host or device float32).  Returns the weighted losses of
         THIS rank's shard {err, pme, sflow, socc, gocc, cvel} (train.lua:471, 497-517).  `step=False` stops after the
-        gradient (flat_grads), for tests."""
+        gradient (flat_grads), for tests.
+
+        `prefetch`: the NEXT step's inputs (a pinned host tensor of the same shape, not modified until that step has
+        been issued).  Their upload is started on a copy stream as soon as this step's work is enqueued, into a staging
+        buffer, and the next `train_batch` called with that very tensor takes the staged copy (one device-to-device
+        copy) instead of uploading again: the 59 MB upload of a step (1.1 ms over PCIe, a twelfth of the step) runs under
+        the previous step's kernels -- the double buffering that the reference's loader threads give `trainBatch`
+        (train.lua:168-189, donkeys) on the host side."""
         net = self.net
         B, nine, H, W = inputs.shape
         key = (B, H, W)
@@ -241,8 +250,15 @@ class Trainer:
                 # the library's loss scratch must exist before a capture
                 _lib.check(self.lib.b2f_reserve_scratch(1 << 20))
             st = self._steps[key]
-            st.plan.x.copy_(inputs, non_blocking=True)
             cur = torch.cuda.current_stream()
+            pf = self._staged.pop(key, None)
+            if pf is not None and pf[2] is inputs:
+                cur.wait_event(pf[1])
+                st.plan.x.copy_(pf[0], non_blocking=True)
+            else:
+                st.plan.x.copy_(inputs, non_blocking=True)
+            x_taken = torch.cuda.Event()
+            x_taken.record(cur)
             segs = self._segments(st)
             multi = self.comm is not None and self.comm.world > 1
             if graph and st.graph is None:
@@ -288,6 +304,20 @@ class Trainer:
                     cur.wait_stream(self._comm_stream)
             if step:
                 net.adam_step(self.opt.LR, self.opt.beta1, self.opt.beta2, self.opt.epsilon, self.opt.weightDecay)
+            if prefetch is not None:
+                if tuple(prefetch.shape) != tuple(inputs.shape) or prefetch.is_cuda:
+                    raise ValueError("train_batch: prefetch must be a host tensor shaped like inputs")
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(net.device)
+                buf = self._stage_buf.get(key)
+                if buf is None:
+                    buf = self._stage_buf[key] = torch.empty(inputs.shape, device=net.device, dtype=torch.float32)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(x_taken)        # the staging buffer has been read by this step
+                    buf.copy_(prefetch, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                self._staged[key] = (buf, ev, prefetch)
             st.loss_host.copy_(st.loss_dev, non_blocking=True)
             cur.synchronize()                                          # cutorch.synchronize(), train.lua:498
         self.batchNumber += 1

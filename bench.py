@@ -602,7 +602,8 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
 def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
     """One optimisation step of train.lua:196-496 through back2future_b200.train.Trainer at the reference's training
     shape (8 samples per GPU, 9 x 320 x 640), inputs uploaded from pinned host memory every step (inside the timed
-    region), losses read back every step (cutorch.synchronize, train.lua:498).  With N > 1 the flat gradient is
+    region; the upload of step k + 1 is issued by step k and runs under its kernels: two host batches alternate),
+    losses read back every step (cutorch.synchronize, train.lua:498).  With N > 1 the flat gradient is
     all-reduced through libb2f_comm.so in 11 buckets started from events inside the backward; `allreduce_exposed_ms`
     is the step time minus the same step without the collective."""
     from back2future_b200 import pwc, train, comm as bcomm
@@ -610,17 +611,22 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
     out = {"shape": "%d x 9 x %d x %d per GPU" % (B, H, W)}
     cm = bcomm.Communicator.from_env() if world > 1 else None
     hin = torch.empty(B, 9, H, W).uniform_(-2.1, 2.6).pin_memory()
+    hin2 = hin.clone().pin_memory()
     def timed(net, topt, c):
         tr = train.Trainer(net, topt, comm=c)
+        # every step uploads its own inputs from pinned host memory; the upload of step k + 1 is started inside step k
+        # (train_batch's `prefetch`: double buffering), two host batches alternate
         for _ in range(2):
-            losses = tr.train_batch(hin)
+            losses = tr.train_batch(hin, prefetch=hin2)
+            losses = tr.train_batch(hin2, prefetch=hin)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(steps):
-            losses = tr.train_batch(hin)
+        for k in range(steps):
+            cur_in, nxt = (hin, hin2) if k % 2 == 0 else (hin2, hin)
+            losses = tr.train_batch(cur_in, prefetch=nxt)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / steps
@@ -645,7 +651,9 @@ def time_training(torch, dev, world, rank, dist, B=BATCH, steps=6):
                     "tensor_cores": "decoders (heads included) and stride-1 pyramid layers with >= 64 channels on tcgen05 in "
                                     "forward, input gradient and weight gradient, stride-2 pyramid layers in the input "
                                     "gradient (three-pass TF32 split); the other pyramid work on the FFMA kernels",
-                    "h2d_bytes_per_step": B * 9 * H * W * 4, "loss": round(losses["err"], 4),
+                    "h2d_bytes_per_step": B * 9 * H * W * 4,
+                    "input_upload": "every step from pinned host memory, started inside the previous step (train_batch prefetch)",
+                    "loss": round(losses["err"], 4),
                     "parameters": net.n_params(), "flat_gradient_floats": int(net.flat_params.numel())}
         if world > 1:
             out[key]["step_without_allreduce_ms"] = round(res["local"], 3)

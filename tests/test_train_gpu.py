@@ -424,6 +424,32 @@ def test_train_batch_with_the_tensor_core_forward(kind):
     assert any(not np.array_equal(after[k], params[k]) for k in params)
 
 
+def test_train_batch_prefetch_stages_the_next_inputs():
+    """train_batch(x, prefetch=y) uploads y under this step; the next call takes the staged copy only when it is given
+    that very tensor, and the losses are those of a plain call."""
+    from back2future_b200 import pwc, train
+    rng = np.random.default_rng(5)
+    xa = torch.from_numpy(_smooth((1, 9, 64, 64), rng)).pin_memory()
+    xb = torch.from_numpy(_smooth((1, 9, 64, 64), rng)).pin_memory()
+    xc = torch.from_numpy(_smooth((1, 9, 64, 64), rng)).pin_memory()
+    ref = {}
+    net = pwc.PWCNet(pwc.Opt(), seed=9)
+    tr = train.Trainer(net, train.TrainOpt.hard())
+    for name, x in (("a", xa), ("b", xb), ("c", xc)):
+        ref[name] = tr.train_batch(x, graph=True, step=False)
+    net2 = pwc.PWCNet(pwc.Opt(), seed=9)
+    tr2 = train.Trainer(net2, train.TrainOpt.hard())
+    la = tr2.train_batch(xa, graph=True, step=False, prefetch=xb)
+    lb = tr2.train_batch(xb, graph=True, step=False, prefetch=xa)      # staged copy of xb
+    lc = tr2.train_batch(xc, graph=True, step=False)                   # xa was staged, xc is given: staged copy dropped
+    la2 = tr2.train_batch(xa, graph=True, step=False)
+    for got, want in ((la, ref["a"]), (lb, ref["b"]), (lc, ref["c"]), (la2, ref["a"])):
+        for k in want:
+            assert abs(got[k] - want[k]) <= 1e-5 * max(abs(want[k]), 1e-6), (k, got[k], want[k])
+    with pytest.raises(ValueError):
+        tr2.train_batch(xa, graph=True, step=False, prefetch=xa[:, :3])
+
+
 @pytest.mark.gpu
 def test_data_parallel_step_with_captured_collectives_two_ranks():
     """Two ranks (when the box has two GPUs): the one-graph training step with the bucket all-reduces captured into the
