@@ -31,6 +31,7 @@ ap.add_argument("--W", type=int, default=640)
 ap.add_argument("--past-flow", action="store_true")
 ap.add_argument("--tc", action="store_true", help="tensor-core forward + input gradients (train_planar)")
 ap.add_argument("--no-side", action="store_true", help="weight gradients on the main stream")
+ap.add_argument("--once", action="store_true", help="two eager forward + backward plans and nothing else (for an ncu launch list)")
 ap.add_argument("--detail", action="store_true", help="list every FFMA convolution call of the backward plan")
 a = ap.parse_args()
 lib = _lib.load()
@@ -42,6 +43,12 @@ out = net.forward(x, graph=False)
 net.backward(x, [torch.randn_like(t) for t in out])
 torch.cuda.synchronize()
 p = net.plan(a.B, a.H, a.W)
+if a.once:
+    p.launch()
+    p.launch_backward()
+    torch.cuda.synchronize()
+    print("launches per forward: %d, backward entries: %d" % (p.n_launches, len(p.bops)))
+    sys.exit(0)
 name_of = {id(getattr(lib, n)): n for n in _lib.SIGNATURES}
 st0 = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 fwd = time_it(lambda: p.launch())
