@@ -62,6 +62,8 @@ def test_no_unexpected_exports_and_no_torch_dependency(built):
 def test_struct_layouts_match_header(built):
     assert C.sizeof(built.ObParams) == 11 * 4
     assert C.sizeof(built.SmoothParams) == 6 * 4
+    assert C.sizeof(built.PackJob) == 3 * 8 + 4 * 4          # b2f_pack_job: three pointers, four int32
+    assert built.PackJob.Cout.offset == 24 and built.PackJob.transpose.offset == 36
 
 
 def test_argument_validation_needs_no_gpu(built):
@@ -74,6 +76,8 @@ def test_argument_validation_needs_no_gpu(built):
     prev = lib.b2f_debug_costvol_path(1)
     assert lib.b2f_debug_costvol_path(prev) == 1
     assert lib.b2f_launch_count(1) == 0
+    assert lib.b2f_conv3x3_tc_pack_from_packed_batch(None, 2, None) == -1
+    assert lib.b2f_conv3x3_tc_backward_data_s2(None, None, None, None, None, 0, 1, 32, 4, 4, 16, 8, 8, 0, None) == -1
 
 
 def test_host_mirror_has_reference_surface_and_no_cpu_fallback(built):

@@ -294,3 +294,29 @@ def test_conv3x3_tc_backward_data_stride2(B, Cout, H, W, Cin, acc):
     assert np.abs(got[:, 1:] - ref).max() < TOL * max(np.abs(want).max(), np.abs(ref).max())
     assert lib.b2f_conv3x3_tc_backward_data_s2(_p(gh), _p(gl), _p(th), _p(tl), _p(op), 0, B, Cout, Ho + 1, Wo, Cin, H, W, 0,
                                                _st()) != 0
+
+
+def test_conv3x3_tc_pack_from_packed_batch_matches_the_single_calls():
+    """One launch over a device table of b2f_pack_job entries against the per-tensor entry point, forward and transposed."""
+    from back2future_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    shapes = [(128, 196, 224, 0), (2, 32, 32, 0), (96, 128, 128, 0), (128, 196, 128, 1), (2, 32, 2, 1), (64, 32, 64, 1)]
+    jobs, singles, keep = [], [], []
+    for cout, cin, K, tr in shapes:
+        w = _dev((rng.standard_normal((cout, cin, 3, 3)) * 0.1).astype(np.float32))
+        wp = torch.empty(int(lib.b2f_conv3x3_packed_floats(cin, cout)), device="cuda")
+        _lib.check(lib.b2f_conv3x3_pack_weights(_p(w), _p(wp), cout, cin, 0, _st()))
+        n = 9 * (cin if tr else cout) * ((K + 31) // 32 * 32)
+        a = [torch.full((n,), 7.0, device="cuda") for _ in range(4)]
+        _lib.check(lib.b2f_conv3x3_tc_pack_from_packed(_p(wp), _p(a[0]), _p(a[1]), cout, cin, K, tr, _st()))
+        jobs.append((wp.data_ptr(), a[2].data_ptr(), a[3].data_ptr(), cout, cin, K, tr))
+        singles.append(a)
+        keep += [w, wp]
+    table = torch.frombuffer(bytearray(_lib.pack_jobs(jobs)), dtype=torch.uint8).cuda()
+    _lib.check(lib.b2f_conv3x3_tc_pack_from_packed_batch(_p(table), len(jobs), _st()))
+    torch.cuda.synchronize()
+    for a in singles:
+        assert torch.equal(a[0], a[2]) and torch.equal(a[1], a[3])
+    assert lib.b2f_conv3x3_tc_pack_from_packed_batch(None, 3, _st()) != 0
+    assert lib.b2f_conv3x3_tc_pack_from_packed_batch(None, 0, _st()) == 0
