@@ -419,7 +419,12 @@ extern "C" int b2f_conv3x3_forward(const float* x, int64_t x_batch_stride, const
                       get_encode_fn() != nullptr;
   if (tma_ok) {
     // channel tile: 64 output channels per CTA when that wastes nothing, else 32 (Cout = 96, 32, 16, 2)
+    // ... and 16 for the first pyramid level and the heads (Cout = 16, 2): half of a 32-channel tile's arithmetic
+    // would be padding (two channel warps x four pixel blocks: 32 output rows per CTA, fewer input channels per stage)
     const bool n64 = Cout % 64 == 0 || Cout > 96;
+    if (Cout <= 16)
+      return stride == 1 ? launch_conv<2, 1, 4>(x, xbs, w_packed, CoutP, a, B, Cin, H, W, st)
+                         : launch_conv<2, 2, 2>(x, xbs, w_packed, CoutP, a, B, Cin, H, W, st);
     if (stride == 1)
       return n64 ? launch_conv<8, 1, 8>(x, xbs, w_packed, CoutP, a, B, Cin, H, W, st)
                  : launch_conv<4, 1, 8>(x, xbs, w_packed, CoutP, a, B, Cin, H, W, st);
@@ -520,6 +525,7 @@ extern "C" int b2f_conv3x3_backward_data(const float* gout, int64_t gout_batch_s
     cv3::Args a{nullptr, gin, nullptr, ibs, 0, Cout, Cin, H, W, 1, leaky_slope, act, abs_, accumulate};
     if (!act) a.slope = 1.f;
     const bool n64 = Cin % 64 == 0 || Cin > 96;
+    if (Cin <= 16) return launch_conv<2, 1, 4>(gout, gbs, wt_packed, CinP, a, B, Cout, H, W, st);
     return n64 ? launch_conv<8, 1, 8>(gout, gbs, wt_packed, CinP, a, B, Cout, H, W, st)
                : launch_conv<4, 1, 8>(gout, gbs, wt_packed, CinP, a, B, Cout, H, W, st);
   }

@@ -73,6 +73,8 @@ CONV_CASES = [
     (1, 5, 10, 38, 7, 1),         # W % 4 != 0 -> direct kernel (1216-wide inputs, levels 6 / 7)
     (1, 6, 5, 19, 4, 2),
     (3, 3, 20, 24, 16, 2),
+    (2, 16, 70, 96, 16, 1),       # 16-channel tiles: 32 output rows per CTA, ragged in y (70 = 2 x 32 + 6)
+    (1, 6, 66, 72, 12, 2),        # 16-channel tiles, stride 2, input channels not a multiple of the 2 per stage
 ]
 
 
