@@ -836,8 +836,11 @@ class PWCNet:
                                           self.flat_params.numel(), lr, beta1, beta2, eps, weight_decay, self.adam_t, st))
 
     # ---- execution --------------------------------------------------------------------------------------
-    def plan(self, B, H, W):
-        key = (B, H, W)
+    def plan(self, B, H, W, slot=0):
+        """The plan (buffers + call list) of one input shape.  `slot` > 0: further, independent sets of buffers for the
+        same shape -- two plans replayed on two streams overlap one batch's coarse levels (launches that cannot fill
+        the machine) with the other's fine ones (bench.py `whole_network.device_two_streams`)."""
+        key = (B, H, W) if slot == 0 else (B, H, W, slot)
         if key not in self._plans:
             with torch.cuda.device(self.device):
                 self._plans[key] = self._build(B, H, W)

@@ -473,7 +473,26 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
     ms = timed(lambda: net.run(p), steps)
     out["device"] = {"triplets_per_s": round(world * B / ms * 1e3, 1), "ms_per_step": round(ms, 3),
                      "launches_per_step": p.n_launches, "outputs": "full table incl. the ten warped frames"}
-    del p, net
+    # two plans (two sets of buffers, two graphs) replayed on two streams: one batch's coarse levels -- launches that
+    # cannot fill the machine, chained by the coarse-to-fine dependency -- run under the other batch's fine levels
+    pb = net.plan(B, H_FULL, W_FULL, slot=1)
+    pb.x.copy_(torch.randn(pb.x.shape, device=dev))
+    sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for q, s_ in ((p, sa), (pb, sb)):          # capture each plan's graph
+        with torch.cuda.stream(s_):
+            net.run(q)
+    torch.cuda.synchronize()
+
+    def two():
+        with torch.cuda.stream(sa):
+            net.run(p)
+        with torch.cuda.stream(sb):
+            net.run(pb)
+
+    ms2 = timed(two, steps, (sa, sb)) / 2
+    out["device_two_streams"] = {"triplets_per_s": round(world * B / ms2 * 1e3, 1), "ms_per_batch": round(ms2, 3),
+                                 "what": "two batches of %d in flight: two plans (buffer sets, graphs) on two streams" % B}
+    del p, pb, net
     # the same network with every convolution on the fp32 FMA pipe (the training path's forward)
     net = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=True, tensor_cores=False)
     p = net.plan(B, H_FULL, W_FULL)
@@ -483,46 +502,48 @@ def time_network(torch, dev, world, rank, dist, B=BATCH, steps=10, cpu=True):
     # end to end: flow + occlusion only (computeFlow never reads the warped frames)
     net2 = pwc.PWCNet(pwc.Opt(), device=dev, image_warps=False, tensor_cores=True)
     p2 = net2.plan(B, H_FULL, W_FULL)
+    # two plans on two compute streams (as `device_two_streams`); every step uploads its frames straight into its plan's
+    # input buffer and reads flow + occlusion straight from the plan's outputs
+    plans = [p2, net2.plan(B, H_FULL, W_FULL, slot=1)]
     hin = [torch.randn(B, 9, H_FULL, W_FULL).pin_memory() for _ in range(2)]
-    din = [torch.empty(B, 9, H_FULL, W_FULL, device=dev) for _ in range(2)]
-    dout = [[torch.empty(B, 2, H_FULL, W_FULL, device=dev) for _ in range(2)] for _ in range(2)]
     hout = [[torch.empty(B, 2, H_FULL, W_FULL).pin_memory() for _ in range(2)] for _ in range(2)]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_cmp = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
     ev_cmp, ev_out = [None, None], [None, None]
     state = {"i": 0}
 
     def e2e_step():
         i = state["i"] & 1
         state["i"] += 1
-        cur = torch.cuda.current_stream()
+        q, sc = plans[i], s_cmp[i]
         with torch.cuda.stream(s_in):
             if ev_cmp[i] is not None:
-                s_in.wait_event(ev_cmp[i])             # din[i] was consumed two steps ago
-            din[i].copy_(hin[i], non_blocking=True)
+                s_in.wait_event(ev_cmp[i])             # this plan's previous batch has been computed
+            q.x.copy_(hin[i], non_blocking=True)
             ev_in = torch.cuda.Event()
             ev_in.record()
-        cur.wait_event(ev_in)
-        p2.x.copy_(din[i], non_blocking=True)
-        net2.run(p2)
-        if ev_out[i] is not None:
-            cur.wait_event(ev_out[i])                  # dout[i] has been read back
-        dout[i][0].copy_(p2.output[0], non_blocking=True)
-        dout[i][1].copy_(p2.output[1], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        ev_cmp[i] = ev
+        with torch.cuda.stream(sc):
+            sc.wait_event(ev_in)
+            if ev_out[i] is not None:
+                sc.wait_event(ev_out[i])               # ... and its results have been read back
+            net2.run(q)
+            ev = torch.cuda.Event()
+            ev.record()
+            ev_cmp[i] = ev
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev)
-            hout[i][0].copy_(dout[i][0], non_blocking=True)
-            hout[i][1].copy_(dout[i][1], non_blocking=True)
+            hout[i][0].copy_(q.output[0], non_blocking=True)
+            hout[i][1].copy_(q.output[1], non_blocking=True)
             eo = torch.cuda.Event()
             eo.record()
             ev_out[i] = eo
 
-    ems = timed(e2e_step, steps, (s_in, s_out))
+    ems = timed(e2e_step, steps, (s_in, s_out, s_cmp[0], s_cmp[1]))
     out["e2e"] = {"triplets_per_s": round(world * B / ems * 1e3, 1), "ms_per_step": round(ems, 3),
                   "h2d_bytes_per_step": B * 9 * H_FULL * W_FULL * 4, "d2h_bytes_per_step": 2 * B * 2 * H_FULL * W_FULL * 4,
-                  "api": "back2future_b200.pwc.PWCNet.run on host frames (the device half of computeFlow)"}
+                  "api": "back2future_b200.pwc.PWCNet.run on host frames (the device half of computeFlow), two batches in "
+                         "flight (two plans on two streams)"}
+    din = dout = None
     del net, p, hin, din, dout, hout
     if rank == 0:
         # the dominant kernel of the whole-network forward against the tensor-core roofline: one level-3 decoder layer
