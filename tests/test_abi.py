@@ -66,6 +66,16 @@ def test_struct_layouts_match_header(built):
     assert built.PackJob.Cout.offset == 24 and built.PackJob.transpose.offset == 36
 
 
+def test_pack_job_table_bytes(built):
+    """_lib.pack_jobs lays the b2f_pack_job array out as the header declares it (the table is uploaded as raw bytes)."""
+    raw = built.pack_jobs([(0x1000, 0x2000, 0x3000, 128, 196, 224, 0), (0x10, 0x20, 0x30, 2, 32, 2, 1)])
+    assert len(raw) == 2 * 40
+    jobs = (built.PackJob * 2).from_buffer_copy(raw)
+    assert (jobs[0].w_packed, jobs[0].w_hi, jobs[0].w_lo) == (0x1000, 0x2000, 0x3000)
+    assert (jobs[0].Cout, jobs[0].Cin, jobs[0].K, jobs[0].transpose) == (128, 196, 224, 0)
+    assert (jobs[1].Cout, jobs[1].Cin, jobs[1].K, jobs[1].transpose) == (2, 32, 2, 1)
+
+
 def test_argument_validation_needs_no_gpu(built):
     """Rejected arguments are reported before any CUDA call."""
     lib = built.load()
