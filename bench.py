@@ -896,95 +896,112 @@ class _NumaLocal:
 class E2E:
     """The same pass through back2future_b200.nn with pinned HOST inputs and outputs.
 
-    Every step copies every input from pinned host memory and reads every result back.  Copies and
-    kernels are pipelined over three streams (H2D / compute / D2H) with per-item events, the way a
-    caller streaming triplets through the reference's modules would overlap its data movement; device
-    staging buffers are allocated once."""
+    Every step copies every input from pinned host memory and reads every result back.  The tensors of a step live
+    back to back in ONE pinned input arena and ONE pinned output arena, so a step is one H2D copy (0.88 GB), the module
+    calls, and one D2H copy (0.93 GB) -- 153 separate copies of 7 KB .. 100 MB reached 39 + 41 GB/s, the link does
+    46.7 GB/s per direction with both directions busy.  Copies and kernels are pipelined over three streams (H2D /
+    compute / D2H) and two sets of device arenas, the way a caller streaming triplets through the reference's modules
+    would overlap its data movement: step k + 1 uploads while step k computes and step k - 1 downloads."""
 
     def __init__(self, torch, dev, B=BATCH, seed=2):
         from back2future_b200 import nn as bnn
         self.torch, self.dev, self.B = torch, dev, B
         g = torch.Generator().manual_seed(seed)
-        self.items = []
-        self.h2d = self.d2h = 0
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-
-        def pin(*shape, scale=1.0):
-            t = torch.randn(shape, generator=g, dtype=torch.float32) * scale
-            return t.pin_memory()
-
-        def pin_out(*shape):
-            return torch.empty(shape, dtype=torch.float32).pin_memory()
-
-        def dev_like(ts):
-            return [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in ts]
-
-        with _NumaLocal(torch, dev) as numa:
-            self.numa_cpus = numa.bound
-            self._alloc(bnn, B, pin, pin_out, dev_like)
-        for it in self.items:
-            self.h2d += sum(t.numel() * 4 for t in it[2])
-            self.d2h += sum(t.numel() * 4 for t in it[3])
-        self.ev_cmp = [None] * len(self.items)
-        self.ev_out = [None] * len(self.items)
-
-    def _alloc(self, bnn, B, pin, pin_out, dev_like):
-        torch, dev = self.torch, self.dev
+        # (kind, module(s), input shapes (+ scale), output shapes)
+        spec = []
         for l in (7, 6, 5, 4, 3):
             Cn = LEVEL_C[l]
             h, w = level_hw(l)
-            hin = [pin(B, Cn, h, w) for _ in range(3)] + [pin(B, 162, h, w)]
-            hout = [pin_out(B, 162, h, w)] + [pin_out(B, Cn, h, w) for _ in range(4)]
-            self.items.append(["cv", (bnn.CostVolMulti(9, True), bnn.CostVolMulti(9, False)), hin, hout,
-                               dev_like(hin), torch.empty((B, 162, h, w), device=dev)])
+            spec.append(("cv", (bnn.CostVolMulti(9, True), bnn.CostVolMulti(9, False)),
+                         [((B, Cn, h, w), 1.0)] * 3 + [((B, 162, h, w), 1.0)],
+                         [(B, 162, h, w)] + [(B, Cn, h, w)] * 4))
         cfgs = [(LEVEL_C[l], level_hw(l)) for l in (6, 5, 4, 3)] + [(3, (H_FULL >> k, W_FULL >> k)) for k in (4, 3, 2, 1, 0)]
         for Cn, (h, w) in cfgs:
             for _ in range(2):
-                hin = [pin(B, h, w, Cn), pin(B, h, w, 2, scale=4.0), pin(B, h, w, Cn)]
-                hout = [pin_out(B, h, w, Cn), pin_out(B, h, w, Cn), pin_out(B, h, w, 2)]
-                self.items.append(["warp", bnn.BilinearSamplerBHWD(), hin, hout, dev_like(hin), None])
+                spec.append(("warp", bnn.BilinearSamplerBHWD(),
+                             [((B, h, w, Cn), 1.0), ((B, h, w, 2), 4.0), ((B, h, w, Cn), 1.0)],
+                             [(B, h, w, Cn), (B, h, w, Cn), (B, h, w, 2)]))
+        def numel(shp):
+            n = 1
+            for v in shp:
+                n *= int(v)
+            return n
+
+        n_in = sum(numel(shp) for _k, _m, ins, _o in spec for shp, _sc in ins)
+        n_out = sum(numel(shp) for _k, _m, _i, outs in spec for shp in outs)
+        self.h2d, self.d2h = 4 * n_in, 4 * n_out
+        with _NumaLocal(torch, dev) as numa:
+            self.numa_cpus = numa.bound
+            self.h_in = torch.empty(n_in, dtype=torch.float32).pin_memory()
+            self.h_out = torch.empty(n_out, dtype=torch.float32).pin_memory()
+        self.d_in = [torch.empty(n_in, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.d_out = [torch.empty(n_out, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.items = []
+        oi = oo = 0
+        for kind, mod, ins, outs in spec:
+            vin = [[], []]
+            for shp, sc in ins:
+                n = numel(shp)
+                self.h_in[oi:oi + n].copy_((torch.randn(shp, generator=g, dtype=torch.float32) * sc).reshape(-1))
+                for s_ in range(2):
+                    vin[s_].append(self.d_in[s_][oi:oi + n].view(shp))
+                oi += n
+            vout = [[], []]
+            for shp in outs:
+                n = numel(shp)
+                for s_ in range(2):
+                    vout[s_].append(self.d_out[s_][oo:oo + n].view(shp))
+                oo += n
+            self.items.append((kind, mod, vin, vout))
+        self.ev_cmp = [None, None]
+        self.ev_out = [None, None]
+        self.k = 0
 
     def step(self):
-        """One pass.  Nothing here waits for the host: the three streams are ordered by per-item events only
-        (inputs of item i are not overwritten before the previous step's kernels on item i have run; its
-        device results are not overwritten before the previous step's read-back of item i has finished), so
-        consecutive steps overlap the way a caller streaming triplets through the modules would run them.
-        `drain()` ends the timed region."""
+        """One pass.  Nothing here waits for the host: the three streams are ordered by events only (the input arena of
+        a slot is not overwritten before the kernels of the step that used it two steps ago have run; its output arena
+        not before that step's read-back has finished).  `drain()` ends the timed region."""
         torch = self.torch
-        for i, (kind, mod, hin, hout, din, joined) in enumerate(self.items):
-            with torch.cuda.stream(self.s_in):
-                if self.ev_cmp[i] is not None:
-                    self.s_in.wait_event(self.ev_cmp[i])
-                for d, h in zip(din, hin):
-                    d.copy_(h, non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record()
-            with torch.cuda.stream(self.s_cmp):
-                self.s_cmp.wait_event(ev_in)
-                if self.ev_out[i] is not None:
-                    self.s_cmp.wait_event(self.ev_out[i])
+        slot = self.k & 1
+        self.k += 1
+        with torch.cuda.stream(self.s_in):
+            if self.ev_cmp[slot] is not None:
+                self.s_in.wait_event(self.ev_cmp[slot])
+            self.d_in[slot].copy_(self.h_in, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record()
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(ev_in)
+            if self.ev_out[slot] is not None:
+                self.s_cmp.wait_event(self.ev_out[slot])
+            for kind, mod, vin, vout in self.items:
+                din, dout = vin[slot], vout[slot]
                 if kind == "cv":
                     ref, past, fut, gj = din
+                    joined = dout[0]
                     mod[0].updateOutput([ref, fut], out=joined[:, :81])
                     mod[1].updateOutput([ref, past], out=joined[:, 81:])
                     gf = mod[0].updateGradInput([ref, fut], gj[:, :81])
                     gp = mod[1].updateGradInput([ref, past], gj[:, 81:])
-                    douts = [joined, gf[0], gf[1], gp[0], gp[1]]
+                    res = [None, gf[0], gf[1], gp[0], gp[1]]
                 else:
                     img, grid, go = din
                     out = mod.updateOutput([img, grid])
                     gi, gg = mod.updateGradInput([img, grid], go)
-                    douts = [out, gi, gg]
-                ev_cmp = torch.cuda.Event()
-                ev_cmp.record()
-                self.ev_cmp[i] = ev_cmp
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_cmp)
-                for h, d in zip(hout, douts):
-                    h.copy_(d, non_blocking=True)
-                ev_out = torch.cuda.Event()
-                ev_out.record()
-                self.ev_out[i] = ev_out
+                    res = [out, gi, gg]
+                for dst, src in zip(dout, res):
+                    if src is not None:
+                        dst.copy_(src, non_blocking=True)       # module-owned result -> output arena (device to device)
+            ev_cmp = torch.cuda.Event()
+            ev_cmp.record()
+            self.ev_cmp[slot] = ev_cmp
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_cmp)
+            self.h_out.copy_(self.d_out[slot], non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record()
+            self.ev_out[slot] = ev_out
 
     def drain(self):
         self.s_out.synchronize()
@@ -1310,6 +1327,8 @@ def main():
                "h2d_bytes_per_step": ee.h2d, "d2h_bytes_per_step": ee.d2h, "steps": args.e2e_steps,
                "ms_per_step": round(ems / args.e2e_steps, 3),
                "api": "back2future_b200.nn.CostVolMulti / BilinearSamplerBHWD updateOutput+updateGradInput",
+               "copies": "one pinned input arena up and one output arena down per step (every input and every result), "
+                         "three streams, two sets of device arenas",
                # CPUs this rank was bound to while it allocated its pinned buffers (GPU-local NUMA node), 0 = not bound
                "pinned_alloc_numa_cpus": ee.numa_cpus}
         del ee

@@ -59,3 +59,54 @@ def test_wrong_results_are_caught(cuda_lib):
         cuda_lib.b2f_debug_costvol_path(prev)
     r = workload_check.check_workload(wl)
     assert r["failed"] and all(n.startswith("costvol") for n in r["failed"])
+
+
+def test_e2e_leg_returns_the_modules_results(cuda_lib):
+    """bench.py's end-to-end leg (one pinned input arena up, module calls on views of the device arena, one output arena
+    down; two sets of device arenas): what arrives in the host output arena after several pipelined steps is what the
+    float64 checker computes from the host input arena -- first cost-volume item, first feature warp, last image warp."""
+    import numpy as np
+    import torch
+    import bench
+    from oracle import check64 as c64
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(0)
+    ee = bench.E2E(torch, dev, B=1)
+    ee.h_out.fill_(float("nan"))
+    for _ in range(3):                # both arena slots, and a slot reused
+        ee.step()
+    ee.drain()
+    torch.cuda.synchronize()
+    hin, hout = ee.h_in.numpy(), ee.h_out.numpy()
+
+    def numel(t):
+        return int(np.prod(t.shape))
+
+    oi = oo = 0
+    checked = 0
+    for idx, (kind, _mod, vin, vout) in enumerate(ee.items):
+        ins, outs = [], []
+        for v in vin[0]:
+            ins.append(hin[oi:oi + numel(v)].reshape(tuple(v.shape)))
+            oi += numel(v)
+        for v in vout[0]:
+            outs.append(hout[oo:oo + numel(v)].reshape(tuple(v.shape)))
+            oo += numel(v)
+        assert all(np.isfinite(o_).all() for o_ in outs), (idx, kind)
+        if kind == "cv" and idx == 0:
+            ref, past, fut, gj = ins
+            want = np.concatenate([c64.costvol_forward([ref, fut], 9, True), c64.costvol_forward([ref, past], 9, False)], 1)
+            assert c64.rel_err(outs[0], want) < 1e-4
+            g = c64.costvol_backward([ref, fut], gj[:, :81], 9, True)
+            assert c64.rel_err(outs[1], g[0]) < 1e-4 and c64.rel_err(outs[2], g[1]) < 1e-4
+            g = c64.costvol_backward([ref, past], gj[:, 81:], 9, False)
+            assert c64.rel_err(outs[3], g[0]) < 1e-4 and c64.rel_err(outs[4], g[1]) < 1e-4
+            checked += 1
+        if kind == "warp" and (idx == 5 or idx == len(ee.items) - 1):
+            img, grid, go = ins
+            assert c64.rel_err(outs[0], c64.warp_forward(img, grid)) < 1e-4
+            gi, gg = c64.warp_backward(img, grid, go)
+            assert c64.rel_err(outs[1], gi) < 1e-4 and c64.rel_err(outs[2], gg) < 1e-4
+            checked += 1
+    assert checked == 3 and oi == ee.h_in.numel() and oo == ee.h_out.numel()
