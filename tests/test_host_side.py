@@ -103,3 +103,101 @@ def test_model_export_import(tmp_path, past_flow):
         assert np.array_equal(got[k], params[k]), k
     with pytest.raises(ValueError):
         t7.import_model(t7.TorchObject("nn.Sequential", {}))
+
+
+def test_backward_plan_lanes_order_their_dependencies(monkeypatch):
+    """pwc._Plan.launch_backward without a GPU: fake streams / events record who waits for what.  A weight gradient
+    (lane 1) waits for the lane that produced its operands at that point of the plan; a flow decoder's chain (lane 2)
+    starts behind the main stream and its accumulating last call behind the occlusion decoder's write; the first call
+    that reads the joined gradient waits for the chains; everything is joined at the end of a slice unless join=False,
+    in which case `backward_streams()` names the streams a collective has to wait for."""
+    import ctypes as C
+    from back2future_b200 import pwc
+
+    log = []
+
+    class FakeStream:
+        n = 0
+
+        def __init__(self):
+            FakeStream.n += 1
+            self.cuda_stream = 1000 + FakeStream.n
+            self.issued = 0                       # work items issued so far (what an event recorded now covers)
+
+        def wait_event(self, ev):
+            log.append(("wait", self.cuda_stream, ev.stream.cuda_stream, ev.mark))
+
+        def wait_stream(self, other):
+            log.append(("join", self.cuda_stream, other.cuda_stream, other.issued))
+
+    class FakeEvent:
+        def record(self, stream):
+            self.stream, self.mark = stream, stream.issued
+
+    main = FakeStream()
+    monkeypatch.setattr(pwc.torch.cuda, "current_stream", lambda *a, **k: main)
+    monkeypatch.setattr(pwc.torch.cuda, "Stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(pwc.torch.cuda, "Event", lambda *a, **k: FakeEvent())
+    by_handle = {}
+
+    def op(name):
+        def fn(stream_handle):
+            s = by_handle[stream_handle.value]
+            s.issued += 1
+            log.append(("run", name, s.cuda_stream))
+            return 0
+        return fn
+
+    p = pwc._Plan(1, 64, 64)
+    p.bops = [
+        (op("g_fs"), ()),                              # main: produces the flow decoder's output gradient
+        (op("flow.split"), (), 2, (0,)),               # flow chain starts behind it
+        (op("flow.wgrad5"), (), 1, (2,)),              # its weight gradient: behind the chain, on lane 1
+        (op("flow.dgrad5"), (), 2),
+        (op("occ.dgrad0 (write)"), ()),                # occlusion decoder on the main stream
+        (op("occ.wgrad0"), (), 1),                     # default dependency: the main stream
+        (op("flow.dgrad0 (add)"), (), 2, (0,)),        # behind the occlusion decoder's write
+        (op("costvol_bwd"), (), 0, (2, 3)),            # reads the joined gradient: behind the chains (lane 3 unused)
+    ]
+    # the executor creates its side streams on first use; register them for the fake launch functions
+    p.launch_backward(0, 0)
+    by_handle[main.cuda_stream] = main
+    for s in p._blanes.values():
+        by_handle[s.cuda_stream] = s
+    lane = {k: s.cuda_stream for k, s in p._blanes.items()}
+    lane[0] = main.cuda_stream
+    log.clear()
+    p.launch_backward(join=False)
+    runs = [e for e in log if e[0] == "run"]
+    assert [(n, s) for _r, n, s in runs] == [
+        ("g_fs", lane[0]), ("flow.split", lane[2]), ("flow.wgrad5", lane[1]), ("flow.dgrad5", lane[2]),
+        ("occ.dgrad0 (write)", lane[0]), ("occ.wgrad0", lane[1]), ("flow.dgrad0 (add)", lane[2]), ("costvol_bwd", lane[0])]
+
+    def waits_before(name):
+        i = log.index(next(e for e in log if e[0] == "run" and e[1] == name))
+        out = []
+        while i > 0 and log[i - 1][0] == "wait":
+            i -= 1
+            out.append(log[i][1:])
+        return out
+
+    assert waits_before("flow.split") == [(lane[2], lane[0], 1)]              # behind g_fs
+    assert waits_before("flow.wgrad5") == [(lane[1], lane[2], 1)]             # behind flow.split
+    assert waits_before("flow.dgrad5") == []                                  # a lane is ordered in itself
+    assert waits_before("occ.wgrad0") == [(lane[1], lane[0], 2)]              # behind occ.dgrad0
+    assert waits_before("flow.dgrad0 (add)") == [(lane[2], lane[0], 2)]       # behind the occlusion decoder's write
+    assert waits_before("costvol_bwd") == [(lane[0], lane[2], 3)]             # lane 3 carries nothing: no wait on it
+    assert not [e for e in log if e[0] == "join"]
+    assert [s.cuda_stream for s in p.backward_streams()] == [lane[1], lane[2]]
+    # the next slice joins what is still in flight
+    p.bops = [(op("adam"), ())]
+    log.clear()
+    p.launch_backward(lo=1, hi=1, join=True)          # lo > 0: a later slice of the same plan run
+    assert sorted(e[2] for e in log if e[0] == "join") == sorted([lane[1], lane[2]])
+    assert p.backward_streams() == []
+    # one stream only: same order, no waits
+    monkeypatch.setattr(pwc, "SIDE_LANES", False)
+    p.bops = [(op("a"), (), 1, (2,)), (op("b"), (), 2, (0,))]
+    log.clear()
+    p.launch_backward()
+    assert log == [("run", "a", lane[0]), ("run", "b", lane[0])]
